@@ -1,0 +1,102 @@
+/*
+ * l4p_b200 — C ABI of the Blackwell-native (sm_100a) L4P inference hot path.
+ *
+ * The reference (NVlabs/L4P, pure Python/PyTorch) has no FFI layer: every "kernel" is an ATen
+ * library call made from an nn.Module.forward. This header is therefore the boundary
+ * a maintainer binds with ctypes/cffi from the module that used to make the ATen call; each entry
+ * point cites the reference call site it replaces (paths relative to the reference repo root).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - "16-bit" tensors are fp16 or bf16 as selected by `bf16` (0 = fp16, 1 = bf16); accumulation,
+ *     residual stream, LayerNorm/softmax statistics are always fp32;
+ *   - sizes are int64_t / int, streams are passed as void* (cudaStream_t);
+ *   - functions return 0 on success, <0 on error (L4P_ERR_*), never exit/throw; the message for the
+ *     last error on the calling thread is l4p_last_error();
+ *   - kernels never allocate: callers own all buffers (workspace sizes via *_workspace_bytes()).
+ */
+#ifndef L4P_B200_H_
+#define L4P_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define L4P_OK 0
+#define L4P_ERR_ARG (-1)
+#define L4P_ERR_SHAPE (-2)
+#define L4P_ERR_ARCH (-3)
+#define L4P_ERR_CUDA (-4)
+#define L4P_ERR_DRIVER (-5)
+
+/* ---- library ------------------------------------------------------------------------------- */
+int l4p_version(void);
+const char* l4p_last_error(void);
+/* Select `device`, verify it is compute capability 10.x when arch_check != 0.
+ * Replaces the implicit device placement of Fabric.setup (l4p/models/utils.py:57-58). */
+int l4p_init(int device, int arch_check);
+
+/* ---- K2: LayerNorm ------------------------------------------------------------------------- */
+/* y16[r, :] = (x[r, :] - mean) * rstd * gamma + beta, biased variance, fp32 statistics.
+ * Replaces Block.norm1/norm2 (l4p/models/VideoMAEv2/models/modeling_finetune.py:247-248), the final
+ * encoder norm (l4p/models/l4p_videomae.py:115) and the SAM LayerNorms (task_heads/sam/transformer.py:139-149).
+ * x fp32 [rows, cols]; y16 16-bit and/or y32 fp32 outputs (either may be NULL). */
+int l4p_layernorm(const float* x, const float* gamma, const float* beta, void* y16, float* y32,
+                  int64_t rows, int cols, float eps, int bf16, void* stream);
+
+/* ---- K3/K5/K6/K7/K8: tcgen05 GEMM / implicit-GEMM convolution ---------------------------------- */
+enum { L4P_ACT_NONE = 0, L4P_ACT_GELU = 1, L4P_ACT_RELU = 2, L4P_ACT_EXP = 3 };
+enum {
+  L4P_STORE_ROWMAJOR = 0, /* out[row, col]                                                        */
+  L4P_STORE_QKV = 1,      /* scatter to Q[B,H,N,dpad], K[B,H,N,dpad], Vt[B,H,dpad,N]                */
+  L4P_STORE_CONVT = 2,    /* ConvTranspose3d(k == s) pixel-shuffle scatter to channels-last         */
+  L4P_STORE_HEAD1X1 = 3   /* ReLU -> 1x1x1 conv to <= 8 channels (+exp) -> fp32 NCTHW              */
+};
+enum { L4P_A_MATRIX = 0, L4P_A_CONV3D = 1 };
+
+typedef struct l4p_gemm_desc {
+  /* D[M,N] = A[M,K] * W[N,K]^T ; A and W 16-bit, K contiguous (nn.Linear weight layout). */
+  const void* a;       /* A_MATRIX: [M, lda] ; A_CONV3D: channels-last activations [B,T,H,W,Cin]   */
+  const void* w;       /* [N, ldw]; for A_CONV3D the K axis is (tap_t, tap_h, tap_w, Cin)           */
+  int64_t M, N, K;     /* A_CONV3D: M = B*T*H*W output voxels, K = taps*Cin                        */
+  int64_t lda, ldw;    /* row strides in elements (multiples of 8)                                 */
+  int bf16;            /* operand type                                                             */
+  int a_mode;          /* L4P_A_*                                                                  */
+  /* A_CONV3D geometry (stride 1, zero padding k/2): */
+  int cB, cT, cH, cW, cCin;
+  int kT, kH, kW;      /* filter extent (odd)                                                      */
+  int bT, bH, bW;      /* voxel box of one 128-row tile, bT*bH*bW == 128                           */
+  /* epilogue */
+  const float* bias;   /* [N] fp32 or NULL                                                         */
+  int act;             /* L4P_ACT_* applied after bias                                             */
+  const float* res_f32;   /* optional residual, same indexing as out_f32                           */
+  const void* res_16;     /* optional 16-bit residual, same indexing as out_16 (row-major)         */
+  const void* res2_16;    /* optional second 16-bit residual                                       */
+  int64_t ld_res;
+  int store_mode;      /* L4P_STORE_*                                                              */
+  float* out_f32;      /* ROWMAJOR: optional fp32 output [M, ld_out]                               */
+  void* out_16;        /* ROWMAJOR/CONVT: 16-bit output                                            */
+  void* out_16_relu;   /* ROWMAJOR: optional second 16-bit output = relu(out)                      */
+  int64_t ld_out;
+  /* STORE_QKV: N = 3*heads*head_dim, rows = (b, token) */
+  void* q; void* k; void* vt;
+  int heads, head_dim, head_dim_pad, tokens;
+  /* STORE_CONVT: rows are input voxels (b,t,h,w) of a [cB,cT,cH,cW] grid, N = sT*sH*sW*Cout ordered
+   * (kt,kh,kw,co); out_16 is channels-last [B, T*sT, H*sH, W*sW, Cout] */
+  int sT, sH, sW, ctCout;
+  /* STORE_HEAD1X1: out_f32[b, c, t, h, w] = f(sum_n relu(acc+bias)[n] * w2[c, n] + b2[c]) */
+  const float* w2; const float* b2; int c2; int exp_out;
+  int block_n;         /* N tile (multiple of 16, <= 256); 0 = choose                              */
+} l4p_gemm_desc;
+
+/* Replaces F.linear/addmm (modeling_finetune.py:62-69,171-177,188), the 1x1x1/3x3x3 Conv3d and k==s
+ * ConvTranspose3d calls of the DPT heads (task_heads/dpt/croco/dpt_block.py:29-90,144-157,255-278,406-414)
+ * and the SAM projections (task_heads/sam/transformer.py:223-245). */
+int l4p_gemm(const l4p_gemm_desc* desc, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* L4P_B200_H_ */

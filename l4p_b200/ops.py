@@ -1,0 +1,197 @@
+"""Thin torch-facing wrappers over the C ABI: torch only supplies device memory and the current stream.
+
+Every function validates its tensors (CUDA, contiguous, dtype) and raises on any library error;
+nothing here computes on the CPU or falls back to ATen.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import lib as _l
+
+_initialised = set()
+
+
+def _dev_init(t: torch.Tensor) -> None:
+    if not t.is_cuda:
+        raise _l.L4PError("l4p_b200 ops need CUDA tensors (no CPU fallback exists for this path)")
+    idx = t.device.index if t.device.index is not None else torch.cuda.current_device()
+    if idx not in _initialised:
+        _l.check(_l.load().l4p_init(idx, 1), "l4p_init")
+        _initialised.add(idx)
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _is16(t: torch.Tensor) -> bool:
+    return t.dtype in (torch.float16, torch.bfloat16)
+
+
+def _chk(t: Optional[torch.Tensor], name: str, dtype=None, sixteen=False) -> None:
+    if t is None:
+        return
+    if not t.is_cuda or not t.is_contiguous():
+        raise _l.L4PError(f"{name}: expected a contiguous CUDA tensor")
+    if dtype is not None and t.dtype != dtype:
+        raise _l.L4PError(f"{name}: expected {dtype}, got {t.dtype}")
+    if sixteen and not _is16(t):
+        raise _l.L4PError(f"{name}: expected fp16/bf16, got {t.dtype}")
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float,
+              out16: Optional[torch.Tensor] = None, out32: Optional[torch.Tensor] = None) -> None:
+    """K2. x fp32 [..., C] -> out16 (fp16/bf16) and/or out32."""
+    _dev_init(x)
+    _chk(x, "x", torch.float32); _chk(gamma, "gamma", torch.float32); _chk(beta, "beta", torch.float32)
+    _chk(out16, "out16", sixteen=True); _chk(out32, "out32", torch.float32)
+    cols = x.shape[-1]
+    rows = x.numel() // cols
+    bf16 = 1 if (out16 is not None and out16.dtype == torch.bfloat16) else 0
+    _l.check(_l.load().l4p_layernorm(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(out16), _ptr(out32), rows, cols,
+                                     float(eps), bf16, _stream()), "l4p_layernorm")
+
+
+def _base_desc(a: torch.Tensor, w: torch.Tensor) -> _l.GemmDesc:
+    _dev_init(a)
+    _chk(a, "a", sixteen=True); _chk(w, "w", sixteen=True)
+    if a.dtype != w.dtype:
+        raise _l.L4PError(f"operand dtypes differ: {a.dtype} vs {w.dtype}")
+    d = _l.GemmDesc()
+    d.a = a.data_ptr(); d.w = w.data_ptr()
+    d.bf16 = 1 if a.dtype == torch.bfloat16 else 0
+    return d
+
+
+def _epilogue(d: _l.GemmDesc, *, bias=None, act=_l.ACT_NONE, res_f32=None, res_16=None, res2_16=None,
+              out_f32=None, out_16=None, out_16_relu=None) -> None:
+    _chk(bias, "bias", torch.float32); _chk(res_f32, "res_f32", torch.float32)
+    _chk(res_16, "res_16", sixteen=True); _chk(res2_16, "res2_16", sixteen=True)
+    _chk(out_f32, "out_f32", torch.float32); _chk(out_16, "out_16", sixteen=True)
+    _chk(out_16_relu, "out_16_relu", sixteen=True)
+    d.bias = _ptr(bias); d.act = act
+    d.res_f32 = _ptr(res_f32); d.res_16 = _ptr(res_16); d.res2_16 = _ptr(res2_16)
+    d.out_f32 = _ptr(out_f32); d.out_16 = _ptr(out_16); d.out_16_relu = _ptr(out_16_relu)
+    d.ld_res = d.N; d.ld_out = d.N
+
+
+def linear(a: torch.Tensor, w: torch.Tensor, *, bias=None, act=_l.ACT_NONE, res_f32=None, res_16=None,
+           out_f32=None, out_16=None, out_16_relu=None, block_n: int = 0) -> None:
+    """out[M,N] = act(a[M,K] @ w[N,K]^T + bias) (+ residual). Replaces F.linear/addmm call sites."""
+    d = _base_desc(a, w)
+    K = a.shape[-1]
+    M = a.numel() // K
+    N = w.shape[0]
+    if w.shape[1] != K:
+        raise _l.L4PError(f"linear: K mismatch {w.shape} vs {a.shape}")
+    d.M, d.N, d.K = M, N, K
+    d.lda, d.ldw = K, K
+    d.a_mode = _l.A_MATRIX
+    d.store_mode = _l.STORE_ROWMAJOR
+    d.block_n = block_n
+    _epilogue(d, bias=bias, act=act, res_f32=res_f32, res_16=res_16, out_f32=out_f32, out_16=out_16,
+              out_16_relu=out_16_relu)
+    _l.check(_l.load().l4p_gemm(C.byref(d), _stream()), "l4p_gemm(linear)")
+
+
+def linear_qkv(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, q: torch.Tensor, k: torch.Tensor,
+               vt: torch.Tensor, heads: int, head_dim: int, tokens: int, block_n: int = 0) -> None:
+    """K3: qkv projection with the attention layout fused into the epilogue.
+
+    a [B*tokens, C]; w [3*heads*head_dim, C]; q,k [B,heads,tokens,dpad]; vt [B,heads,dpad,tokens]
+    (pad lanes are never written: allocate them zero-filled once)."""
+    d = _base_desc(a, w)
+    K = a.shape[-1]
+    d.M, d.N, d.K = a.numel() // K, w.shape[0], K
+    d.lda, d.ldw = K, K
+    d.a_mode = _l.A_MATRIX
+    d.store_mode = _l.STORE_QKV
+    _chk(bias, "bias", torch.float32)
+    for n, t in (("q", q), ("k", k), ("vt", vt)):
+        _chk(t, n, sixteen=True)
+        if t.dtype != a.dtype:
+            raise _l.L4PError(f"{n}: dtype {t.dtype} != operand dtype {a.dtype}")
+    d.bias = _ptr(bias)
+    d.q, d.k, d.vt = q.data_ptr(), k.data_ptr(), vt.data_ptr()
+    d.heads, d.head_dim, d.head_dim_pad, d.tokens = heads, head_dim, q.shape[-1], tokens
+    d.block_n = block_n
+    _l.check(_l.load().l4p_gemm(C.byref(d), _stream()), "l4p_gemm(qkv)")
+
+
+def pick_box(T: int, H: int, W: int) -> Tuple[int, int, int]:
+    """(bT,bH,bW) voxel box with 128 voxels that tiles [T,H,W] with the least padding."""
+    best = None
+    for bw in (128, 64, 32, 16, 8, 4, 2, 1):
+        for bh in (128, 64, 32, 16, 8, 4, 2, 1):
+            if bw * bh > 128 or 128 % (bw * bh):
+                continue
+            bt = 128 // (bw * bh)
+            waste = (-(-T // bt) * bt) * (-(-H // bh) * bh) * (-(-W // bw) * bw)
+            key = (waste, -bw, -bh)
+            if best is None or key < best[0]:
+                best = (key, (bt, bh, bw))
+    return best[1]
+
+
+def conv3d(x: torch.Tensor, w: torch.Tensor, *, ksize: Tuple[int, int, int], bias=None, act=_l.ACT_NONE,
+           res_16=None, res2_16=None, out_16=None, out_16_relu=None, out_f32=None,
+           head_w2=None, head_b2=None, head_exp=False, block_n: int = 0) -> None:
+    """K8: stride-1 'same' Conv3d as implicit GEMM.
+
+    x channels-last [B,T,H,W,Cin] (16-bit); w [Cout, kT*kH*kW*Cin] with the K axis ordered (kt,kh,kw,cin).
+    With head_w2/head_b2 the epilogue is ReLU -> 1x1x1 conv (+exp) -> out_f32 [B,C2,T,H,W]."""
+    d = _base_desc(x, w)
+    B, T, H, W, Cin = x.shape
+    kT, kH, kW = ksize
+    Cout = w.shape[0]
+    if w.shape[1] != kT * kH * kW * Cin:
+        raise _l.L4PError(f"conv3d: weight {tuple(w.shape)} vs taps*Cin={kT * kH * kW * Cin}")
+    d.M, d.N, d.K = B * T * H * W, Cout, kT * kH * kW * Cin
+    d.lda, d.ldw = Cin, w.shape[1]
+    d.a_mode = _l.A_CONV3D
+    d.cB, d.cT, d.cH, d.cW, d.cCin = B, T, H, W, Cin
+    d.kT, d.kH, d.kW = kT, kH, kW
+    d.bT, d.bH, d.bW = pick_box(T, H, W)
+    d.block_n = block_n
+    if head_w2 is not None:
+        _chk(head_w2, "head_w2", torch.float32); _chk(head_b2, "head_b2", torch.float32)
+        _chk(out_f32, "out_f32", torch.float32); _chk(bias, "bias", torch.float32)
+        d.store_mode = _l.STORE_HEAD1X1
+        d.bias = _ptr(bias); d.act = _l.ACT_RELU
+        d.w2, d.b2, d.c2, d.exp_out = head_w2.data_ptr(), head_b2.data_ptr(), head_w2.shape[0], int(head_exp)
+        d.out_f32 = out_f32.data_ptr()
+    else:
+        d.store_mode = _l.STORE_ROWMAJOR
+        _epilogue(d, bias=bias, act=act, res_16=res_16, res2_16=res2_16, out_f32=out_f32, out_16=out_16,
+                  out_16_relu=out_16_relu)
+    _l.check(_l.load().l4p_gemm(C.byref(d), _stream()), "l4p_gemm(conv3d)")
+
+
+def conv_transpose3d(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, stride: Tuple[int, int, int],
+                     out_16: torch.Tensor, block_n: int = 0) -> None:
+    """K7: ConvTranspose3d with kernel == stride as GEMM + pixel-shuffle store.
+
+    x channels-last [B,T,H,W,Cin]; w [sT*sH*sW*Cout, Cin] with rows ordered (kt,kh,kw,co);
+    bias [sT*sH*sW*Cout] (the per-channel bias tiled over taps); out_16 [B,T*sT,H*sH,W*sW,Cout]."""
+    d = _base_desc(x, w)
+    B, T, H, W, Cin = x.shape
+    sT, sH, sW = stride
+    Cout = w.shape[0] // (sT * sH * sW)
+    d.M, d.N, d.K = B * T * H * W, w.shape[0], Cin
+    d.lda, d.ldw = Cin, Cin
+    d.a_mode = _l.A_MATRIX
+    d.store_mode = _l.STORE_CONVT
+    d.cB, d.cT, d.cH, d.cW = B, T, H, W
+    d.sT, d.sH, d.sW, d.ctCout = sT, sH, sW, Cout
+    _chk(bias, "bias", torch.float32); _chk(out_16, "out_16", sixteen=True)
+    d.bias = _ptr(bias); d.out_16 = out_16.data_ptr()
+    d.block_n = block_n
+    _l.check(_l.load().l4p_gemm(C.byref(d), _stream()), "l4p_gemm(convT)")

@@ -1,0 +1,186 @@
+"""GPU parity of the tcgen05 GEMM / implicit-GEMM conv kernel (through the C ABI) against plain
+torch fp32 ops on identically pre-rounded 16-bit inputs. Tolerances: fp32 accumulation of exactly
+representable products -> 1e-4 relative to the output scale for fp32 outputs, one 16-bit ulp otherwise."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+DT = [torch.float16, torch.bfloat16]
+
+
+def _ops():
+    from l4p_b200 import ops
+    return ops
+
+
+def _rand(shape, dtype, seed, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(dtype).cuda()
+
+
+def _close(got, ref, tol):
+    scale = ref.abs().max().item() + 1e-12
+    err = (got.float() - ref.float()).abs().max().item()
+    assert err <= tol * scale, f"max abs err {err:.3e} > {tol:.1e} * {scale:.3e}"
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 256, 128), (2048, 1408, 1408), (384, 176, 1176),
+                                   (2048, 4224, 1408), (130, 48, 72), (2048, 6144, 1408)])
+def test_linear_plain(dtype, M, N, K):
+    ops = _ops()
+    a = _rand((M, K), dtype, 1)
+    w = _rand((N, K), dtype, 2, K ** -0.5)
+    out = torch.empty(M, N, device="cuda", dtype=torch.float32)
+    ops.linear(a, w, out_f32=out)
+    torch.cuda.synchronize()
+    ref = a.float() @ w.float().t()
+    _close(out, ref, 2e-5)
+
+
+@pytest.mark.parametrize("dtype", DT)
+def test_linear_bias_gelu_16(dtype):
+    ops = _ops()
+    from l4p_b200 import lib
+    M, N, K = 512, 6144, 1408
+    a = _rand((M, K), dtype, 3)
+    w = _rand((N, K), dtype, 4, K ** -0.5)
+    b = _rand((N,), torch.float32, 5)
+    out = torch.empty(M, N, device="cuda", dtype=dtype)
+    ops.linear(a, w, bias=b, act=lib.ACT_GELU, out_16=out)
+    torch.cuda.synchronize()
+    ref = F.gelu(a.float() @ w.float().t() + b)
+    _close(out, ref, 2 ** -8 if dtype == torch.bfloat16 else 2 ** -10)
+
+
+@pytest.mark.parametrize("dtype", DT)
+def test_linear_residual_inplace(dtype):
+    ops = _ops()
+    M, N, K = 2048, 1408, 6144
+    a = _rand((M, K), dtype, 6)
+    w = _rand((N, K), dtype, 7, K ** -0.5)
+    b = _rand((N,), torch.float32, 8)
+    x = _rand((M, N), torch.float32, 9)
+    ref = x + a.float() @ w.float().t() + b
+    o16 = torch.empty(M, N, device="cuda", dtype=dtype)
+    ops.linear(a, w, bias=b, res_f32=x, out_f32=x, out_16=o16)
+    torch.cuda.synchronize()
+    _close(x, ref, 2e-5)
+    _close(o16, ref, 2 ** -8 if dtype == torch.bfloat16 else 2 ** -10)
+
+
+@pytest.mark.parametrize("dtype", DT)
+def test_linear_qkv_scatter(dtype):
+    ops = _ops()
+    B, H, d, dp, Ntok, Cdim = 2, 16, 88, 96, 256, 1408
+    a = _rand((B * Ntok, Cdim), dtype, 10)
+    w = _rand((3 * H * d, Cdim), dtype, 11, Cdim ** -0.5)
+    b = _rand((3 * H * d,), torch.float32, 12)
+    q = torch.zeros(B, H, Ntok, dp, device="cuda", dtype=dtype)
+    k = torch.zeros_like(q)
+    vt = torch.zeros(B, H, dp, Ntok, device="cuda", dtype=dtype)
+    ops.linear_qkv(a, w, b, q, k, vt, H, d, Ntok)
+    torch.cuda.synchronize()
+    ref = (a.float() @ w.float().t() + b).reshape(B, Ntok, 3, H, d).permute(2, 0, 3, 1, 4)
+    tol = 2 ** -8 if dtype == torch.bfloat16 else 2 ** -10
+    _close(q[..., :d], ref[0], tol)
+    _close(k[..., :d], ref[1], tol)
+    _close(vt[:, :, :d].transpose(-1, -2), ref[2], tol)
+    assert q[..., d:].abs().max().item() == 0 and vt[:, :, d:].abs().max().item() == 0
+
+
+def _conv_ref(x_cl, w_k, ksize, bias=None):
+    """x_cl [B,T,H,W,C]; w_k [Cout, taps*Cin] (kt,kh,kw,cin) -> [B,T,H,W,Cout] fp32."""
+    B, T, H, W, Cin = x_cl.shape
+    kT, kH, kW = ksize
+    Cout = w_k.shape[0]
+    w = w_k.float().reshape(Cout, kT, kH, kW, Cin).permute(0, 4, 1, 2, 3).contiguous()
+    y = F.conv3d(x_cl.float().permute(0, 4, 1, 2, 3), w, bias, padding=(kT // 2, kH // 2, kW // 2))
+    return y.permute(0, 2, 3, 4, 1).contiguous()
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("shape", [(1, 4, 8, 8, 64, 64), (2, 8, 16, 16, 128, 256), (1, 2, 32, 32, 256, 128),
+                                   (1, 3, 20, 24, 64, 32)])
+def test_conv3d_3x3x3(dtype, shape):
+    ops = _ops()
+    B, T, H, W, Cin, Cout = shape
+    x = _rand((B, T, H, W, Cin), dtype, 13)
+    w = _rand((Cout, 27 * Cin), dtype, 14, (27 * Cin) ** -0.5)
+    b = _rand((Cout,), torch.float32, 15)
+    out = torch.empty(B, T, H, W, Cout, device="cuda", dtype=torch.float32)
+    ops.conv3d(x, w, ksize=(3, 3, 3), bias=b, out_f32=out)
+    torch.cuda.synchronize()
+    _close(out, _conv_ref(x, w, (3, 3, 3), b), 3e-5)
+
+
+@pytest.mark.parametrize("dtype", DT)
+def test_conv3d_rcu_epilogue(dtype):
+    """conv + bias + two 16-bit residuals, dual output (raw and ReLU'd) as used by the RefineNet blocks."""
+    ops = _ops()
+    B, T, H, W, Cc = 1, 4, 16, 16, 256
+    x = _rand((B, T, H, W, Cc), dtype, 16)
+    w = _rand((Cc, 27 * Cc), dtype, 17, (27 * Cc) ** -0.5)
+    b = _rand((Cc,), torch.float32, 18)
+    r1 = _rand((B, T, H, W, Cc), dtype, 19)
+    r2 = _rand((B, T, H, W, Cc), dtype, 20)
+    o = torch.empty_like(x)
+    orl = torch.empty_like(x)
+    ops.conv3d(x, w, ksize=(3, 3, 3), bias=b, res_16=r1, res2_16=r2, out_16=o, out_16_relu=orl)
+    torch.cuda.synchronize()
+    ref = _conv_ref(x, w, (3, 3, 3), b) + r1.float() + r2.float()
+    tol = 2 ** -8 if dtype == torch.bfloat16 else 2 ** -10
+    _close(o, ref, tol)
+    _close(orl, ref.clamp_min(0), tol)
+
+
+@pytest.mark.parametrize("dtype", DT)
+def test_conv3d_head1x1(dtype):
+    ops = _ops()
+    B, T, H, W, Cc, C2 = 1, 2, 28, 32, 128, 2
+    x = _rand((B, T, H, W, Cc), dtype, 21)
+    w = _rand((Cc, 27 * Cc), dtype, 22, (27 * Cc) ** -0.5)
+    b = _rand((Cc,), torch.float32, 23)
+    w2 = _rand((C2, Cc), torch.float32, 24, Cc ** -0.5)
+    b2 = _rand((C2,), torch.float32, 25)
+    out = torch.empty(B, C2, T, H, W, device="cuda", dtype=torch.float32)
+    ops.conv3d(x, w, ksize=(3, 3, 3), bias=b, head_w2=w2, head_b2=b2, head_exp=True, out_f32=out)
+    torch.cuda.synchronize()
+    hid = _conv_ref(x, w, (3, 3, 3), b).clamp_min(0)
+    ref = torch.exp(hid @ w2.t() + b2).permute(0, 4, 1, 2, 3)
+    _close(out, ref, 5e-5)
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("stride", [(2, 4, 4), (2, 2, 2), (2, 1, 1), (1, 2, 2)])
+def test_conv_transpose(dtype, stride):
+    ops = _ops()
+    B, T, H, W, Cin, Cout = 1, 4, 8, 8, 256, 64
+    sT, sH, sW = stride
+    x = _rand((B, T, H, W, Cin), dtype, 26)
+    wt = _rand((Cin, Cout, sT, sH, sW), dtype, 27, Cin ** -0.5)  # torch ConvTranspose3d layout
+    b = _rand((Cout,), torch.float32, 28)
+    wk = wt.permute(2, 3, 4, 1, 0).reshape(sT * sH * sW * Cout, Cin).contiguous()
+    bk = b.repeat(sT * sH * sW).contiguous()
+    out = torch.empty(B, T * sT, H * sH, W * sW, Cout, device="cuda", dtype=dtype)
+    ops.conv_transpose3d(x, wk, bk, stride, out)
+    torch.cuda.synchronize()
+    ref = F.conv_transpose3d(x.float().permute(0, 4, 1, 2, 3), wt.float(), b, stride=stride).permute(0, 2, 3, 4, 1)
+    _close(out, ref, 2 ** -8 if dtype == torch.bfloat16 else 2 ** -10)
+
+
+@pytest.mark.parametrize("dtype", DT)
+def test_layernorm(dtype):
+    ops = _ops()
+    x = _rand((2048, 1408), torch.float32, 29, 3.0) + 0.5
+    g = _rand((1408,), torch.float32, 30) + 1.0
+    b = _rand((1408,), torch.float32, 31)
+    o16 = torch.empty(2048, 1408, device="cuda", dtype=dtype)
+    o32 = torch.empty(2048, 1408, device="cuda", dtype=torch.float32)
+    ops.layernorm(x, g, b, 1e-6, out16=o16, out32=o32)
+    torch.cuda.synchronize()
+    ref = F.layer_norm(x, (1408,), g, b, 1e-6)
+    _close(o32, ref, 2e-6)
+    _close(o16, ref, 2 ** -8 if dtype == torch.bfloat16 else 2 ** -10)
