@@ -512,7 +512,7 @@ extern "C" int l4p_gemm(const l4p_gemm_desc* d, void* stream_) {
   auto kfn = d->bf16 ? gemm_kernel<true> : gemm_kernel<false>;
   static bool attr_set[2] = {false, false};
   if (!attr_set[d->bf16 ? 1 : 0]) {
-    L4P_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    L4P_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
     attr_set[d->bf16 ? 1 : 0] = true;
   }
   kfn<<<grid, kGemmThreads, smem, stream>>>(tmA, tmB, p);
