@@ -96,6 +96,15 @@ typedef struct l4p_gemm_desc {
  * and the SAM projections (task_heads/sam/transformer.py:223-245). */
 int l4p_gemm(const l4p_gemm_desc* desc, void* stream);
 
+/* ---- K4: fused attention -------------------------------------------------------------------- */
+/* out[b*N+n, h*head_dim + c] = sum_m softmax_m(scale * q[b,h,n,:] . k[b,h,m,:]) * v[b,h,m,c]
+ * Replaces the q@k^T -> softmax -> @v sequence of Attention.forward
+ * (l4p/models/VideoMAEv2/models/modeling_finetune.py:180-186); the [B,H,N,N] score tensor is never
+ * materialised. q,k: [B,H,N,head_dim_pad]; vt: [B,H,head_dim_pad,N] (pad lanes zero); out 16-bit
+ * [B*N, H*head_dim]. This build: head_dim_pad == 96, N a multiple of 256. */
+int l4p_attention(const void* q, const void* k, const void* vt, void* out, int B, int H, int N,
+                  int head_dim, int head_dim_pad, float scale, int bf16, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

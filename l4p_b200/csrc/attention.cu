@@ -1,0 +1,348 @@
+// K4: fused spatio-temporal multi-head attention, softmax(Q K^T * scale) V, for sm_100a.
+//
+// Flash-style, never materialises the [N,N] score matrix (the reference does: modeling_finetune.py:180-186).
+// One CTA owns two 128-row query tiles of one (batch, head) and streams the keys/values in blocks of 128:
+//
+//   warp 0       TMA producer: Q tiles once, then K blocks ([128 keys x 96] as three 64-byte-swizzled
+//                32-element chunks) and V^T blocks ([96 x 128 keys], two 128-byte-swizzled chunks) in rings
+//   warp 1       UMMA issuer (one thread): S_t = Q_t K_j^T (M128 N128 K96) into TMEM, O_t += P_t V_j
+//                (M128 N96 K128) into TMEM; S_t(j+1) is issued before P_t(j) V_j so the tensor pipe
+//                works while the softmax warps run
+//   warp 2       TMEM allocator (512 columns: S0 | S1 | O0 | O1)
+//   warps 4..7   softmax warpgroup for tile 0, one query row per thread
+//   warps 8..11  softmax warpgroup for tile 1
+//
+// Softmax: fp32 scores from TMEM, running max with lazy rescale (O is only rescaled in TMEM when the row max
+// grew by more than 2^8), exp2 with the scale folded into one FFMA, fp32 row sums, P rounded to the operand
+// type and written to 128B-swizzled smem as the A operand of the PV UMMA.
+//
+// Layouts (produced by the QKV GEMM epilogue, see gemm.cu L4P_STORE_QKV):
+//   Q, K : [B, H, N, dpad]   (dpad = 96, columns >= head_dim are zero)
+//   Vt   : [B, H, dpad, N]
+//   out  : [B*N, H*head_dim] row-major 16-bit (operand of the output projection GEMM)
+#include "common.cuh"
+
+namespace l4p {
+
+constexpr int kAttThreads = 384;
+constexpr int kDPad = 96;
+constexpr int kTileM = 128;   // query rows per tile
+constexpr int kTileN = 128;   // keys per block
+constexpr int kQTileBytes = kTileM * kDPad * 2;  // 24576: 3 chunks x (128 rows x 64 B)
+constexpr int kKBytes = kTileN * kDPad * 2;      // 24576
+constexpr int kVBytes = kDPad * kTileN * 2;      // 24576: 2 chunks x (96 rows x 128 B)
+constexpr int kPBytes = kTileM * kTileN * 2;     // 32768: 2 chunks x (128 rows x 128 B)
+constexpr int kKS = 2, kVS = 2;
+constexpr int kAttSmem = 2 * kQTileBytes + kKS * kKBytes + kVS * kVBytes + 2 * kPBytes + 1024;
+constexpr uint32_t kColS0 = 0, kColS1 = 128, kColO0 = 256, kColO1 = 384;
+constexpr float kRescaleThreshold = 8.0f;  // log2 units
+
+struct AttParams {
+  uint16_t* out;
+  int B, H, N, head_dim;
+  float scale_log2;  // scale * log2(e)
+};
+
+L4P_DEVICE float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <bool BF16>
+__global__ void __launch_bounds__(kAttThreads, 1)
+attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                 const __grid_constant__ CUtensorMap tmV, const AttParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_q;
+  __shared__ __align__(8) uint64_t bar_kfull[kKS], bar_kempty[kKS];
+  __shared__ __align__(8) uint64_t bar_vfull[kVS], bar_vempty[kVS];
+  __shared__ __align__(8) uint64_t bar_sfull[2], bar_sfree[2], bar_pfull[2], bar_pvdone[2];
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sQ = smem_base;
+  const uint32_t sK = sQ + 2 * kQTileBytes;
+  const uint32_t sV = sK + kKS * kKBytes;
+  const uint32_t sP = sV + kVS * kVBytes;
+
+  const int pairs_per_head = p.N / (2 * kTileM);
+  const int pair = blockIdx.x % pairs_per_head;
+  const int bh = blockIdx.x / pairs_per_head;  // b * H + h
+  const int nblk = p.N / kTileN;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(smem_u32(&bar_q), 1);
+    for (int s = 0; s < kKS; ++s) { mbar_init(smem_u32(&bar_kfull[s]), 1); mbar_init(smem_u32(&bar_kempty[s]), 1); }
+    for (int s = 0; s < kVS; ++s) { mbar_init(smem_u32(&bar_vfull[s]), 1); mbar_init(smem_u32(&bar_vempty[s]), 1); }
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(smem_u32(&bar_sfull[t]), 1);
+      mbar_init(smem_u32(&bar_sfree[t]), 128);
+      mbar_init(smem_u32(&bar_pfull[t]), 128);
+      mbar_init(smem_u32(&bar_pvdone[t]), 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(smem_u32(&tmem_base_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (warp == 0 && lane == 0) {
+      // ---------------------------------------------------------------- TMA producer
+      const int q_row0 = bh * p.N + pair * 2 * kTileM;  // row in the [B*H*N, 96] view
+      const uint32_t qb = smem_u32(&bar_q);
+      mbar_expect_tx(qb, 2 * kQTileBytes);
+      for (int t = 0; t < 2; ++t)
+        for (int c = 0; c < 3; ++c)
+          tma_load_2d(sQ + t * kQTileBytes + c * (kTileM * 64), &tmQ, qb, c * 32, q_row0 + t * kTileM);
+      for (int j = 0; j < nblk; ++j) {
+        {
+          const int s = j % kKS;
+          mbar_wait(smem_u32(&bar_kempty[s]), (((uint32_t)(j / kKS)) & 1u) ^ 1u);
+          const uint32_t fb = smem_u32(&bar_kfull[s]);
+          mbar_expect_tx(fb, kKBytes);
+          for (int c = 0; c < 3; ++c)
+            tma_load_2d(sK + s * kKBytes + c * (kTileN * 64), &tmK, fb, c * 32, bh * p.N + j * kTileN);
+        }
+        {
+          const int s = j % kVS;
+          mbar_wait(smem_u32(&bar_vempty[s]), (((uint32_t)(j / kVS)) & 1u) ^ 1u);
+          const uint32_t fb = smem_u32(&bar_vfull[s]);
+          mbar_expect_tx(fb, kVBytes);
+          for (int c = 0; c < 2; ++c)
+            tma_load_2d(sV + s * kVBytes + c * (kDPad * 128), &tmV, fb, j * kTileN + c * 64, bh * kDPad);
+        }
+      }
+    } else if (warp == 1 && lane == 0) {
+      // ---------------------------------------------------------------- UMMA issuer
+      const uint32_t idesc_s = umma_idesc_f16(BF16, kTileM, kTileN);
+      const uint32_t idesc_o = umma_idesc_f16(BF16, kTileM, kDPad);
+      auto issue_s = [&](int t, int j) {
+        const int s = j % kKS;
+        const uint32_t d = tmem_base + (t == 0 ? kColS0 : kColS1);
+#pragma unroll
+        for (int kk = 0; kk < kDPad / 16; ++kk) {
+          const uint32_t off = (uint32_t)(kk >> 1) * (kTileM * 64) + (uint32_t)(kk & 1) * 32;
+          const uint64_t da = umma_desc_kmajor(sQ + t * kQTileBytes + off, 64, 4);
+          const uint64_t db = umma_desc_kmajor(sK + s * kKBytes + off, 64, 4);
+          umma_ss(d, da, db, idesc_s, kk != 0 ? 1u : 0u);
+        }
+        umma_commit(smem_u32(&bar_sfull[t]));
+      };
+      auto issue_pv = [&](int t, int j) {
+        const int s = j % kVS;
+        const uint32_t d = tmem_base + (t == 0 ? kColO0 : kColO1);
+#pragma unroll
+        for (int kk = 0; kk < kTileN / 16; ++kk) {
+          const uint32_t c = (uint32_t)(kk >> 2), o = (uint32_t)(kk & 3) * 32;
+          const uint64_t da = umma_desc_kmajor(sP + t * kPBytes + c * (kTileM * 128) + o, 128, 2);
+          const uint64_t db = umma_desc_kmajor(sV + s * kVBytes + c * (kDPad * 128) + o, 128, 2);
+          umma_ss(d, da, db, idesc_o, (j | kk) != 0 ? 1u : 0u);
+        }
+        umma_commit(smem_u32(&bar_pvdone[t]));
+      };
+
+      mbar_wait(smem_u32(&bar_q), 0);
+      mbar_wait(smem_u32(&bar_kfull[0]), 0);
+      tc_fence_after();
+      issue_s(0, 0);
+      issue_s(1, 0);
+      umma_commit(smem_u32(&bar_kempty[0]));
+      for (int j = 0; j < nblk; ++j) {
+        for (int t = 0; t < 2; ++t) {
+          if (j + 1 < nblk) {
+            const int jn = j + 1;
+            if (t == 0) mbar_wait(smem_u32(&bar_kfull[jn % kKS]), ((uint32_t)(jn / kKS)) & 1u);
+            mbar_wait(smem_u32(&bar_sfree[t]), (uint32_t)j & 1u);  // softmax t holds S_t(j) in registers
+            tc_fence_after();
+            issue_s(t, jn);
+            if (t == 1) umma_commit(smem_u32(&bar_kempty[jn % kKS]));
+          }
+          mbar_wait(smem_u32(&bar_pfull[t]), (uint32_t)j & 1u);  // P_t(j) in smem (and O_t rescaled)
+          if (t == 0) mbar_wait(smem_u32(&bar_vfull[j % kVS]), ((uint32_t)(j / kVS)) & 1u);
+          tc_fence_after();
+          issue_pv(t, j);
+          if (t == 1) umma_commit(smem_u32(&bar_vempty[j % kVS]));
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax warpgroups
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
+    const int t = (warp - 4) >> 2;            // tile
+    const int q4 = warp & 3;                   // TMEM lane quarter
+    const int r = q4 * 32 + lane;              // row in tile
+    const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
+    const uint32_t tS = tmem_base + lane_addr + (t == 0 ? kColS0 : kColS1);
+    const uint32_t tO = tmem_base + lane_addr + (t == 0 ? kColO0 : kColO1);
+    const uint32_t pRow = sP + t * kPBytes + (uint32_t)r * 128u;
+    const uint32_t swz = (uint32_t)(r & 7);
+    const float c = p.scale_log2;
+
+    float m_used = -INFINITY;
+    float l = 0.f;
+
+    for (int j = 0; j < nblk; ++j) {
+      mbar_wait(smem_u32(&bar_sfull[t]), (uint32_t)j & 1u);
+      tc_fence_after();
+      uint32_t s[128];
+      tmem_ld32(tS + 0, s + 0);
+      tmem_ld32(tS + 32, s + 32);
+      tmem_ld32(tS + 64, s + 64);
+      tmem_ld32(tS + 96, s + 96);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(smem_u32(&bar_sfree[t]));
+
+      float mx0 = __uint_as_float(s[0]), mx1 = __uint_as_float(s[1]), mx2 = __uint_as_float(s[2]),
+            mx3 = __uint_as_float(s[3]);
+#pragma unroll
+      for (int i = 4; i < 128; i += 4) {
+        mx0 = fmaxf(mx0, __uint_as_float(s[i]));
+        mx1 = fmaxf(mx1, __uint_as_float(s[i + 1]));
+        mx2 = fmaxf(mx2, __uint_as_float(s[i + 2]));
+        mx3 = fmaxf(mx3, __uint_as_float(s[i + 3]));
+      }
+      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * c;
+
+      if (j == 0) {
+        m_used = mx;
+      } else {
+        const bool need = mx > m_used + kRescaleThreshold;
+        if (__any_sync(0xffffffffu, need)) {
+          // rare: rescale the running output in TMEM (whole warp, each row with its own factor)
+          const float m_new = fmaxf(m_used, mx);
+          const float alpha = ex2(m_used - m_new);
+          mbar_wait(smem_u32(&bar_pvdone[t]), (uint32_t)(j - 1) & 1u);
+          tc_fence_after();
+#pragma unroll
+          for (int cc = 0; cc < kDPad; cc += 32) {
+            uint32_t o[32];
+            tmem_ld32(tO + cc, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st16(tO + cc, o);
+            tmem_st16(tO + cc + 16, o + 16);
+          }
+          tmem_st_wait();
+          tc_fence_before();
+          l *= alpha;
+          m_used = m_new;
+        }
+      }
+
+      // p = exp2(s*c - m_used), row sum in fp32, pack pairs in place
+      float l0 = 0.f, l1 = 0.f;
+      const float nm = -m_used;
+#pragma unroll
+      for (int i = 0; i < 128; i += 2) {
+        const float p0 = ex2(fmaf(__uint_as_float(s[i]), c, nm));
+        const float p1 = ex2(fmaf(__uint_as_float(s[i + 1]), c, nm));
+        l0 += p0;
+        l1 += p1;
+        s[i >> 1] = pack2<BF16>(p0, p1);
+      }
+      l += l0 + l1;
+
+      if (j > 0) mbar_wait(smem_u32(&bar_pvdone[t]), (uint32_t)(j - 1) & 1u);  // P_t smem is free again
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        // 16-byte unit u: keys [8u, 8u+8); chunk = u/8; swizzled unit inside the 128-byte row
+        const uint32_t addr = pRow + (uint32_t)(u >> 3) * (kTileM * 128) + ((((uint32_t)u & 7u) ^ swz) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(s[4 * u]), "r"(s[4 * u + 1]),
+                     "r"(s[4 * u + 2]), "r"(s[4 * u + 3])
+                     : "memory");
+      }
+      fence_proxy_async();
+      mbar_arrive(smem_u32(&bar_pfull[t]));
+    }
+
+    // ---- epilogue: O_t / l -> global
+    mbar_wait(smem_u32(&bar_pvdone[t]), (uint32_t)(nblk - 1) & 1u);
+    tc_fence_after();
+    const float inv_l = 1.0f / l;
+    const int b = bh / p.H, h = bh - b * p.H;
+    const long long row = (long long)b * p.N + (long long)pair * 2 * kTileM + t * kTileM + r;
+    uint16_t* dst = p.out + row * ((long long)p.H * p.head_dim) + (long long)h * p.head_dim;
+#pragma unroll
+    for (int cc = 0; cc < kDPad; cc += 32) {
+      uint32_t o[32];
+      tmem_ld32(tO + cc, o);
+      tmem_ld_wait();
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int col = cc + g * 8;
+        if (col < p.head_dim) {  // head_dim is a multiple of 8
+          float f[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(o[g * 8 + i]) * inv_l;
+          *reinterpret_cast<uint4*>(dst + col) = make_uint4(pack2<BF16>(f[0], f[1]), pack2<BF16>(f[2], f[3]),
+                                                            pack2<BF16>(f[4], f[5]), pack2<BF16>(f[6], f[7]));
+        }
+      }
+    }
+    tc_fence_before();
+  }
+
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace l4p
+
+using namespace l4p;
+
+extern "C" int l4p_attention(const void* q, const void* k, const void* vt, void* out, int B, int H, int N,
+                             int head_dim, int head_dim_pad, float scale, int bf16, void* stream) {
+  L4P_REQUIRE(q && k && vt && out, L4P_ERR_ARG, "l4p_attention: null pointer");
+  L4P_REQUIRE(B > 0 && H > 0, L4P_ERR_SHAPE, "l4p_attention: B=%d H=%d", B, H);
+  L4P_REQUIRE(head_dim_pad == kDPad && head_dim % 8 == 0 && head_dim > 0 && head_dim <= kDPad, L4P_ERR_SHAPE,
+              "l4p_attention: head_dim=%d pad=%d (this build: pad 96, head_dim multiple of 8 <= 96)", head_dim,
+              head_dim_pad);
+  L4P_REQUIRE(N >= 2 * kTileM && N % (2 * kTileM) == 0, L4P_ERR_SHAPE, "l4p_attention: N=%d must be a multiple of 256", N);
+  CUtensorMap tmQ, tmK, tmV;
+  int rc;
+  {
+    const uint64_t dims[2] = {(uint64_t)kDPad, (uint64_t)B * H * N};
+    const uint64_t strides[1] = {(uint64_t)kDPad * 2};
+    const uint32_t box[2] = {32, (uint32_t)kTileM};
+    rc = host_make_tmap_16b(&tmQ, q, 2, dims, strides, box, 64);
+    if (rc != L4P_OK) return rc;
+    rc = host_make_tmap_16b(&tmK, k, 2, dims, strides, box, 64);
+    if (rc != L4P_OK) return rc;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)N, (uint64_t)B * H * kDPad};
+    const uint64_t strides[1] = {(uint64_t)N * 2};
+    const uint32_t box[2] = {64, (uint32_t)kDPad};
+    rc = host_make_tmap_16b(&tmV, vt, 2, dims, strides, box, 128);
+    if (rc != L4P_OK) return rc;
+  }
+  AttParams p;
+  p.out = (uint16_t*)out;
+  p.B = B; p.H = H; p.N = N; p.head_dim = head_dim;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  auto kfn = bf16 ? attention_kernel<true> : attention_kernel<false>;
+  static bool attr_set[2] = {false, false};
+  if (!attr_set[bf16 ? 1 : 0]) {
+    L4P_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmem));
+    attr_set[bf16 ? 1 : 0] = true;
+  }
+  const int grid = B * H * (N / (2 * kTileM));
+  kfn<<<grid, kAttThreads, kAttSmem, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
+  L4P_CHECK_CUDA(cudaGetLastError());
+  return L4P_OK;
+}

@@ -53,6 +53,8 @@ _SIGNATURES = {
     "l4p_layernorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
                                 C.c_float, C.c_int, C.c_void_p]),
     "l4p_gemm": (C.c_int, [C.POINTER(GemmDesc), C.c_void_p]),
+    "l4p_attention": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                C.c_int, C.c_float, C.c_int, C.c_void_p]),
 }
 
 _lib: Optional[C.CDLL] = None

@@ -195,3 +195,21 @@ def conv_transpose3d(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, strid
     d.bias = _ptr(bias); d.out_16 = out_16.data_ptr()
     d.block_n = block_n
     _l.check(_l.load().l4p_gemm(C.byref(d), _stream()), "l4p_gemm(convT)")
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, out: torch.Tensor, head_dim: int,
+              scale: float) -> None:
+    """K4: fused softmax(q k^T scale) v. q,k [B,H,N,dpad]; vt [B,H,dpad,N]; out [B*N, H*head_dim] 16-bit."""
+    _dev_init(q)
+    for n, t in (("q", q), ("k", k), ("vt", vt), ("out", out)):
+        _chk(t, n, sixteen=True)
+        if t.dtype != q.dtype:
+            raise _l.L4PError(f"attention: {n} dtype {t.dtype} != {q.dtype}")
+    B, H, N, dpad = q.shape
+    if tuple(k.shape) != (B, H, N, dpad) or tuple(vt.shape) != (B, H, dpad, N):
+        raise _l.L4PError(f"attention: shapes q{tuple(q.shape)} k{tuple(k.shape)} vt{tuple(vt.shape)}")
+    if out.numel() != B * N * H * head_dim:
+        raise _l.L4PError(f"attention: out has {out.numel()} elements, expected {B * N * H * head_dim}")
+    _l.check(_l.load().l4p_attention(q.data_ptr(), k.data_ptr(), vt.data_ptr(), out.data_ptr(), B, H, N, head_dim,
+                                     dpad, float(scale), 1 if q.dtype == torch.bfloat16 else 0, _stream()),
+             "l4p_attention")

@@ -184,3 +184,34 @@ def test_layernorm(dtype):
     ref = F.layer_norm(x, (1408,), g, b, 1e-6)
     _close(o32, ref, 2e-6)
     _close(o16, ref, 2 ** -8 if dtype == torch.bfloat16 else 2 ** -10)
+
+
+def _attn_ref(q, k, v, scale):
+    s = (q.float() @ k.float().transpose(-1, -2)) * scale
+    return torch.softmax(s, dim=-1) @ v.float()
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("B,H,N,peaky", [(1, 2, 256, 1.0), (1, 16, 2048, 1.0), (2, 3, 512, 6.0), (1, 2, 1024, 30.0)])
+def test_attention(dtype, B, H, N, peaky):
+    """Fused attention vs fp32 softmax attention on the same rounded q,k,v. `peaky` scales q so the row max
+    moves by many log2 units across key blocks (exercises the lazy TMEM rescale)."""
+    ops = _ops()
+    d, dp = 88, 96
+    q = torch.zeros(B, H, N, dp, device="cuda", dtype=dtype)
+    k = torch.zeros_like(q)
+    vt = torch.zeros(B, H, dp, N, device="cuda", dtype=dtype)
+    q[..., :d] = _rand((B, H, N, d), dtype, 40, peaky)
+    k[..., :d] = _rand((B, H, N, d), dtype, 41)
+    v = _rand((B, H, N, d), dtype, 42)
+    vt[:, :, :d] = v.transpose(-1, -2)
+    out = torch.empty(B * N, H * d, device="cuda", dtype=dtype)
+    scale = d ** -0.5
+    ops.attention(q, k, vt, out, d, scale)
+    torch.cuda.synchronize()
+    ref = _attn_ref(q[..., :d], k[..., :d], v, scale)  # [B,H,N,d]
+    ref = ref.permute(0, 2, 1, 3).reshape(B * N, H * d)
+    # P is rounded to the operand type before the PV contraction: tolerance = a few operand ulps of |v|max
+    _close(out, ref, 2 ** -6 if dtype == torch.bfloat16 else 2 ** -9)
+    rel_l2 = ((out.float() - ref).norm() / ref.norm()).item()
+    assert rel_l2 < (6e-3 if dtype == torch.bfloat16 else 1e-3), rel_l2
