@@ -75,6 +75,7 @@ typedef struct l4p_gemm_desc {
   const void* res_16;     /* optional 16-bit residual, same indexing as out_16 (row-major)         */
   const void* res2_16;    /* optional second 16-bit residual                                       */
   int64_t ld_res;
+  int res_row_mod;        /* >0: res_f32 row index = row % res_row_mod (broadcast table, e.g. pos-embed) */
   int store_mode;      /* L4P_STORE_*                                                              */
   float* out_f32;      /* ROWMAJOR: optional fp32 output [M, ld_out]                               */
   void* out_16;        /* ROWMAJOR/CONVT: 16-bit output                                            */
@@ -96,6 +97,24 @@ typedef struct l4p_gemm_desc {
  * and the SAM projections (task_heads/sam/transformer.py:223-245). */
 int l4p_gemm(const l4p_gemm_desc* desc, void* stream);
 
+/* ---- K1/K7/K9 helpers (HBM-bound) ------------------------------------------------------------- */
+/* Tubelet gather for the patch embedding: rgb fp32 [B,C,T,H,W] -> 16-bit [B*(T/pt)*(H/ph)*(W/pw), C*pt*ph*pw],
+ * K ordered (c,dt,dh,dw) = flattened Conv3d weight; token order t'*nh*nw + h'*nw + w'.
+ * With l4p_gemm this replaces PatchEmbed.forward (modeling_finetune.py:276-283). */
+int l4p_patchify(const float* rgb, void* out16, int B, int C, int T, int H, int W, int pt, int ph, int pw,
+                 int bf16, void* stream);
+/* fp32 -> 16-bit cast, n a multiple of 4. */
+int l4p_cast16(const float* x, void* y16, int64_t n, int bf16, void* stream);
+/* Trilinear resampling of channels-last 16-bit [B,Ti,Hi,Wi,C] -> [B,To,Ho,Wo,C] (y16 and/or its ReLU y16_relu).
+ * Replaces F.interpolate(mode="trilinear") (dpt_block.py:231-236, dpt_head.py:79-83: align_corners=1;
+ * sparse_heads.py:645-647: align_corners=0). */
+int l4p_upsample3d(const void* x16, void* y16, void* y16_relu, int B, int Ti, int Hi, int Wi, int To, int Ho,
+                   int Wo, int C, int align_corners, int bf16, void* stream);
+/* 3x3x3 / pad 1 / stride (sT,sH,sW) gather of channels-last x into [B*To*Ho*Wo, 27*C] rows (kt,kh,kw,c);
+ * with l4p_gemm this replaces the stride-2 Conv3d of the DPT reassemble stage (dpt_block.py:265-278). */
+int l4p_im2col3(const void* x16, void* out16, int B, int T, int H, int W, int C, int sT, int sH, int sW,
+                void* stream);
+
 /* ---- K4: fused attention -------------------------------------------------------------------- */
 /* out[b*N+n, h*head_dim + c] = sum_m softmax_m(scale * q[b,h,n,:] . k[b,h,m,:]) * v[b,h,m,c]
  * Replaces the q@k^T -> softmax -> @v sequence of Attention.forward
@@ -104,6 +123,25 @@ int l4p_gemm(const l4p_gemm_desc* desc, void* stream);
  * [B*N, H*head_dim]. This build: head_dim_pad == 96, N a multiple of 256. */
 int l4p_attention(const void* q, const void* k, const void* vt, void* out, int B, int H, int N,
                   int head_dim, int head_dim_pad, float scale, int bf16, void* stream);
+
+/* ---- K11: camera pose from Plücker rays ------------------------------------------------------ */
+/* rays fp32 [B,6,T,h,w] (direction, moment). mode 0: use normalised intrinsics k_norm [B,4,4,T]
+ * (rays_to_cameras, l4p/utils/geometry_utils.py:331-406); mode 1: estimate one fixed K from frame 0 by a
+ * normalised-DLT homography with `refits` consensus refits at `reproj_threshold`, RQ-decomposed
+ * (rays_to_cameras_and_fixed_per_frame_intrinsics, :493-579, replacing cv2.findHomography/RQDecomp3x3 :436-448),
+ * k_est [B,4,4,T] is reported at (outH,outW). Outputs: ext [B,4,4,T] (cam<-world), pose [B,4,4,T] = ext^-1
+ * (dense_heads.py:346), centers [B,T,3]. ws_kgrid: B*9 doubles of scratch (mode 1). */
+int l4p_pose_from_rays(const float* rays, const float* k_norm, int mode, int B, int T, int h, int w, int outH,
+                       int outW, float reproj_threshold, int refits, double* ws_kgrid, float* ext, float* pose,
+                       float* centers, float* k_est, void* stream);
+
+/* ---- K16: depth window affine aligner ----------------------------------------------------------- */
+/* sol[b] = argmin_(s,t) || s*f(pred[b]) + t - f(target[b]) ||^2 over n elements, f = safe_inverse when
+ * inverse != 0 (LstSqAffineAligner.solve, l4p/models/aligner.py:45-57; misc.py:48-62). ws_moments: 5*B doubles. */
+int l4p_affine_align_solve(const float* pred, const float* target, int B, int64_t n, int64_t pred_stride,
+                           int64_t target_stride, int inverse, double* ws_moments, float* sol, void* stream);
+/* y = f(s*f(x)+t) (LstSqAffineAligner.apply, aligner.py:59-66); x,y [B,n]. */
+int l4p_affine_align_apply(const float* x, float* y, const float* sol, int B, int64_t n, int inverse, void* stream);
 
 #ifdef __cplusplus
 }

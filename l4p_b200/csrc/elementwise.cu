@@ -1,0 +1,223 @@
+// HBM-bound helper kernels around the tensor-core path: tubelet gather for the patch embedding (K1),
+// fp32 -> 16-bit casts, channels-last trilinear resampling (K9), strided-conv gather (K7, the one stride-2
+// convolution of the DPT reassemble stage). All are coalesced / 16-byte vectorised over the channel axis.
+#include "common.cuh"
+
+namespace l4p {
+
+// ------------------------------------------------------------------------------------------------
+// K1 gather: rgb [B,C,T,H,W] fp32 -> A [B*nt*nh*nw, C*pt*ph*pw] 16-bit, K ordered (c,dt,dh,dw) which is the
+// flattened Conv3d weight order (modeling_finetune.py:268-273), token order t'*nh*nw + h'*nw + w' (:282).
+// ------------------------------------------------------------------------------------------------
+template <bool BF16>
+__global__ void patchify_kernel(const float* __restrict__ rgb, uint16_t* __restrict__ out, int B, int C, int T, int H,
+                                int W, int pt, int ph, int pw, long long total) {
+  const int nt = T / pt, nh = H / ph, nw = W / pw;
+  const int K = C * pt * ph * pw;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int kk = (int)(idx % K);
+    long long row = idx / K;
+    const int dw = kk % pw;
+    const int dh = (kk / pw) % ph;
+    const int dt = (kk / (pw * ph)) % pt;
+    const int c = kk / (pw * ph * pt);
+    const int wq = (int)(row % nw); row /= nw;
+    const int hq = (int)(row % nh); row /= nh;
+    const int tq = (int)(row % nt); row /= nt;
+    const long long b = row;
+    const long long src = (((b * C + c) * T + (tq * pt + dt)) * H + (hq * ph + dh)) * (long long)W + (wq * pw + dw);
+    out[idx] = pack1<BF16>(rgb[src]);
+  }
+}
+
+template <bool BF16>
+__global__ void cast16_kernel(const float4* __restrict__ x, uint2* __restrict__ y, long long n4) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = x[i];
+    y[i] = make_uint2(pack2<BF16>(v.x, v.y), pack2<BF16>(v.z, v.w));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K9: trilinear resampling of channels-last [B,Ti,Hi,Wi,C] -> [B,To,Ho,Wo,C]; one thread per (voxel, 8 channels).
+// align_corners=1: src = dst*(in-1)/(out-1)   (dpt_block.py:231-236, dpt_head.py:81-83)
+// align_corners=0: src = max((dst+0.5)*in/out - 0.5, 0)   (sparse_heads.py:645-647)
+// ------------------------------------------------------------------------------------------------
+struct Axis {
+  int i0, i1;
+  float w1;
+};
+L4P_DEVICE Axis axis_coord(int o, int in, int out, int align) {
+  Axis a;
+  float s;
+  if (align) {
+    s = out > 1 ? (float)o * ((float)(in - 1) / (float)(out - 1)) : 0.f;
+  } else {
+    s = ((float)o + 0.5f) * ((float)in / (float)out) - 0.5f;
+    s = s < 0.f ? 0.f : s;
+  }
+  a.i0 = (int)s;
+  if (a.i0 > in - 1) a.i0 = in - 1;
+  a.i1 = a.i0 + 1 < in ? a.i0 + 1 : in - 1;
+  a.w1 = s - (float)a.i0;
+  return a;
+}
+
+template <bool BF16>
+__global__ void upsample_cl_kernel(const uint16_t* __restrict__ x, uint16_t* __restrict__ y,
+                                   uint16_t* __restrict__ y_relu, int B, int Ti, int Hi, int Wi, int To, int Ho, int Wo,
+                                   int C, int align, long long total) {
+  const int cg = C / 8;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(idx % cg);
+    long long v = idx / cg;
+    const int wo = (int)(v % Wo); v /= Wo;
+    const int ho = (int)(v % Ho); v /= Ho;
+    const int to = (int)(v % To); v /= To;
+    const long long b = v;
+    const Axis at = axis_coord(to, Ti, To, align);
+    const Axis ah = axis_coord(ho, Hi, Ho, align);
+    const Axis aw = axis_coord(wo, Wi, Wo, align);
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll
+    for (int ct = 0; ct < 2; ++ct) {
+      const float wt = ct ? at.w1 : 1.f - at.w1;
+      if (wt == 0.f) continue;
+      const int ti = ct ? at.i1 : at.i0;
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch) {
+        const float wh = ch ? ah.w1 : 1.f - ah.w1;
+        if (wh == 0.f) continue;
+        const int hi = ch ? ah.i1 : ah.i0;
+#pragma unroll
+        for (int cw = 0; cw < 2; ++cw) {
+          const float ww = cw ? aw.w1 : 1.f - aw.w1;
+          if (ww == 0.f) continue;
+          const int wi = cw ? aw.i1 : aw.i0;
+          const float wgt = wt * wh * ww;
+          const uint4 raw = *reinterpret_cast<const uint4*>(
+              x + ((((b * Ti + ti) * Hi + hi) * (long long)Wi + wi) * C + g * 8));
+          const uint32_t r[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 f = unpack2<BF16>(r[i]);
+            acc[2 * i] = fmaf(wgt, f.x, acc[2 * i]);
+            acc[2 * i + 1] = fmaf(wgt, f.y, acc[2 * i + 1]);
+          }
+        }
+      }
+    }
+    const long long o = ((((b * To + to) * Ho + ho) * (long long)Wo + wo) * C + g * 8);
+    if (y != nullptr)
+      *reinterpret_cast<uint4*>(y + o) = make_uint4(pack2<BF16>(acc[0], acc[1]), pack2<BF16>(acc[2], acc[3]),
+                                                    pack2<BF16>(acc[4], acc[5]), pack2<BF16>(acc[6], acc[7]));
+    if (y_relu != nullptr) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = fmaxf(acc[i], 0.f);
+      *reinterpret_cast<uint4*>(y_relu + o) = make_uint4(pack2<BF16>(acc[0], acc[1]), pack2<BF16>(acc[2], acc[3]),
+                                                         pack2<BF16>(acc[4], acc[5]), pack2<BF16>(acc[6], acc[7]));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Strided 3x3x3 gather (pad 1): x [B,T,H,W,C] -> A [B*To*Ho*Wo, 27*C], K ordered (kt,kh,kw,c).
+// Only used for the 1024->1024 stride-2 conv on the 8x16x16 grid (dpt_block.py:265-278): 14 MB.
+// ------------------------------------------------------------------------------------------------
+__global__ void im2col3_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int B, int T, int H, int W, int C,
+                               int sT, int sH, int sW, int To, int Ho, int Wo, long long total) {
+  const int cg = C / 8;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(idx % cg);
+    long long v = idx / cg;
+    const int tap = (int)(v % 27); v /= 27;
+    const int wo = (int)(v % Wo); v /= Wo;
+    const int ho = (int)(v % Ho); v /= Ho;
+    const int to = (int)(v % To); v /= To;
+    const long long b = v;
+    const int ti = to * sT + tap / 9 - 1;
+    const int hi = ho * sH + (tap / 3) % 3 - 1;
+    const int wi = wo * sW + tap % 3 - 1;
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (ti >= 0 && ti < T && hi >= 0 && hi < H && wi >= 0 && wi < W)
+      val = x[(((b * T + ti) * H + hi) * (long long)W + wi) * cg + g];
+    out[idx] = val;
+  }
+}
+
+static unsigned grid_for(long long total, int block) {
+  long long g = (total + block - 1) / block;
+  const long long cap = (long long)host_num_sms() * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (unsigned)g;
+}
+
+}  // namespace l4p
+
+using namespace l4p;
+
+extern "C" int l4p_patchify(const float* rgb, void* out16, int B, int C, int T, int H, int W, int pt, int ph, int pw,
+                            int bf16, void* stream) {
+  L4P_REQUIRE(rgb && out16, L4P_ERR_ARG, "l4p_patchify: null pointer");
+  L4P_REQUIRE(B > 0 && C > 0 && pt > 0 && ph > 0 && pw > 0 && T % pt == 0 && H % ph == 0 && W % pw == 0, L4P_ERR_SHAPE,
+              "l4p_patchify: [%d,%d,%d,%d,%d] not divisible by tubelet (%d,%d,%d)", B, C, T, H, W, pt, ph, pw);
+  const long long total = (long long)B * C * T * H * W;
+  const unsigned grid = grid_for(total, 256);
+  if (bf16)
+    patchify_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(rgb, (uint16_t*)out16, B, C, T, H, W, pt, ph, pw, total);
+  else
+    patchify_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(rgb, (uint16_t*)out16, B, C, T, H, W, pt, ph, pw, total);
+  L4P_CHECK_CUDA(cudaGetLastError());
+  return L4P_OK;
+}
+
+extern "C" int l4p_cast16(const float* x, void* y16, int64_t n, int bf16, void* stream) {
+  L4P_REQUIRE(x && y16, L4P_ERR_ARG, "l4p_cast16: null pointer");
+  L4P_REQUIRE(n >= 0 && n % 4 == 0, L4P_ERR_SHAPE, "l4p_cast16: n=%lld must be a multiple of 4", (long long)n);
+  if (n == 0) return L4P_OK;
+  const unsigned grid = grid_for(n / 4, 256);
+  if (bf16)
+    cast16_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>((const float4*)x, (uint2*)y16, n / 4);
+  else
+    cast16_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>((const float4*)x, (uint2*)y16, n / 4);
+  L4P_CHECK_CUDA(cudaGetLastError());
+  return L4P_OK;
+}
+
+extern "C" int l4p_upsample3d(const void* x16, void* y16, void* y16_relu, int B, int Ti, int Hi, int Wi, int To, int Ho,
+                              int Wo, int C, int align_corners, int bf16, void* stream) {
+  L4P_REQUIRE(x16 && (y16 || y16_relu), L4P_ERR_ARG, "l4p_upsample3d: null pointer");
+  L4P_REQUIRE(B > 0 && Ti > 0 && Hi > 0 && Wi > 0 && To > 0 && Ho > 0 && Wo > 0 && C > 0 && C % 8 == 0, L4P_ERR_SHAPE,
+              "l4p_upsample3d: bad shape (C=%d must be a multiple of 8)", C);
+  const long long total = (long long)B * To * Ho * Wo * (C / 8);
+  const unsigned grid = grid_for(total, 256);
+  if (bf16)
+    upsample_cl_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>((const uint16_t*)x16, (uint16_t*)y16,
+                                                                       (uint16_t*)y16_relu, B, Ti, Hi, Wi, To, Ho, Wo, C,
+                                                                       align_corners, total);
+  else
+    upsample_cl_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>((const uint16_t*)x16, (uint16_t*)y16,
+                                                                        (uint16_t*)y16_relu, B, Ti, Hi, Wi, To, Ho, Wo, C,
+                                                                        align_corners, total);
+  L4P_CHECK_CUDA(cudaGetLastError());
+  return L4P_OK;
+}
+
+extern "C" int l4p_im2col3(const void* x16, void* out16, int B, int T, int H, int W, int C, int sT, int sH, int sW,
+                           void* stream) {
+  L4P_REQUIRE(x16 && out16, L4P_ERR_ARG, "l4p_im2col3: null pointer");
+  L4P_REQUIRE(B > 0 && T > 0 && H > 0 && W > 0 && C % 8 == 0 && sT > 0 && sH > 0 && sW > 0, L4P_ERR_SHAPE,
+              "l4p_im2col3: bad shape");
+  const int To = (T + 2 - 3) / sT + 1, Ho = (H + 2 - 3) / sH + 1, Wo = (W + 2 - 3) / sW + 1;
+  const long long total = (long long)B * To * Ho * Wo * 27 * (C / 8);
+  im2col3_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)x16, (uint4*)out16, B, T, H, W, C,
+                                                                        sT, sH, sW, To, Ho, Wo, total);
+  L4P_CHECK_CUDA(cudaGetLastError());
+  return L4P_OK;
+}

@@ -40,6 +40,7 @@ struct GemmKParams {
   const uint16_t* res_16;
   const uint16_t* res2_16;
   long long ld_res;
+  int res_row_mod;
   int store_mode;
   float* out_f32;
   uint16_t* out_16;
@@ -229,7 +230,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           // masked row: nothing to store (loads above are warp-collective, stores are per-thread)
         } else if (p.store_mode == L4P_STORE_ROWMAJOR) {
           if (p.res_f32 != nullptr) {
-            const float* rp = p.res_f32 + row * p.ld_res + col0;
+            const long long rrow = p.res_row_mod > 0 ? row % p.res_row_mod : row;
+            const float* rp = p.res_f32 + rrow * p.ld_res + col0;
 #pragma unroll
             for (int i = 0; i < 16; i += 4) {
               const float4 rv = *reinterpret_cast<const float4*>(rp + i);
@@ -458,6 +460,7 @@ extern "C" int l4p_gemm(const l4p_gemm_desc* d, void* stream_) {
   p.res_16 = (const uint16_t*)d->res_16;
   p.res2_16 = (const uint16_t*)d->res2_16;
   p.ld_res = d->ld_res;
+  p.res_row_mod = d->res_row_mod;
   p.out_f32 = d->out_f32;
   p.out_16 = (uint16_t*)d->out_16;
   p.out_16_relu = (uint16_t*)d->out_16_relu;

@@ -34,6 +34,7 @@ class GemmDesc(C.Structure):
         ("bT", C.c_int), ("bH", C.c_int), ("bW", C.c_int),
         ("bias", C.c_void_p), ("act", C.c_int),
         ("res_f32", C.c_void_p), ("res_16", C.c_void_p), ("res2_16", C.c_void_p), ("ld_res", C.c_int64),
+        ("res_row_mod", C.c_int),
         ("store_mode", C.c_int),
         ("out_f32", C.c_void_p), ("out_16", C.c_void_p), ("out_16_relu", C.c_void_p), ("ld_out", C.c_int64),
         ("q", C.c_void_p), ("k", C.c_void_p), ("vt", C.c_void_p),
@@ -53,6 +54,14 @@ _SIGNATURES = {
     "l4p_layernorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
                                 C.c_float, C.c_int, C.c_void_p]),
     "l4p_gemm": (C.c_int, [C.POINTER(GemmDesc), C.c_void_p]),
+    "l4p_patchify": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 9 + [C.c_void_p]),
+    "l4p_cast16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
+    "l4p_upsample3d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 10 + [C.c_void_p]),
+    "l4p_im2col3": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 8 + [C.c_void_p]),
+    "l4p_pose_from_rays": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 7 + [C.c_float, C.c_int] + [C.c_void_p] * 6),
+    "l4p_affine_align_solve": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int,
+                                         C.c_void_p, C.c_void_p, C.c_void_p]),
+    "l4p_affine_align_apply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p]),
     "l4p_attention": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                 C.c_int, C.c_float, C.c_int, C.c_void_p]),
 }

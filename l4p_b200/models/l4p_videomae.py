@@ -1,0 +1,128 @@
+"""L4P model = shared video encoder + task heads. Drop-in mirror of l4p/models/l4p_videomae.py
+(VideoMAEEncoder :17-122 re-exported from .videomae, L4P_VideoMAE :125-330): same constructor arguments,
+state-dict keys (`video_encoder.*`, `task_heads.<task>.*`), `forward(data, tasks)`, `forward_single_window`,
+`encode_features`, assertion messages and output keys.
+
+B200-first difference: the reference encodes the sliding windows one after the other (:278-293); here all
+windows of the clip (and all clips of the batch) are stacked and go through the encoder kernels as one batch,
+in chunks of `max_windows_per_pass`, and the per-window lists the heads expect are views of that batch.
+"""
+from __future__ import annotations
+
+from functools import partial
+from typing import Any, Dict, List, Optional, Tuple
+
+import torch
+
+from ..utils.geometry_utils import normalize_intrinsics
+from .task_heads.dense_heads import joint_windowed_estimation
+from .videomae import FeatureList, VideoMAEEncoder
+
+__all__ = ["VideoMAEEncoder", "L4P_VideoMAE"]
+
+
+class L4P_VideoMAE(torch.nn.Module):
+    def __init__(self, task_heads: torch.nn.ModuleDict, video_encoder_ckpt_path: Optional[str] = None,
+                 window_size: Tuple[int, int, int] = (16, 224, 224), window_stride_T: int = 8,
+                 freeze_video_encoder: bool = False, freeze_heads: Optional[List[str]] = None,
+                 unfreeze_blocks: Optional[List[int]] = None, always_use_windowed_version: bool = False,
+                 joint_alignment: bool = False, cam_emb_placed_at_enc: Optional[str] = None, cam_emb_type: str = "add",
+                 compute_dtype: torch.dtype = torch.float16, max_windows_per_pass: int = 8, device=None) -> None:
+        super().__init__()
+        # Same hyper-parameters as the reference (l4p_videomae.py:163-186): ViT-giant, patch 14, tubelet 2.
+        self.video_encoder = VideoMAEEncoder(
+            img_size=224, patch_size=14, in_chans=3, num_classes=0, embed_dim=1408, depth=40, num_heads=16,
+            mlp_ratio=48 / 11, qkv_bias=True, qk_scale=None, drop_rate=0, attn_drop_rate=0, drop_path_rate=0,
+            norm_layer=partial(torch.nn.LayerNorm, eps=1e-6), init_values=0.0, tubelet_size=2,
+            use_learnable_pos_emb=False, with_cp=False, all_frames=16, cos_attn=False,
+            cam_emb_placed_at=cam_emb_placed_at_enc, cam_emb_type=cam_emb_type, compute_dtype=compute_dtype,
+            device=device)
+        if video_encoder_ckpt_path is not None:
+            print(f"Loading video model: {video_encoder_ckpt_path}")
+            ckpt = torch.load(video_encoder_ckpt_path, map_location="cpu", weights_only=True)
+            self.video_encoder.load_state_dict(ckpt, strict=False)
+            print("Successfully loaded video model")
+        self.task_heads = task_heads
+        self.window_size = window_size
+        self.window_stride_T = window_stride_T
+        self.always_use_windowed_version = always_use_windowed_version
+        self.joint_alignment = joint_alignment
+        self.max_windows_per_pass = max_windows_per_pass
+        self.set_compute_dtype(compute_dtype)
+        # freeze_* / unfreeze_blocks are training-only knobs: accepted for config compatibility, parameters of
+        # this inference-only implementation never require grad.
+
+    def set_compute_dtype(self, dtype: torch.dtype) -> None:
+        assert dtype in (torch.float16, torch.bfloat16)
+        self.compute_dtype = dtype
+        self.video_encoder.compute_dtype = dtype
+        self.video_encoder.invalidate()
+        for head in self.task_heads.values():
+            if hasattr(head, "compute_dtype"):
+                head.compute_dtype = dtype
+
+    def encode_features(self, data: Dict[str, Any]):
+        """Generates video encoder features for a single window (l4p_videomae.py:222-232)."""
+        return self.video_encoder(data["rgb_b3thw"])
+
+    def forward_single_window(self, data: Dict[str, Any], tasks: List[str]) -> Dict[str, Any]:
+        """l4p_videomae.py:234-254."""
+        enc_features_bpc_list = self.video_encoder(data["rgb_b3thw"])
+        out = {"enc_features_bpc_list": enc_features_bpc_list}
+        for task in tasks:
+            out.update(self.task_heads[task](enc_features_bpc_list=enc_features_bpc_list, **data))
+        return out
+
+    def _encode_windows(self, rgb: torch.Tensor, starts: List[int]):
+        """All windows of all clips as one encoder batch (window-major: index = w*B + b)."""
+        B = rgb.shape[0]
+        Tw = self.window_size[0]
+        wins = torch.cat([rgb[:, :, s:s + Tw] for s in starts], dim=0)  # [nW*B, 3, Tw, H, W]
+        n = wins.shape[0]
+        chunks: List[FeatureList] = []
+        for i in range(0, n, self.max_windows_per_pass):
+            chunks.append(self.video_encoder(wins[i:i + self.max_windows_per_pass]))
+        if len(chunks) == 1:
+            batched = chunks[0]
+        else:
+            L = len(chunks[0])
+            feats = [None if chunks[0][i] is None else torch.cat([c[i] for c in chunks], dim=0) for i in range(L)]
+            taps = {k: torch.cat([c.taps16[k] for c in chunks], dim=0) for k in chunks[0].taps16}
+            batched = FeatureList(feats, taps)
+        per_window = []
+        for w in range(len(starts)):
+            sl = slice(w * B, (w + 1) * B)
+            per_window.append([None if f is None else f[sl] for f in batched])
+        return batched, per_window
+
+    def forward(self, data: Dict[str, Any], tasks: List[str]) -> Dict[str, Any]:
+        """Main forward pass for both single and multi-window inference (l4p_videomae.py:256-330)."""
+        B, _, T, H, W = data["rgb_b3thw"].shape
+        assert H == self.window_size[1] and W == self.window_size[2], "Supports only fixed spatial size"
+        if (not self.always_use_windowed_version) and (T == self.window_size[0]):
+            return self.forward_single_window(data, tasks)
+        assert T % self.window_stride_T == 0, "Temporal window needs to be a multiple of window stride, for now!"
+        time_strides = torch.arange(0, T - self.window_size[0] + 1, self.window_stride_T)
+
+        batched, enc_features_bpc_2dlist = self._encode_windows(data["rgb_b3thw"], [int(s) for s in time_strides])
+        out: Dict[str, Any] = {"enc_features_bpc_2dlist": enc_features_bpc_2dlist}
+
+        joint_alignment_possible = "depth" in tasks and "camray" in tasks
+        if self.joint_alignment and joint_alignment_possible:
+            for task in ["track_2d", "dyn_mask", "flow_2d_backward"]:
+                if task in tasks:
+                    out.update(self.task_heads[task].forward_windowed(
+                        enc_features_bpc_2dlist=enc_features_bpc_2dlist, time_strides=time_strides,
+                        _batched_windows=batched, **data))
+            assert "depth" in tasks and "camray" in tasks, "Depth and camray must be present for joint alignment"
+            out.update(joint_windowed_estimation(["depth", "camray"], self.task_heads,
+                                                 enc_features_bpc_2dlist=enc_features_bpc_2dlist,
+                                                 time_strides=time_strides, _batched_windows=batched, **data))
+        else:
+            if self.joint_alignment:
+                print("Joint alignment is not possible as depth or camray tasks are not present")
+            for task in tasks:
+                out.update(self.task_heads[task].forward_windowed(
+                    enc_features_bpc_2dlist=enc_features_bpc_2dlist, time_strides=time_strides,
+                    _batched_windows=batched, **data))
+        return out

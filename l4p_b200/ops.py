@@ -84,7 +84,7 @@ def _epilogue(d: _l.GemmDesc, *, bias=None, act=_l.ACT_NONE, res_f32=None, res_1
 
 
 def linear(a: torch.Tensor, w: torch.Tensor, *, bias=None, act=_l.ACT_NONE, res_f32=None, res_16=None,
-           out_f32=None, out_16=None, out_16_relu=None, block_n: int = 0) -> None:
+           out_f32=None, out_16=None, out_16_relu=None, block_n: int = 0, res_row_mod: int = 0) -> None:
     """out[M,N] = act(a[M,K] @ w[N,K]^T + bias) (+ residual). Replaces F.linear/addmm call sites."""
     d = _base_desc(a, w)
     K = a.shape[-1]
@@ -97,6 +97,7 @@ def linear(a: torch.Tensor, w: torch.Tensor, *, bias=None, act=_l.ACT_NONE, res_
     d.a_mode = _l.A_MATRIX
     d.store_mode = _l.STORE_ROWMAJOR
     d.block_n = block_n
+    d.res_row_mod = res_row_mod
     _epilogue(d, bias=bias, act=act, res_f32=res_f32, res_16=res_16, out_f32=out_f32, out_16=out_16,
               out_16_relu=out_16_relu)
     _l.check(_l.load().l4p_gemm(C.byref(d), _stream()), "l4p_gemm(linear)")
@@ -213,3 +214,47 @@ def attention(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, out: torch.Ten
     _l.check(_l.load().l4p_attention(q.data_ptr(), k.data_ptr(), vt.data_ptr(), out.data_ptr(), B, H, N, head_dim,
                                      dpad, float(scale), 1 if q.dtype == torch.bfloat16 else 0, _stream()),
              "l4p_attention")
+
+
+def patchify(rgb: torch.Tensor, out16: torch.Tensor, tubelet: Tuple[int, int, int]) -> None:
+    """K1 gather: rgb fp32 [B,C,T,H,W] -> out16 [B*tokens, C*pt*ph*pw]."""
+    _dev_init(rgb)
+    _chk(rgb, "rgb", torch.float32); _chk(out16, "out16", sixteen=True)
+    B, Cc, T, H, W = rgb.shape
+    pt, ph, pw = tubelet
+    if out16.numel() != rgb.numel():
+        raise _l.L4PError("patchify: output size mismatch")
+    _l.check(_l.load().l4p_patchify(rgb.data_ptr(), out16.data_ptr(), B, Cc, T, H, W, pt, ph, pw,
+                                    1 if out16.dtype == torch.bfloat16 else 0, _stream()), "l4p_patchify")
+
+
+def cast16(x: torch.Tensor, y16: torch.Tensor) -> None:
+    _dev_init(x)
+    _chk(x, "x", torch.float32); _chk(y16, "y16", sixteen=True)
+    if x.numel() != y16.numel():
+        raise _l.L4PError("cast16: size mismatch")
+    _l.check(_l.load().l4p_cast16(x.data_ptr(), y16.data_ptr(), x.numel(), 1 if y16.dtype == torch.bfloat16 else 0,
+                                  _stream()), "l4p_cast16")
+
+
+def upsample3d(x: torch.Tensor, out_size: Tuple[int, int, int], *, align_corners: bool, y: Optional[torch.Tensor] = None,
+               y_relu: Optional[torch.Tensor] = None) -> None:
+    """K9: trilinear resampling of channels-last [B,T,H,W,C] 16-bit to out_size."""
+    _dev_init(x)
+    _chk(x, "x", sixteen=True); _chk(y, "y", sixteen=True); _chk(y_relu, "y_relu", sixteen=True)
+    B, Ti, Hi, Wi, Cc = x.shape
+    To, Ho, Wo = out_size
+    for t in (y, y_relu):
+        if t is not None and (t.numel() != B * To * Ho * Wo * Cc or t.dtype != x.dtype):
+            raise _l.L4PError("upsample3d: output size/dtype mismatch")
+    _l.check(_l.load().l4p_upsample3d(x.data_ptr(), _ptr(y), _ptr(y_relu), B, Ti, Hi, Wi, To, Ho, Wo, Cc,
+                                      int(align_corners), 1 if x.dtype == torch.bfloat16 else 0, _stream()),
+             "l4p_upsample3d")
+
+
+def im2col3(x: torch.Tensor, out: torch.Tensor, stride: Tuple[int, int, int]) -> None:
+    """3x3x3/pad-1 strided gather of channels-last x [B,T,H,W,C] into out [B*To*Ho*Wo, 27*C]."""
+    _dev_init(x)
+    _chk(x, "x", sixteen=True); _chk(out, "out", sixteen=True)
+    B, T, H, W, Cc = x.shape
+    _l.check(_l.load().l4p_im2col3(x.data_ptr(), out.data_ptr(), B, T, H, W, Cc, *stride, _stream()), "l4p_im2col3")

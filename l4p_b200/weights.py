@@ -1,0 +1,52 @@
+"""Deterministic synthetic weights, `w = f(seed, state_dict_key, shape)`.
+
+There is no network for the released checkpoint, so benchmarks and parity tests use random weights of the
+reference architecture. The generator is keyed on the *state-dict key*, so the reference model, the oracle
+and this package get bit-identical tensors without sharing any initialisation code.
+"""
+from __future__ import annotations
+
+import math
+import zlib
+from typing import Dict, Iterable, Tuple
+
+import torch
+
+
+def _gen(seed: int, key: str) -> torch.Generator:
+    g = torch.Generator(device="cpu")
+    g.manual_seed((zlib.crc32(key.encode()) ^ (seed * 0x9E3779B1)) & 0x7FFFFFFF)
+    return g
+
+
+def synth_tensor(key: str, shape: Tuple[int, ...], seed: int = 0, peaky: bool = False) -> torch.Tensor:
+    g = _gen(seed, key)
+    shape = tuple(shape)
+    if "positional_encoding_gaussian_matrix" in key:
+        return torch.randn(shape, generator=g)
+    if len(shape) >= 2:
+        recept = 1
+        for s in shape[2:]:
+            recept *= s
+        fan_in, fan_out = shape[1] * recept, shape[0] * recept
+        a = math.sqrt(6.0 / (fan_in + fan_out))
+        w = (torch.rand(shape, generator=g) * 2 - 1) * a
+        if peaky and key.endswith("attn.qkv.weight"):
+            w *= 4.0
+        return w
+    u = torch.rand(shape, generator=g) * 2 - 1
+    if key.endswith("weight"):  # norm scales
+        return 1.0 + 0.1 * u
+    return 0.05 * u  # biases
+
+
+def synth_state_dict(manifest: Iterable[Tuple[str, Tuple[int, ...]]], seed: int = 0,
+                     peaky: bool = False) -> Dict[str, torch.Tensor]:
+    return {k: synth_tensor(k, tuple(s), seed, peaky) for k, s in manifest}
+
+
+def fill_module_(module: torch.nn.Module, seed: int = 0, peaky: bool = False, prefix: str = "") -> None:
+    """In-place synthetic init of every state-dict entry (CPU generator -> copied to the tensor's device)."""
+    with torch.no_grad():
+        for k, t in module.state_dict().items():
+            t.copy_(synth_tensor(prefix + k, tuple(t.shape), seed, peaky).to(t.device))
