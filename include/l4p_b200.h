@@ -52,7 +52,8 @@ enum {
   L4P_STORE_ROWMAJOR = 0, /* out[row, col]                                                        */
   L4P_STORE_QKV = 1,      /* scatter to Q[B,H,N,dpad], K[B,H,N,dpad], Vt[B,H,dpad,N]                */
   L4P_STORE_CONVT = 2,    /* ConvTranspose3d(k == s) pixel-shuffle scatter to channels-last         */
-  L4P_STORE_HEAD1X1 = 3   /* ReLU -> 1x1x1 conv to <= 8 channels (+exp) -> fp32 NCTHW              */
+  L4P_STORE_HEAD1X1 = 3,  /* ReLU -> 1x1x1 conv to <= 8 channels (+exp) -> fp32 NCTHW              */
+  L4P_STORE_HYPER = 4     /* ConvT(k==s) tap -> act -> dot with per-group hyper vectors -> fp32 masks */
 };
 enum { L4P_A_MATRIX = 0, L4P_A_CONV3D = 1 };
 
@@ -89,6 +90,9 @@ typedef struct l4p_gemm_desc {
   int sT, sH, sW, ctCout;
   /* STORE_HEAD1X1: out_f32[b, c, t, h, w] = f(sum_n relu(acc+bias)[n] * w2[c, n] + b2[c]) */
   const float* w2; const float* b2; int c2; int exp_out;
+  /* STORE_HYPER (mask decoder, sam/mask_decoder.py:62-66,137-139): geometry as STORE_CONVT, block_n == ctCout;
+   * out_f32[g, c, t', h', w'] = sum_co act(acc+bias)[tap, co] * w2[g, c, co], g = row / rows_per_group, c < c2 <= 4 */
+  int64_t rows_per_group;
   int block_n;         /* N tile (multiple of 16, <= 256); 0 = choose                              */
 } l4p_gemm_desc;
 
@@ -114,6 +118,26 @@ int l4p_upsample3d(const void* x16, void* y16, void* y16_relu, int B, int Ti, in
  * with l4p_gemm this replaces the stride-2 Conv3d of the DPT reassemble stage (dpt_block.py:265-278). */
 int l4p_im2col3(const void* x16, void* out16, int B, int T, int H, int W, int C, int sT, int sH, int sW,
                 void* stream);
+
+/* ---- K13-K15: track head (SAM two-way transformer + mask decoder read-outs) -------------------- */
+/* Few queries x many keys: out[g,j,h*d+c] = softmax_k(scale * q[g,j,h,:].k[g,k,h,:]) v[g,k,h,c].
+ * q,out fp32 [G,nq<=8,H*d]; k16,v16 16-bit rows [.., H*d], group g starts at row g*kv_group_rows (0 = shared).
+ * Replaces Attention.forward for token->image and token self attention (sam/transformer.py:223-245). */
+int l4p_token_attention(const float* q, const void* k16, const void* v16, float* out, int G, int nq, int Nk,
+                        int H, int d, int64_t kv_group_rows, float scale, int bf16, void* stream);
+/* Many queries x few keys (image -> token cross attention, sam/transformer.py:179-184):
+ * q16,out16 16-bit [G*Np, H*d]; k,v fp32 [G,nk<=8,H*d]. This build: d == 88. */
+int l4p_image_attention(const void* q16, const float* k, const float* v, void* out16, int G, int Np, int nk,
+                        int H, int d, float scale, int bf16, void* stream);
+/* LayerNorm over the channels of 16-bit rows (+GELU): LayerNorm3d + activation of MaskDecoder.output_upscaling
+ * (sam/mask_decoder.py:58-66,145-157). */
+int l4p_layernorm16(const void* x16, const float* gamma, const float* beta, void* y16, int64_t rows, int cols,
+                    float eps, int gelu, int bf16, void* stream);
+/* masks fp32 [G,nch<=3,T,h,w] low-res logits -> bilinear (align_corners=False) to (H,W) fused with the
+ * read-outs: traj[G,2,T] = soft-argmax of channel 0 at pixel centres (+0.5), vis[G,1,T] = mean of channel 1,
+ * depth[G,1,T] = exp(mean of channel 2) (sparse_heads.py:140-160,574-589,645-647). */
+int l4p_track_readout(const float* masks, float* traj, float* vis, float* depth, int G, int nch, int T, int h,
+                      int w, int H, int W, void* stream);
 
 /* ---- K4: fused attention -------------------------------------------------------------------- */
 /* out[b*N+n, h*head_dim + c] = sum_m softmax_m(scale * q[b,h,n,:] . k[b,h,m,:]) * v[b,h,m,c]

@@ -52,6 +52,7 @@ struct GemmKParams {
   const float* w2;
   const float* b2;
   int c2, exp_out;
+  long long rows_per_group;  // STORE_HYPER: w2 is indexed by row / rows_per_group
 };
 
 struct TileCoord {
@@ -331,6 +332,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 make_uint4(pack2<BF16>(vv[0], vv[1]), pack2<BF16>(vv[2], vv[3]), pack2<BF16>(vv[4], vv[5]),
                            pack2<BF16>(vv[6], vv[7]));
           }
+        } else if (p.store_mode == L4P_STORE_HYPER) {
+          // v = act(acc + bias) of one ConvT tap (this N tile); dot with the per-query hyper-network vectors
+          const float* wg = p.w2 + (row / p.rows_per_group) * (long long)(p.c2 * p.ctCout) + c0;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            if (c < p.c2) {
+              const float* wr = wg + c * p.ctCout;
+              float a = head_acc[c];
+#pragma unroll
+              for (int i = 0; i < 16; i += 4) {
+                const float4 wv = *reinterpret_cast<const float4*>(wr + i);
+                a = fmaf(v[i], wv.x, a); a = fmaf(v[i + 1], wv.y, a);
+                a = fmaf(v[i + 2], wv.z, a); a = fmaf(v[i + 3], wv.w, a);
+              }
+              head_acc[c] = a;
+            }
+          }
         } else {  // L4P_STORE_HEAD1X1: v already bias+ReLU'd; accumulate the tiny second conv
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
@@ -353,6 +371,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       mbar_arrive(smem_u32(&bar_tempty[acc]));
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
 
+      if (p.store_mode == L4P_STORE_HYPER && row_ok) {
+        // row = input voxel (g,t,h,w) of the [cB,cT,cH,cW] grid; this N tile = tap (kt,kh,kw)
+        long long rr = row;
+        const int w_ = (int)(rr % p.cW); rr /= p.cW;
+        const int h_ = (int)(rr % p.cH); rr /= p.cH;
+        const int t_ = (int)(rr % p.cT); rr /= p.cT;
+        const long long g_ = rr;
+        const int tapi = tc.n_blk;
+        const int kw = tapi % p.sW, kh = (tapi / p.sW) % p.sH, kt = tapi / (p.sW * p.sH);
+        const long long oT = (long long)p.cT * p.sT, oH = (long long)p.cH * p.sH, oW = (long long)p.cW * p.sW;
+        const long long vox = ((long long)(t_ * p.sT + kt) * oH + (h_ * p.sH + kh)) * oW + (w_ * p.sW + kw);
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (c < p.c2) p.out_f32[((g_ * p.c2 + c) * oT * oH * oW) + vox] = head_acc[c];
+      }
       if (p.store_mode == L4P_STORE_HEAD1X1 && row_ok) {
         const long long plane = (long long)p.cT * p.cH * p.cW;
         const long long vox = ((long long)ct_ * p.cH + ch_) * p.cW + cw_;
@@ -495,6 +528,17 @@ extern "C" int l4p_gemm(const l4p_gemm_desc* d, void* stream_) {
       L4P_REQUIRE(d->out_f32 && d->w2 && d->b2 && d->c2 >= 1 && d->c2 <= 8, L4P_ERR_ARG, "l4p_gemm(head1x1): args");
       L4P_REQUIRE(p.tiles_n == 1, L4P_ERR_SHAPE, "l4p_gemm(head1x1): N=%lld must fit one tile", (long long)d->N);
       p.w2 = d->w2; p.b2 = d->b2; p.c2 = d->c2; p.exp_out = d->exp_out;
+      break;
+    case L4P_STORE_HYPER:
+      L4P_REQUIRE(d->out_f32 && d->w2 && d->c2 >= 1 && d->c2 <= 4, L4P_ERR_ARG, "l4p_gemm(hyper): args");
+      L4P_REQUIRE(d->ctCout % 16 == 0 && d->N == (int64_t)d->sT * d->sH * d->sW * d->ctCout, L4P_ERR_SHAPE,
+                  "l4p_gemm(hyper): N != sT*sH*sW*Cout");
+      L4P_REQUIRE(p.block_n == d->ctCout, L4P_ERR_SHAPE, "l4p_gemm(hyper): block_n must equal Cout (one tap per tile)");
+      L4P_REQUIRE(d->M == (int64_t)d->cB * d->cT * d->cH * d->cW && d->rows_per_group > 0, L4P_ERR_SHAPE,
+                  "l4p_gemm(hyper): M mismatch");
+      p.cB = d->cB; p.cT = d->cT; p.cH = d->cH; p.cW = d->cW;
+      p.sT = d->sT; p.sH = d->sH; p.sW = d->sW; p.ctCout = d->ctCout;
+      p.w2 = d->w2; p.c2 = d->c2; p.rows_per_group = d->rows_per_group;
       break;
     default:
       return host_set_error(L4P_ERR_ARG, "l4p_gemm: store_mode=%d", d->store_mode);

@@ -1,0 +1,406 @@
+// Track-head kernels (K13-K15): the token<->image attentions of SAM's two-way transformer are extremely
+// skinny (6 prompt tokens per query against 2048 video tokens), so they run on CUDA cores and are HBM-bound
+// on the per-query K/V/Q projections; the big projections themselves go through the tcgen05 GEMM (gemm.cu).
+//
+//   l4p_token_attention   few queries x many keys   (sam/transformer.py:223-245 as used at :163-171,104-107,
+//                         and the 6x6 token self-attention :157-161)
+//   l4p_image_attention   many queries x few keys   (image -> token cross attention, :179-184)
+//   l4p_layernorm16       channel LayerNorm on 16-bit rows with optional GELU (LayerNorm3d + GELU of the mask
+//                         decoder's upscaling path, sam/mask_decoder.py:58-66,145-157)
+//   l4p_track_readout     fused trilinear upsample (align_corners=False) of the low-res mask logits to the image
+//                         size + soft-argmax / visibility mean / depth exp-mean (sparse_heads.py:140-160,574-589,
+//                         645-647): the [Nq,3,16,224,224] logits (1.2 GB at Nq=128) never exist in HBM.
+#include "common.cuh"
+
+namespace l4p {
+
+constexpr int kTokMaxQ = 8;     // prompt tokens per group (6 used)
+constexpr int kTokMaxPairs = 3; // channel pairs per lane: head_dim <= 192
+
+// ------------------------------------------------------------------------------------------------
+// q fp32 [G, nq, ldq] ; k16/v16 rows [.., ldkv] 16-bit, group g starts at row g*kv_group_rows (0 = shared) ;
+// out fp32 [G, nq, ldq]. grid (H, G), 256 threads, dynamic smem: nq*Nk floats (scores) + nq*d (q) + 8*nq*d (partials)
+// ------------------------------------------------------------------------------------------------
+template <bool BF16>
+__global__ void __launch_bounds__(256)
+token_attention_kernel(const float* __restrict__ q, const uint16_t* __restrict__ k16, const uint16_t* __restrict__ v16,
+                       float* __restrict__ out, int nq, int Nk, int d, int ldq, int ldkv, long long kv_group_rows,
+                       float scale) {
+  extern __shared__ float sm[];
+  float* s_scores = sm;                    // [nq][Nk]
+  float* s_q = s_scores + nq * Nk;         // [nq][d]
+  float* s_part = s_q + nq * d;            // [8][nq][d]
+  __shared__ float s_max[kTokMaxQ], s_sum[kTokMaxQ];
+  const int h = blockIdx.x, g = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* qg = q + ((long long)g * nq) * ldq + h * d;
+  const uint16_t* kg = k16 + (long long)g * kv_group_rows * ldkv + h * d;
+  const uint16_t* vg = v16 + (long long)g * kv_group_rows * ldkv + h * d;
+  for (int i = tid; i < nq * d; i += blockDim.x) s_q[i] = qg[(i / d) * ldq + (i % d)] * scale;
+  __syncthreads();
+  // pass 1: one key per thread, d multiple of 8 (16-byte chunks)
+  for (int key = tid; key < Nk; key += blockDim.x) {
+    float acc[kTokMaxQ];
+#pragma unroll
+    for (int j = 0; j < kTokMaxQ; ++j) acc[j] = 0.f;
+    const uint4* kr = reinterpret_cast<const uint4*>(kg + (long long)key * ldkv);
+    for (int c8 = 0; c8 < d / 8; ++c8) {
+      const uint4 raw = kr[c8];
+      const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+      float kv[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = unpack2<BF16>(w[i]);
+        kv[2 * i] = f.x; kv[2 * i + 1] = f.y;
+      }
+#pragma unroll
+      for (int j = 0; j < kTokMaxQ; ++j) {
+        if (j < nq) {
+          const float* qq = s_q + j * d + c8 * 8;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[j] = fmaf(kv[i], qq[i], acc[j]);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kTokMaxQ; ++j)
+      if (j < nq) s_scores[j * Nk + key] = acc[j];
+  }
+  __syncthreads();
+  // softmax statistics: warp j handles query row j
+  if (warp < nq) {
+    float m = -INFINITY;
+    for (int key = lane; key < Nk; key += 32) m = fmaxf(m, s_scores[warp * Nk + key]);
+    m = warp_max(m);
+    float s = 0.f;
+    for (int key = lane; key < Nk; key += 32) {
+      const float p = __expf(s_scores[warp * Nk + key] - m);
+      s_scores[warp * Nk + key] = p;
+      s += p;
+    }
+    s = warp_sum(s);
+    if (lane == 0) { s_max[warp] = m; s_sum[warp] = s; }
+  }
+  __syncthreads();
+  // pass 2: each warp takes a strided subset of keys, lanes cover channel pairs
+  float o[kTokMaxQ][kTokMaxPairs][2];
+#pragma unroll
+  for (int j = 0; j < kTokMaxQ; ++j)
+#pragma unroll
+    for (int c = 0; c < kTokMaxPairs; ++c) o[j][c][0] = o[j][c][1] = 0.f;
+  const int npairs = d / 2;
+  for (int key = warp; key < Nk; key += 8) {
+    const uint32_t* vr = reinterpret_cast<const uint32_t*>(vg + (long long)key * ldkv);
+#pragma unroll
+    for (int c = 0; c < kTokMaxPairs; ++c) {
+      const int cp = lane + c * 32;
+      if (cp < npairs) {
+        const float2 f = unpack2<BF16>(vr[cp]);
+#pragma unroll
+        for (int j = 0; j < kTokMaxQ; ++j) {
+          if (j < nq) {
+            const float p = s_scores[j * Nk + key];
+            o[j][c][0] = fmaf(p, f.x, o[j][c][0]);
+            o[j][c][1] = fmaf(p, f.y, o[j][c][1]);
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < kTokMaxQ; ++j)
+    if (j < nq)
+#pragma unroll
+      for (int c = 0; c < kTokMaxPairs; ++c) {
+        const int cp = lane + c * 32;
+        if (cp < npairs) {
+          s_part[(warp * nq + j) * d + 2 * cp] = o[j][c][0];
+          s_part[(warp * nq + j) * d + 2 * cp + 1] = o[j][c][1];
+        }
+      }
+  __syncthreads();
+  for (int i = tid; i < nq * d; i += blockDim.x) {
+    const int j = i / d;
+    float a = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) a += s_part[(w * nq + j) * d + (i % d)];
+    out[((long long)g * nq + j) * ldq + h * d + (i % d)] = a / s_sum[j];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// q16 [G*Np, H*d] ; k,v fp32 [G, nk, H*d] ; out16 [G*Np, H*d]. One thread per (row, head); block = rows_per_block x H.
+// ------------------------------------------------------------------------------------------------
+template <bool BF16, int D>
+__global__ void __launch_bounds__(256)
+image_attention_kernel(const uint16_t* __restrict__ q16, const float* __restrict__ kf, const float* __restrict__ vf,
+                       uint16_t* __restrict__ out16, int Np, int nk, int H, float scale, int rows_per_block) {
+  extern __shared__ float sm[];  // k [nk][H*D], v [nk][H*D]
+  const int ld = H * D;
+  const long long row0 = (long long)blockIdx.x * rows_per_block;
+  const int g = (int)(row0 / Np);
+  float* s_k = sm;
+  float* s_v = sm + nk * ld;
+  for (int i = threadIdx.x; i < nk * ld; i += blockDim.x) {
+    s_k[i] = kf[(long long)g * nk * ld + i] * scale;
+    s_v[i] = vf[(long long)g * nk * ld + i];
+  }
+  __syncthreads();
+  const int h = threadIdx.x % H;
+  const int rsub = threadIdx.x / H;
+  const int rstep = blockDim.x / H;
+  for (int rr = rsub; rr < rows_per_block; rr += rstep) {
+    const long long row = row0 + rr;
+    const uint4* qr = reinterpret_cast<const uint4*>(q16 + row * ld + h * D);
+    float qv[D];
+#pragma unroll
+    for (int c8 = 0; c8 < D / 8; ++c8) {
+      const uint4 raw = qr[c8];
+      const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = unpack2<BF16>(w[i]);
+        qv[c8 * 8 + 2 * i] = f.x; qv[c8 * 8 + 2 * i + 1] = f.y;
+      }
+    }
+    float sc[kTokMaxQ];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < kTokMaxQ; ++j) {
+      sc[j] = -INFINITY;
+      if (j < nk) {
+        const float* kk = s_k + j * ld + h * D;
+        float a = 0.f;
+#pragma unroll
+        for (int c = 0; c < D; ++c) a = fmaf(qv[c], kk[c], a);
+        sc[j] = a;
+        mx = fmaxf(mx, a);
+      }
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < kTokMaxQ; ++j) {
+      sc[j] = j < nk ? __expf(sc[j] - mx) : 0.f;
+      sum += sc[j];
+    }
+    const float inv = 1.f / sum;
+#pragma unroll
+    for (int c = 0; c < D; ++c) qv[c] = 0.f;
+#pragma unroll
+    for (int j = 0; j < kTokMaxQ; ++j) {
+      if (j < nk) {
+        const float p = sc[j] * inv;
+        const float* vv = s_v + j * ld + h * D;
+#pragma unroll
+        for (int c = 0; c < D; ++c) qv[c] = fmaf(p, vv[c], qv[c]);
+      }
+    }
+    uint4* orow = reinterpret_cast<uint4*>(out16 + row * ld + h * D);
+#pragma unroll
+    for (int c8 = 0; c8 < D / 8; ++c8)
+      orow[c8] = make_uint4(pack2<BF16>(qv[c8 * 8], qv[c8 * 8 + 1]), pack2<BF16>(qv[c8 * 8 + 2], qv[c8 * 8 + 3]),
+                            pack2<BF16>(qv[c8 * 8 + 4], qv[c8 * 8 + 5]), pack2<BF16>(qv[c8 * 8 + 6], qv[c8 * 8 + 7]));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm over 16-bit rows (+ optional GELU), one warp per row, cols multiple of 8 and <= 2048.
+// ------------------------------------------------------------------------------------------------
+template <bool BF16>
+__global__ void __launch_bounds__(256)
+layernorm16_kernel(const uint16_t* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                   uint16_t* __restrict__ y, long long rows, int cols, float eps, int gelu) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+  if (row >= rows) return;
+  const int nch = cols >> 3;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + row * cols);
+  float v[8][8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int j = lane + i * 32;
+    if (j < nch) {
+      const uint4 raw = xr[j];
+      const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float2 f = unpack2<BF16>(w[t]);
+        v[i][2 * t] = f.x; v[i][2 * t + 1] = f.y;
+        s += f.x + f.y;
+      }
+    }
+  }
+  const float mean = warp_sum(s) / (float)cols;
+  float qq = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int j = lane + i * 32;
+    if (j < nch)
+#pragma unroll
+      for (int t = 0; t < 8; ++t) { const float dlt = v[i][t] - mean; qq += dlt * dlt; }
+  }
+  const float rstd = rsqrtf(warp_sum(qq) / (float)cols + eps);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int j = lane + i * 32;
+    if (j < nch) {
+      float o[8];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        o[t] = (v[i][t] - mean) * rstd * gamma[j * 8 + t] + beta[j * 8 + t];
+        if (gelu) o[t] = gelu_erf(o[t]);
+      }
+      reinterpret_cast<uint4*>(y + row * cols)[j] = make_uint4(pack2<BF16>(o[0], o[1]), pack2<BF16>(o[2], o[3]),
+                                                               pack2<BF16>(o[4], o[5]), pack2<BF16>(o[6], o[7]));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// masks fp32 [G, 3, T, h, w] (low-res logits) -> traj [G,2,T], vis [G,1,T], depth [G,1,T]. One block per (g,t).
+// Spatial bilinear upsample to (H,W) with align_corners=False; T is not resampled (T_in == T_out).
+// ------------------------------------------------------------------------------------------------
+L4P_DEVICE float bilerp(const float* s, int h, int w, int y, int x, int H, int W) {
+  float sy = ((float)y + 0.5f) * ((float)h / (float)H) - 0.5f;
+  float sx = ((float)x + 0.5f) * ((float)w / (float)W) - 0.5f;
+  sy = sy < 0.f ? 0.f : sy;
+  sx = sx < 0.f ? 0.f : sx;
+  const int y0 = (int)sy, x0 = (int)sx;
+  const int y1 = y0 + 1 < h ? y0 + 1 : h - 1, x1 = x0 + 1 < w ? x0 + 1 : w - 1;
+  const float wy = sy - (float)y0, wx = sx - (float)x0;
+  const float a = s[y0 * w + x0], b = s[y0 * w + x1], c = s[y1 * w + x0], d = s[y1 * w + x1];
+  return (1.f - wy) * ((1.f - wx) * a + wx * b) + wy * ((1.f - wx) * c + wx * d);
+}
+
+__global__ void __launch_bounds__(256)
+track_readout_kernel(const float* __restrict__ masks, float* __restrict__ traj, float* __restrict__ vis,
+                     float* __restrict__ depth, int T, int h, int w, int H, int W, int has_vis, int has_depth,
+                     int nch) {
+  extern __shared__ float sm[];  // [h*w]
+  __shared__ float red[4 * 32];
+  const int g = blockIdx.x / T, t = blockIdx.x % T;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int npix = H * W;
+  for (int ch = 0; ch < nch; ++ch) {
+    const float* src = masks + (((long long)g * nch + ch) * T + t) * (long long)(h * w);
+    __syncthreads();
+    for (int i = threadIdx.x; i < h * w; i += blockDim.x) sm[i] = src[i];
+    __syncthreads();
+    if (ch == 0) {
+      // online soft-argmax: per-thread (m, s, sx, sy), merged across the block
+      float m = -INFINITY, s = 0.f, sx = 0.f, sy = 0.f;
+      for (int p = threadIdx.x; p < npix; p += blockDim.x) {
+        const int y = p / W, x = p - y * W;
+        const float v = bilerp(sm, h, w, y, x, H, W);
+        if (v > m) {
+          const float r = __expf(m - v);
+          s *= r; sx *= r; sy *= r;
+          m = v;
+        }
+        const float e = __expf(v - m);
+        s += e;
+        sx = fmaf(e, (float)x + 0.5f, sx);
+        sy = fmaf(e, (float)y + 0.5f, sy);
+      }
+      const float bm = warp_max(m);
+      const float r = (m == -INFINITY) ? 0.f : __expf(m - bm);
+      s = warp_sum(s * r); sx = warp_sum(sx * r); sy = warp_sum(sy * r);
+      if (lane == 0) { red[warp] = bm; red[32 + warp] = s; red[64 + warp] = sx; red[96 + warp] = sy; }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        float gm = -INFINITY;
+        for (int i = 0; i < nwarps; ++i) gm = fmaxf(gm, red[i]);
+        float ts = 0.f, tx = 0.f, ty = 0.f;
+        for (int i = 0; i < nwarps; ++i) {
+          const float rr = __expf(red[i] - gm);
+          ts += red[32 + i] * rr; tx += red[64 + i] * rr; ty += red[96 + i] * rr;
+        }
+        traj[((long long)g * 2 + 0) * T + t] = tx / ts;
+        traj[((long long)g * 2 + 1) * T + t] = ty / ts;
+      }
+    } else {
+      float a = 0.f;
+      for (int p = threadIdx.x; p < npix; p += blockDim.x) {
+        const int y = p / W, x = p - y * W;
+        a += bilerp(sm, h, w, y, x, H, W);
+      }
+      a = warp_sum(a);
+      if (lane == 0) red[warp] = a;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        float tot = 0.f;
+        for (int i = 0; i < nwarps; ++i) tot += red[i];
+        const float mean = tot / (float)npix;
+        if (ch == 1 && has_vis) vis[(long long)g * T + t] = mean;
+        else if (has_depth) depth[(long long)g * T + t] = expf(mean);
+      }
+    }
+  }
+}
+
+}  // namespace l4p
+
+using namespace l4p;
+
+extern "C" int l4p_token_attention(const float* q, const void* k16, const void* v16, float* out, int G, int nq, int Nk,
+                                   int H, int d, int64_t kv_group_rows, float scale, int bf16, void* stream) {
+  L4P_REQUIRE(q && k16 && v16 && out, L4P_ERR_ARG, "l4p_token_attention: null pointer");
+  L4P_REQUIRE(G > 0 && nq > 0 && nq <= kTokMaxQ && Nk > 0 && H > 0 && d % 8 == 0 && d <= 64 * kTokMaxPairs, L4P_ERR_SHAPE,
+              "l4p_token_attention: nq=%d (<=8) Nk=%d d=%d (multiple of 8, <=192)", nq, Nk, d);
+  const size_t smem = sizeof(float) * ((size_t)nq * Nk + (size_t)nq * d + 8 * (size_t)nq * d);
+  L4P_REQUIRE(smem <= 200 * 1024, L4P_ERR_SHAPE, "l4p_token_attention: Nk=%d too large", Nk);
+  auto kfn = bf16 ? token_attention_kernel<true> : token_attention_kernel<false>;
+  L4P_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  kfn<<<dim3(H, G), 256, smem, (cudaStream_t)stream>>>(q, (const uint16_t*)k16, (const uint16_t*)v16, out, nq, Nk, d, H * d,
+                                                       H * d, kv_group_rows, scale);
+  L4P_CHECK_CUDA(cudaGetLastError());
+  return L4P_OK;
+}
+
+extern "C" int l4p_image_attention(const void* q16, const float* k, const float* v, void* out16, int G, int Np, int nk,
+                                   int H, int d, float scale, int bf16, void* stream) {
+  L4P_REQUIRE(q16 && k && v && out16, L4P_ERR_ARG, "l4p_image_attention: null pointer");
+  L4P_REQUIRE(d == 88, L4P_ERR_SHAPE, "l4p_image_attention: head_dim=%d (this build: 88)", d);
+  L4P_REQUIRE(G > 0 && nk > 0 && nk <= kTokMaxQ && H > 0 && 256 % H == 0, L4P_ERR_SHAPE, "l4p_image_attention: nk=%d H=%d", nk, H);
+  const int rows_per_block = 128;
+  L4P_REQUIRE(Np % rows_per_block == 0, L4P_ERR_SHAPE, "l4p_image_attention: Np=%d must be a multiple of %d", Np, rows_per_block);
+  const size_t smem = sizeof(float) * 2 * (size_t)nk * H * d;
+  const unsigned grid = (unsigned)(((long long)G * Np) / rows_per_block);
+  if (bf16) {
+    L4P_CHECK_CUDA(cudaFuncSetAttribute(image_attention_kernel<true, 88>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    image_attention_kernel<true, 88><<<grid, 256, smem, (cudaStream_t)stream>>>((const uint16_t*)q16, k, v, (uint16_t*)out16, Np, nk, H, scale, rows_per_block);
+  } else {
+    L4P_CHECK_CUDA(cudaFuncSetAttribute(image_attention_kernel<false, 88>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    image_attention_kernel<false, 88><<<grid, 256, smem, (cudaStream_t)stream>>>((const uint16_t*)q16, k, v, (uint16_t*)out16, Np, nk, H, scale, rows_per_block);
+  }
+  L4P_CHECK_CUDA(cudaGetLastError());
+  return L4P_OK;
+}
+
+extern "C" int l4p_layernorm16(const void* x16, const float* gamma, const float* beta, void* y16, int64_t rows, int cols,
+                               float eps, int gelu, int bf16, void* stream) {
+  L4P_REQUIRE(x16 && gamma && beta && y16, L4P_ERR_ARG, "l4p_layernorm16: null pointer");
+  L4P_REQUIRE(rows >= 0 && cols > 0 && cols % 8 == 0 && cols <= 2048, L4P_ERR_SHAPE, "l4p_layernorm16: cols=%d", cols);
+  if (rows == 0) return L4P_OK;
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  if (bf16)
+    layernorm16_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>((const uint16_t*)x16, gamma, beta, (uint16_t*)y16, rows, cols, eps, gelu);
+  else
+    layernorm16_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>((const uint16_t*)x16, gamma, beta, (uint16_t*)y16, rows, cols, eps, gelu);
+  L4P_CHECK_CUDA(cudaGetLastError());
+  return L4P_OK;
+}
+
+extern "C" int l4p_track_readout(const float* masks, float* traj, float* vis, float* depth, int G, int nch, int T, int h,
+                                 int w, int H, int W, void* stream) {
+  L4P_REQUIRE(masks && traj, L4P_ERR_ARG, "l4p_track_readout: null pointer");
+  L4P_REQUIRE(G > 0 && nch >= 1 && nch <= 3 && T > 0 && h > 0 && w > 0 && H > 0 && W > 0 && (size_t)h * w * 4 <= 160 * 1024,
+              L4P_ERR_SHAPE, "l4p_track_readout: bad shape");
+  L4P_REQUIRE((nch < 2 || vis) && (nch < 3 || depth), L4P_ERR_ARG, "l4p_track_readout: missing output");
+  L4P_CHECK_CUDA(cudaFuncSetAttribute(track_readout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  track_readout_kernel<<<G * T, 256, (size_t)h * w * 4, (cudaStream_t)stream>>>(masks, traj, vis, depth, T, h, w, H, W,
+                                                                                nch >= 2, nch >= 3, nch);
+  L4P_CHECK_CUDA(cudaGetLastError());
+  return L4P_OK;
+}

@@ -13,7 +13,7 @@ _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "libl4p_b200.so"
 
 ACT_NONE, ACT_GELU, ACT_RELU, ACT_EXP = 0, 1, 2, 3
-STORE_ROWMAJOR, STORE_QKV, STORE_CONVT, STORE_HEAD1X1 = 0, 1, 2, 3
+STORE_ROWMAJOR, STORE_QKV, STORE_CONVT, STORE_HEAD1X1, STORE_HYPER = 0, 1, 2, 3, 4
 A_MATRIX, A_CONV3D = 0, 1
 
 
@@ -41,6 +41,7 @@ class GemmDesc(C.Structure):
         ("heads", C.c_int), ("head_dim", C.c_int), ("head_dim_pad", C.c_int), ("tokens", C.c_int),
         ("sT", C.c_int), ("sH", C.c_int), ("sW", C.c_int), ("ctCout", C.c_int),
         ("w2", C.c_void_p), ("b2", C.c_void_p), ("c2", C.c_int), ("exp_out", C.c_int),
+        ("rows_per_group", C.c_int64),
         ("block_n", C.c_int),
     ]
 
@@ -62,6 +63,10 @@ _SIGNATURES = {
     "l4p_affine_align_solve": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int,
                                          C.c_void_p, C.c_void_p, C.c_void_p]),
     "l4p_affine_align_apply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p]),
+    "l4p_token_attention": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 5 + [C.c_int64, C.c_float, C.c_int, C.c_void_p]),
+    "l4p_image_attention": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 5 + [C.c_float, C.c_int, C.c_void_p]),
+    "l4p_layernorm16": (C.c_int, [C.c_void_p] * 4 + [C.c_int64, C.c_int, C.c_float, C.c_int, C.c_int, C.c_void_p]),
+    "l4p_track_readout": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 7 + [C.c_void_p]),
     "l4p_attention": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                 C.c_int, C.c_float, C.c_int, C.c_void_p]),
 }

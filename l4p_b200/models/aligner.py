@@ -8,6 +8,8 @@ from typing import Optional
 import torch
 
 from .. import lib as _l
+from .. import ops as _ops
+from .. import ops as _ops
 from ..ops import _dev_init, _stream
 
 
@@ -44,6 +46,7 @@ class LstSqAffineAligner(WindowOverlapAligner):
         self.sol = torch.empty(bs, 2, device=p.device, dtype=torch.float32)
         _l.check(_l.load().l4p_affine_align_solve(p.data_ptr(), t.data_ptr(), bs, n, n, n, self.inverse, ws.data_ptr(),
                                                   self.sol.data_ptr(), _stream()), "l4p_affine_align_solve")
+        _ops._count(2)
 
     def apply(self, pred):
         bs = pred.shape[0]
@@ -51,6 +54,7 @@ class LstSqAffineAligner(WindowOverlapAligner):
         y = torch.empty_like(x)
         _l.check(_l.load().l4p_affine_align_apply(x.data_ptr(), y.data_ptr(), self.sol.data_ptr(), bs, x.shape[1],
                                                   self.inverse, _stream()), "l4p_affine_align_apply")
+        _ops._count(1)
         return y.reshape(pred.shape).to(pred.dtype)
 
 

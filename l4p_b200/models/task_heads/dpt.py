@@ -93,6 +93,7 @@ class DPTOutputAdapter_fix(nn.Module):
                   1: _reassemble_op(layer_dims[i], layer_dims[i], self.actpost_scale_factors[i], device)})
             for i in range(4)])
         self._packed: Optional[Dict[str, object]] = None
+        self.debug: Optional[Dict[str, torch.Tensor]] = None  # set to {} to capture intermediates (tests)
         self.register_load_state_dict_post_hook(lambda m, k: m.invalidate())
 
     def invalidate(self) -> None:
@@ -228,6 +229,10 @@ class DPTOutputAdapter_fix(nn.Module):
         p1 = self._fuse(f1, p2, None, layers[0], layers_relu[0])
         h1 = torch.empty(*p1.shape[:4], self.feature_dim // 2, device=dev, dtype=dt)
         ops.conv3d(p1, pk["h1w"], ksize=(3, 3, 3), bias=pk["h1b"], out_16=h1)
+        if self.debug is not None:
+            cf = lambda t: t.float().permute(0, 4, 1, 2, 3)
+            self.debug.update(l0=cf(layers[0]), l1=cf(layers[1]), l2=cf(layers[2]), l3=cf(layers[3]), p4=cf(p4), p3=cf(p3),
+                              p2=cf(p2), p1=cf(p1), h1=cf(h1))
         osz = tuple(image_size) if self.output_size is None else self.output_size
         if tuple(h1.shape[1:4]) != osz:
             r = torch.empty(B, *osz, h1.shape[-1], device=dev, dtype=dt)

@@ -14,6 +14,10 @@ from . import lib as _l
 
 _initialised = set()
 
+# --- instrumentation used by bench.py (never changes results) ------------------------------------------
+LAUNCHES = 0            # kernels launched through this module since import (bench.py reports the delta)
+ATTN_EVENTS = None      # set to a list to record (start, end) CUDA events around every attention launch
+
 
 def _dev_init(t: torch.Tensor) -> None:
     if not t.is_cuda:
@@ -26,6 +30,11 @@ def _dev_init(t: torch.Tensor) -> None:
 
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
+
+
+def _count(n: int = 1) -> None:
+    global LAUNCHES
+    LAUNCHES += n
 
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -58,6 +67,7 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
     bf16 = 1 if (out16 is not None and out16.dtype == torch.bfloat16) else 0
     _l.check(_l.load().l4p_layernorm(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(out16), _ptr(out32), rows, cols,
                                      float(eps), bf16, _stream()), "l4p_layernorm")
+    _count()
 
 
 def _base_desc(a: torch.Tensor, w: torch.Tensor) -> _l.GemmDesc:
@@ -101,6 +111,7 @@ def linear(a: torch.Tensor, w: torch.Tensor, *, bias=None, act=_l.ACT_NONE, res_
     _epilogue(d, bias=bias, act=act, res_f32=res_f32, res_16=res_16, out_f32=out_f32, out_16=out_16,
               out_16_relu=out_16_relu)
     _l.check(_l.load().l4p_gemm(C.byref(d), _stream()), "l4p_gemm(linear)")
+    _count()
 
 
 def linear_qkv(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, q: torch.Tensor, k: torch.Tensor,
@@ -125,6 +136,7 @@ def linear_qkv(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, q: torch.Te
     d.heads, d.head_dim, d.head_dim_pad, d.tokens = heads, head_dim, q.shape[-1], tokens
     d.block_n = block_n
     _l.check(_l.load().l4p_gemm(C.byref(d), _stream()), "l4p_gemm(qkv)")
+    _count()
 
 
 def pick_box(T: int, H: int, W: int) -> Tuple[int, int, int]:
@@ -174,6 +186,7 @@ def conv3d(x: torch.Tensor, w: torch.Tensor, *, ksize: Tuple[int, int, int], bia
         _epilogue(d, bias=bias, act=act, res_16=res_16, res2_16=res2_16, out_f32=out_f32, out_16=out_16,
                   out_16_relu=out_16_relu)
     _l.check(_l.load().l4p_gemm(C.byref(d), _stream()), "l4p_gemm(conv3d)")
+    _count()
 
 
 def conv_transpose3d(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, stride: Tuple[int, int, int],
@@ -196,6 +209,7 @@ def conv_transpose3d(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, strid
     d.bias = _ptr(bias); d.out_16 = out_16.data_ptr()
     d.block_n = block_n
     _l.check(_l.load().l4p_gemm(C.byref(d), _stream()), "l4p_gemm(convT)")
+    _count()
 
 
 def attention(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, out: torch.Tensor, head_dim: int,
@@ -211,9 +225,17 @@ def attention(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, out: torch.Ten
         raise _l.L4PError(f"attention: shapes q{tuple(q.shape)} k{tuple(k.shape)} vt{tuple(vt.shape)}")
     if out.numel() != B * N * H * head_dim:
         raise _l.L4PError(f"attention: out has {out.numel()} elements, expected {B * N * H * head_dim}")
+    ev = None
+    if ATTN_EVENTS is not None:
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
     _l.check(_l.load().l4p_attention(q.data_ptr(), k.data_ptr(), vt.data_ptr(), out.data_ptr(), B, H, N, head_dim,
                                      dpad, float(scale), 1 if q.dtype == torch.bfloat16 else 0, _stream()),
              "l4p_attention")
+    if ev is not None:
+        ev[1].record()
+        ATTN_EVENTS.append((ev[0], ev[1], B * H * N * N * head_dim * 4))
+    _count()
 
 
 def patchify(rgb: torch.Tensor, out16: torch.Tensor, tubelet: Tuple[int, int, int]) -> None:
@@ -226,6 +248,7 @@ def patchify(rgb: torch.Tensor, out16: torch.Tensor, tubelet: Tuple[int, int, in
         raise _l.L4PError("patchify: output size mismatch")
     _l.check(_l.load().l4p_patchify(rgb.data_ptr(), out16.data_ptr(), B, Cc, T, H, W, pt, ph, pw,
                                     1 if out16.dtype == torch.bfloat16 else 0, _stream()), "l4p_patchify")
+    _count()
 
 
 def cast16(x: torch.Tensor, y16: torch.Tensor) -> None:
@@ -235,6 +258,7 @@ def cast16(x: torch.Tensor, y16: torch.Tensor) -> None:
         raise _l.L4PError("cast16: size mismatch")
     _l.check(_l.load().l4p_cast16(x.data_ptr(), y16.data_ptr(), x.numel(), 1 if y16.dtype == torch.bfloat16 else 0,
                                   _stream()), "l4p_cast16")
+    _count()
 
 
 def upsample3d(x: torch.Tensor, out_size: Tuple[int, int, int], *, align_corners: bool, y: Optional[torch.Tensor] = None,
@@ -250,6 +274,7 @@ def upsample3d(x: torch.Tensor, out_size: Tuple[int, int, int], *, align_corners
     _l.check(_l.load().l4p_upsample3d(x.data_ptr(), _ptr(y), _ptr(y_relu), B, Ti, Hi, Wi, To, Ho, Wo, Cc,
                                       int(align_corners), 1 if x.dtype == torch.bfloat16 else 0, _stream()),
              "l4p_upsample3d")
+    _count()
 
 
 def im2col3(x: torch.Tensor, out: torch.Tensor, stride: Tuple[int, int, int]) -> None:
@@ -258,3 +283,85 @@ def im2col3(x: torch.Tensor, out: torch.Tensor, stride: Tuple[int, int, int]) ->
     _chk(x, "x", sixteen=True); _chk(out, "out", sixteen=True)
     B, T, H, W, Cc = x.shape
     _l.check(_l.load().l4p_im2col3(x.data_ptr(), out.data_ptr(), B, T, H, W, Cc, *stride, _stream()), "l4p_im2col3")
+    _count()
+
+
+def conv_transpose3d_hyper(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, stride: Tuple[int, int, int],
+                           hyper: torch.Tensor, out_f32: torch.Tensor, act=_l.ACT_GELU) -> None:
+    """K14: last ConvTranspose3d of the mask decoder fused with its activation and the hyper-network dot.
+
+    x channels-last [G,T,H,W,Cin]; w [sT*sH*sW*Cout, Cin] rows (kt,kh,kw,co); bias tiled likewise;
+    hyper fp32 [G, c2, Cout]; out_f32 [G, c2, T*sT, H*sH, W*sW]."""
+    d = _base_desc(x, w)
+    G, T, H, W, Cin = x.shape
+    sT, sH, sW = stride
+    Cout = w.shape[0] // (sT * sH * sW)
+    _chk(bias, "bias", torch.float32); _chk(hyper, "hyper", torch.float32); _chk(out_f32, "out_f32", torch.float32)
+    if tuple(hyper.shape) != (G, hyper.shape[1], Cout) or out_f32.numel() != G * hyper.shape[1] * T * sT * H * sH * W * sW:
+        raise _l.L4PError("conv_transpose3d_hyper: shape mismatch")
+    d.M, d.N, d.K = G * T * H * W, w.shape[0], Cin
+    d.lda, d.ldw = Cin, Cin
+    d.a_mode = _l.A_MATRIX
+    d.store_mode = _l.STORE_HYPER
+    d.cB, d.cT, d.cH, d.cW = G, T, H, W
+    d.sT, d.sH, d.sW, d.ctCout = sT, sH, sW, Cout
+    d.bias = _ptr(bias); d.act = act
+    d.w2 = hyper.data_ptr(); d.c2 = hyper.shape[1]
+    d.rows_per_group = T * H * W
+    d.out_f32 = out_f32.data_ptr()
+    d.block_n = Cout
+    _l.check(_l.load().l4p_gemm(C.byref(d), _stream()), "l4p_gemm(hyper)")
+    _count()
+
+
+def token_attention(q: torch.Tensor, k16: torch.Tensor, v16: torch.Tensor, out: torch.Tensor, heads: int,
+                    shared_kv: bool, scale: float) -> None:
+    """K13a: q,out fp32 [G,nq,C]; k16,v16 16-bit [G*Nk, C] (or [Nk, C] when shared_kv)."""
+    _dev_init(q)
+    _chk(q, "q", torch.float32); _chk(out, "out", torch.float32); _chk(k16, "k16", sixteen=True); _chk(v16, "v16", sixteen=True)
+    G, nq, Cc = q.shape
+    Nk = k16.shape[0] if shared_kv else k16.shape[0] // G
+    d = Cc // heads
+    _l.check(_l.load().l4p_token_attention(q.data_ptr(), k16.data_ptr(), v16.data_ptr(), out.data_ptr(), G, nq, Nk, heads, d,
+                                           0 if shared_kv else Nk, float(scale), 1 if k16.dtype == torch.bfloat16 else 0,
+                                           _stream()), "l4p_token_attention")
+    _count()
+
+
+def image_attention(q16: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out16: torch.Tensor, G: int, heads: int,
+                    scale: float) -> None:
+    """K13b: q16,out16 16-bit [G*Np, C]; k,v fp32 [G,nk,C]."""
+    _dev_init(q16)
+    _chk(q16, "q16", sixteen=True); _chk(out16, "out16", sixteen=True); _chk(k, "k", torch.float32); _chk(v, "v", torch.float32)
+    Np = q16.shape[0] // G
+    Cc = q16.shape[1]
+    _l.check(_l.load().l4p_image_attention(q16.data_ptr(), k.data_ptr(), v.data_ptr(), out16.data_ptr(), G, Np, k.shape[1],
+                                           heads, Cc // heads, float(scale), 1 if q16.dtype == torch.bfloat16 else 0,
+                                           _stream()), "l4p_image_attention")
+    _count()
+
+
+def layernorm16(x16: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, y16: torch.Tensor,
+                gelu: bool = False) -> None:
+    _dev_init(x16)
+    _chk(x16, "x16", sixteen=True); _chk(y16, "y16", sixteen=True); _chk(gamma, "gamma", torch.float32); _chk(beta, "beta", torch.float32)
+    cols = x16.shape[-1]
+    _l.check(_l.load().l4p_layernorm16(x16.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y16.data_ptr(), x16.numel() // cols,
+                                       cols, float(eps), int(gelu), 1 if x16.dtype == torch.bfloat16 else 0, _stream()),
+             "l4p_layernorm16")
+    _count()
+
+
+def track_readout(masks: torch.Tensor, image_hw: Tuple[int, int]):
+    """K15: masks fp32 [G,nch,T,h,w] -> (traj [G,2,T], vis [G,1,T] | None, depth [G,1,T] | None)."""
+    _dev_init(masks)
+    _chk(masks, "masks", torch.float32)
+    G, nch, T, h, w = masks.shape
+    dev = masks.device
+    traj = torch.empty(G, 2, T, device=dev, dtype=torch.float32)
+    vis = torch.empty(G, 1, T, device=dev, dtype=torch.float32) if nch >= 2 else None
+    depth = torch.empty(G, 1, T, device=dev, dtype=torch.float32) if nch >= 3 else None
+    _l.check(_l.load().l4p_track_readout(masks.data_ptr(), traj.data_ptr(), _ptr(vis), _ptr(depth), G, nch, T, h, w,
+                                         image_hw[0], image_hw[1], _stream()), "l4p_track_readout")
+    _count()
+    return traj, vis, depth

@@ -8,6 +8,7 @@ from typing import Optional, Tuple
 import torch
 
 from .. import lib as _l
+from .. import ops as _ops
 from ..ops import _dev_init, _stream
 
 
@@ -47,6 +48,7 @@ def _pose_call(camray_b6thw: torch.Tensor, k_norm: Optional[torch.Tensor], mode:
         rays.data_ptr(), None if kn is None else kn.data_ptr(), mode, B, T, h, w, H, W, float(thr), refits,
         None if kgrid is None else kgrid.data_ptr(), ext.data_ptr(), pose.data_ptr(), centers.data_ptr(),
         None if kest is None else kest.data_ptr(), _stream()), "l4p_pose_from_rays")
+    _ops._count(2 if mode == 1 else 1)
     return ext, pose, centers, kest
 
 

@@ -29,7 +29,13 @@ def synth_tensor(key: str, shape: Tuple[int, ...], seed: int = 0, peaky: bool = 
         for s in shape[2:]:
             recept *= s
         fan_in, fan_out = shape[1] * recept, shape[0] * recept
-        a = math.sqrt(6.0 / (fan_in + fan_out))
+        if len(shape) == 2:
+            # Linear / Embedding: Xavier-uniform, the encoder's own init (modeling_pretrain.py:106-113)
+            a = math.sqrt(6.0 / (fan_in + fan_out))
+        else:
+            # Conv3d / ConvTranspose3d: torch's default kaiming_uniform(a=sqrt(5)) bound = 1/sqrt(fan_in), which is
+            # what the reference's DPT / SAM convolutions are constructed with (no custom init in dpt_block.py)
+            a = 1.0 / math.sqrt(fan_in)
         w = (torch.rand(shape, generator=g) * 2 - 1) * a
         if peaky and key.endswith("attn.qkv.weight"):
             w *= 4.0
@@ -37,7 +43,7 @@ def synth_tensor(key: str, shape: Tuple[int, ...], seed: int = 0, peaky: bool = 
     u = torch.rand(shape, generator=g) * 2 - 1
     if key.endswith("weight"):  # norm scales
         return 1.0 + 0.1 * u
-    return 0.05 * u  # biases
+    return 0.02 * u  # biases
 
 
 def synth_state_dict(manifest: Iterable[Tuple[str, Tuple[int, ...]]], seed: int = 0,

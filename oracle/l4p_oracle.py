@@ -137,7 +137,8 @@ CAMRAY_FUSION = ((1, 1, 1), (1, 1, 1), (2, 1, 1), (2, 2, 2))
 
 
 def dpt_forward(sd: SD, pre: str, feats: Sequence[torch.Tensor], hooks=(14, 21, 28, 36), img_info=(16, 224, 224),
-                actpost=DENSE_ACTPOST, fusion=DENSE_FUSION, output_size=None, patch=(2, 14, 14)) -> torch.Tensor:
+                actpost=DENSE_ACTPOST, fusion=DENSE_FUSION, output_size=None, patch=(2, 14, 14),
+                debug: Optional[dict] = None) -> torch.Tensor:
     """DPTOutputAdapter_fix.forward, dpt_head.py:41-86. `pre` ends with 'task_head.dpt.'."""
     T, H, W = img_info
     nt, nh, nw = T // patch[0], H // patch[1], W // patch[2]
@@ -153,6 +154,8 @@ def dpt_forward(sd: SD, pre: str, feats: Sequence[torch.Tensor], hooks=(14, 21, 
     p2 = _fusion(sd, pre + "scratch.refinenet2.", fusion[1], p3, layers[1])
     p1 = _fusion(sd, pre + "scratch.refinenet1.", fusion[0], p2, layers[0])
     out = F.conv3d(p1, sd[pre + "head1.0.weight"], sd[pre + "head1.0.bias"], padding=1)
+    if debug is not None:
+        debug.update(l0=layers[0], l1=layers[1], l2=layers[2], l3=layers[3], p4=p4, p3=p3, p2=p2, p1=p1, h1=out)
     osz = tuple(img_info) if output_size is None else tuple(output_size)
     if tuple(out.shape[-3:]) != osz:
         out = F.interpolate(out, size=osz, mode="trilinear", align_corners=True)

@@ -1,0 +1,73 @@
+"""Track head (SAM two-way transformer + mask decoder + read-outs) GPU parity against the CPU oracle at the full
+token size (2048 x 1408), seeded synthetic weights, single window through the windowed driver (first-window
+semantics: video tokens + learned mask token, labels rewritten by the driver)."""
+import pytest
+import torch
+
+from tests.util import grid_queries, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def _head():
+    from l4p_b200 import weights
+    from l4p_b200.models.task_heads.sparse_heads import VideoMAETrack2DSamHead
+
+    h = VideoMAETrack2DSamHead(task_name="track_2d", estimate_vis=True, estimate_depth=True, sam_head_depth=2,
+                               num_point_embeddings=2, prompt_using_features=True, attend_to_past=True,
+                               modify_pointlabels_for_windowing=True, estimation_directions=[1], depth_fn="exp",
+                               vis_fn="linear")
+    weights.fill_module_(h, seed=3)
+    return h
+
+
+def test_track_single_window_vs_oracle():
+    from oracle import l4p_oracle as O
+
+    head = _head()
+    sd = {k: v.clone() for k, v in head.state_dict().items()}
+    g = torch.Generator().manual_seed(5)
+    feat = torch.randn(1, 2048, 1408, generator=g)
+    q = grid_queries(3)  # 9 queries at t = 0.5
+    q[0, 4, 0] = 6.5     # one query starting mid-window
+    lab = torch.ones(1, q.shape[1])
+    head = head.cuda()
+    feats = [None] * 40 + [feat.cuda()]
+    out = head.forward_windowed([feats], q.cuda(), lab.cuda(), time_strides=torch.tensor([0]))
+    torch.cuda.synchronize()
+
+    enc = feat + sd["processed_video_mask_token.weight"][0]
+    ref = O.track_head_window(sd, "", enc, q, lab, torch.zeros(1, q.shape[1], 1408), torch.zeros(1, q.shape[1]))
+    valid = (torch.arange(16).view(1, 1, 1, 16) + 0.5 - q[:, :, 0:1, None]) >= 0
+
+    traj, vis, dep = out["track_2d_traj_est_bn2t"].cpu(), out["track_2d_vis_est_bn1t"].cpu(), out["track_2d_depth_est_bn1t"].cpu()
+    assert traj.shape == (1, 9, 2, 16) and vis.shape == (1, 9, 1, 16) and dep.shape == (1, 9, 1, 16)
+    # frames before the query time keep the buffer initialisation (exact): traj 0, vis -10, depth 0
+    assert (traj[~valid.expand_as(traj)] == 0).all() and (vis[~valid] == -10).all() and (dep[~valid] == 0).all()
+    rt, rv, rd = ref["track_2d_traj_est_bn2t"], ref["track_2d_vis_est_bn1t"], ref["track_2d_depth_est_bn1t"]
+    m2 = valid.expand_as(traj)
+    err_px = (traj - rt)[m2].abs().max().item()
+    print(f"traj max err {err_px:.4f} px; vis max abs err {(vis - rv)[valid].abs().max():.3e}; "
+          f"depth rel {rel_l2(dep[valid], rd[valid]):.3e}")
+    assert err_px < 0.05                                        # pixels (soft-argmax over 224x224)
+    assert (vis - rv)[valid].abs().max().item() < 5e-3          # logits
+    assert rel_l2(dep[valid], rd[valid]) < 2e-3
+
+
+def test_track_readout_peaked():
+    """Known answer: a sharply peaked low-res logit map -> soft-argmax lands on the upsampled peak location."""
+    from l4p_b200 import ops
+
+    G, T, h, w, H, W = 2, 16, 64, 64, 224, 224
+    masks = torch.zeros(G, 3, T, h, w)
+    masks[:, 0, :, 20, 40] = 200.0
+    masks[:, 1] = 0.25
+    masks[:, 2] = -1.5
+    traj, vis, depth = ops.track_readout(masks.cuda(), (H, W))
+    ref = torch.nn.functional.interpolate(masks, size=(T, H, W), mode="trilinear", align_corners=False)
+    hm = torch.softmax(ref[:, 0].reshape(G, T, -1), dim=-1)
+    ys, xs = torch.meshgrid(torch.arange(H) + 0.5, torch.arange(W) + 0.5, indexing="ij")
+    rx, ry = (hm * xs.reshape(-1)).sum(-1), (hm * ys.reshape(-1)).sum(-1)
+    assert (traj[:, 0].cpu() - rx).abs().max() < 1e-3 and (traj[:, 1].cpu() - ry).abs().max() < 1e-3
+    assert (vis.cpu() - 0.25).abs().max() < 1e-6
+    assert (depth.cpu() - torch.exp(torch.tensor(-1.5))).abs().max() < 1e-6
