@@ -1,0 +1,267 @@
+#!/usr/bin/env python
+"""Headline benchmark of the L4P inference hot path on B200 (contract: see the build brief / DESIGN.md §Measurement).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One step = one pass of the all-heads hot path (encoder + flow/depth/dyn-mask/camray DPT heads + 128-query track head)
+over `clips_per_gpu` synthetic 16x224x224 clips per GPU. Metric: frames/s = 16 * clips / step time (BASELINE.json).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+TASKS = ["flow_2d_backward", "track_2d", "depth", "dyn_mask", "camray"]
+NQ = 128
+ATT_FLOPS_PER_BLOCK_WINDOW = 4 * 2048 * 2048 * 88 * 16  # 23 622 320 128 (unpadded d=88)
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        j = json.loads(p.read_text())
+        return dict(tflops=j.get("bf16_tflops_sustained", j["bf16_tflops"]), hbm=j["hbm_gbs"], src="measured (MEASURED_PEAKS.json, sustained)")
+    return dict(tflops=1400.0, hbm=6650.0, src="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.stop, self.index = [], False, index
+        self.t = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        while not self.stop:
+            try:
+                o = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                   capture_output=True, text=True, timeout=5).stdout.strip()
+                if o:
+                    self.rows.append([c.strip() for c in o.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        self.t.join(timeout=6)
+
+    def summary(self):
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def synth_batch(clips: int):
+    from tests.util import grid_queries, synth_intrinsics, synth_rgb
+
+    rgb = synth_rgb(clips, 16, seed=0)
+    intr = synth_intrinsics(clips, 16)
+    xs = torch.linspace(7, 217, 16)
+    ys = torch.linspace(14, 210, 8)
+    gy, gx = torch.meshgrid(ys, xs, indexing="ij")
+    q = torch.stack([torch.full_like(gx, 0.5), gx + 0.5, gy + 0.5], dim=-1).reshape(1, NQ, 3).repeat(clips, 1, 1)
+    return dict(rgb_b3thw=rgb, intrinsics_b44t=intr, track_2d_pointquerries_bn3=q,
+                track_2d_pointlabels_bn=torch.ones(clips, NQ))
+
+
+OUT_KEYS = ["depth_est_b1thw", "flow_2d_backward_est_b2thw", "dyn_mask_est_b1thw", "traj3d_est_b16t",
+            "traj3d_intrinsics_est_b16t", "track_2d_traj_est_bn2t", "track_2d_vis_est_bn1t", "track_2d_depth_est_bn1t"]
+
+
+def run_clip(model, batch, c):
+    one = {k: v[c:c + 1] for k, v in batch.items()}
+    out = model.forward(one, TASKS)
+    return torch.cat([out[k].reshape(-1).float() for k in OUT_KEYS])
+
+
+def cpu_baseline_sample():
+    from l4p_b200 import weights
+    from l4p_b200.models.task_heads.dense_heads import VideoMAEDepthDPTHead, VideoMAETraj3DDPTHead
+    from l4p_b200.models.task_heads.sparse_heads import VideoMAETrack2DSamHead
+    from l4p_b200.models.videomae import Block
+    from oracle import cpu_bench
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    hooks = [0, 1, 2, 3]
+    mods = dict(
+        block=Block(1408, 16, 48 / 11, True, None, 1e-6, 0.0, device="meta"),
+        depth=VideoMAEDepthDPTHead("depth", hooks_idx=hooks, device="meta"),
+        cam=VideoMAETraj3DDPTHead("traj3d", hooks_idx=hooks, use_intrinsics=False, fixed_intrinsics=True, device="meta"),
+        track=VideoMAETrack2DSamHead(estimate_vis=True, estimate_depth=True, prompt_using_features=True, attend_to_past=True,
+                                     modify_pointlabels_for_windowing=True, estimation_directions=[1], depth_fn="exp",
+                                     device="meta"))
+    sds = {n: weights.synth_state_dict([(k, tuple(v.shape)) for k, v in m.state_dict().items()], seed=0) for n, m in mods.items()}
+    return cpu_bench.sample(sds["block"], sds["depth"], sds["cam"], sds["track"], NQ), cpu_bench.SAMPLE_DESC
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    for _ in range(max(args.warmup, 0) and 1):
+        cpu_baseline_sample()
+    vals = []
+    t_all = time.perf_counter()
+    for _ in range(args.steps):
+        s, desc = cpu_baseline_sample()
+        vals.append(s["frames_per_s"])
+    v = sum(vals) / len(vals)
+    line = {"impl": "reference", "metric": "frames/sec (16x224x224, all heads)", "value": v, "unit": "frames/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * (time.perf_counter() - t_all) / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "single 16x224x224 clip, all heads, 128 track queries (BASELINE.json configs[1])"},
+            "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": "port", "sample": desc},
+            "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "the reference is pure Python and cannot travel to the GPU box (/root/reference absent there); this "
+                    "arm times the oracle port (oracle/l4p_oracle.py, pinned against the reference by tests/golden)"}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--clips-per-gpu", type=int, default=1)
+    ap.add_argument("--dtype", default="fp16", choices=["fp16", "bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+
+    from l4p_b200 import ops, weights
+    from l4p_b200.config import load_model
+
+    dt = torch.float16 if args.dtype == "fp16" else torch.bfloat16
+    lit = load_model(device=dev, max_queries=NQ + 1, compute_dtype=dt)
+    model = lit.l4p_model
+    weights.fill_module_fast_(model, seed=rank)
+    clips = args.clips_per_gpu
+    host = {k: v.pin_memory() for k, v in synth_batch(clips).items()}
+    batch = {k: v.to(dev) for k, v in host.items()}
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+
+    gather_buf = None
+
+    def step(b):
+        outs = [run_clip(model, b, c) for c in range(clips)]
+        packed = torch.cat(outs) if clips > 1 else outs[0]
+        if world > 1:
+            nonlocal gather_buf
+            if gather_buf is None:
+                gather_buf = torch.empty(world * packed.numel(), device=dev, dtype=torch.float32)
+            dist.all_gather_into_tensor(gather_buf, packed)  # the single exchange step: head outputs over NVLink
+            return gather_buf
+        return packed
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            res = step(batch)
+        d2h = res.numel() * 4 if world == 1 else res.numel() * 4
+        host_out = torch.empty(res.shape, dtype=torch.float32).pin_memory()
+        # ---------------- device-resident timed region
+        sync_all()
+        launches0 = ops.LAUNCHES
+        ops.ATTN_EVENTS = []
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(local) as cs:
+            e0.record()
+            for _ in range(args.steps):
+                step(batch)
+            e1.record()
+            sync_all()
+        ms = e0.elapsed_time(e1) / args.steps
+        launches = (ops.LAUNCHES - launches0) // args.steps
+        att = ops.ATTN_EVENTS
+        ops.ATTN_EVENTS = None
+        att_ms = sum(a.elapsed_time(b) for a, b, _ in att) / max(len(att), 1)
+        att_flops = sum(f for _, _, f in att) / max(len(att), 1)
+        # ---------------- end-to-end timed region: pinned host inputs -> H2D -> forward -> D2H of all head outputs
+        sync_all()
+        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e2.record()
+        for _ in range(args.steps):
+            b = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+            r = step(b)
+            host_out.copy_(r, non_blocking=True)
+        e3.record()
+        sync_all()
+        ms_e2e = e2.elapsed_time(e3) / args.steps
+
+    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = t.tolist()
+    frames = 16 * clips * world
+    if rank == 0:
+        pk = peaks()
+        ach = att_flops / (att_ms * 1e-3) / 1e12
+        line = {
+            "metric": "frames/sec (16x224x224, all heads)", "value": frames / (ms * 1e-3), "unit": "frames/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": "single 16x224x224 clip per GPU, all heads (flow, depth, dyn-mask, camray pose, 128-query "
+                                   "2D/3D tracks), BASELINE.json configs[1]; N>1: one clip per GPU + one all-gather of head outputs",
+                       "clips_per_gpu": clips, "track_queries": NQ, "weights": "random (seeded), reference architecture",
+                       "l2": "per-step working set (2.8 GB weights + >1 GB activations) exceeds the 126 MB L2; no explicit flush"},
+            "e2e": {"value": frames / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches),
+            "clocks": cs.summary(),
+            "roofline": {"kernel": "attention_kernel (fused QK^T+softmax+PV, tcgen05)", "bound": "tensor", "achieved": ach,
+                         "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"], "traffic": None,
+                         "peak_source": pk["src"], "launch_us": att_ms * 1e3,
+                         "algorithmic_flops_per_launch": att_flops},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            s, desc = cpu_baseline_sample()
+            line["cpu_baseline"] = {"value": s["frames_per_s"], "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+                                    "sample": desc, "detail": {k: round(v, 4) for k, v in s.items()}}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -56,3 +56,25 @@ def fill_module_(module: torch.nn.Module, seed: int = 0, peaky: bool = False, pr
     with torch.no_grad():
         for k, t in module.state_dict().items():
             t.copy_(synth_tensor(prefix + k, tuple(t.shape), seed, peaky).to(t.device))
+
+
+def fill_module_fast_(module: torch.nn.Module, seed: int = 0) -> None:
+    """Same distributions as `fill_module_`, generated on the tensor's own device (benchmarks: the values
+    need not be reproducible across devices, 1.4 B parameters should not take a minute of CPU RNG)."""
+    with torch.no_grad():
+        for i, (k, t) in enumerate(module.state_dict().items()):
+            g = torch.Generator(device=t.device)
+            g.manual_seed((zlib.crc32(k.encode()) ^ (seed * 0x9E3779B1)) & 0x7FFFFFFF)
+            shape = tuple(t.shape)
+            if "positional_encoding_gaussian_matrix" in k:
+                t.copy_(torch.randn(shape, generator=g, device=t.device))
+            elif len(shape) >= 2:
+                recept = 1
+                for s in shape[2:]:
+                    recept *= s
+                fan_in, fan_out = shape[1] * recept, shape[0] * recept
+                a = math.sqrt(6.0 / (fan_in + fan_out)) if len(shape) == 2 else 1.0 / math.sqrt(fan_in)
+                t.copy_((torch.rand(shape, generator=g, device=t.device) * 2 - 1) * a)
+            else:
+                u = torch.rand(shape, generator=g, device=t.device) * 2 - 1
+                t.copy_(1.0 + 0.1 * u if k.endswith("weight") else 0.02 * u)
