@@ -151,6 +151,8 @@ def main():
     ap.add_argument("--clips-per-gpu", type=int, default=1)
     ap.add_argument("--dtype", default="fp16", choices=["fp16", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ncu-range", action="store_true", help="bracket the timed region with cudaProfilerStart/Stop "
+                    "(run under `ncu --profile-from-start off`)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -207,11 +209,15 @@ def main():
         ops.ATTN_EVENTS = []
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with ClockSampler(local) as cs:
+            if args.ncu_range:
+                torch.cuda.profiler.start()
             e0.record()
             for _ in range(args.steps):
                 step(batch)
             e1.record()
             sync_all()
+            if args.ncu_range:
+                torch.cuda.profiler.stop()
         ms = e0.elapsed_time(e1) / args.steps
         launches = (ops.LAUNCHES - launches0) // args.steps
         att = ops.ATTN_EVENTS

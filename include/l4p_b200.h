@@ -144,9 +144,10 @@ int l4p_track_readout(const float* masks, float* traj, float* vis, float* depth,
  * Replaces the q@k^T -> softmax -> @v sequence of Attention.forward
  * (l4p/models/VideoMAEv2/models/modeling_finetune.py:180-186); the [B,H,N,N] score tensor is never
  * materialised. q,k: [B,H,N,head_dim_pad]; vt: [B,H,head_dim_pad,N] (pad lanes zero); out 16-bit
- * [B*N, H*head_dim]. This build: head_dim_pad == 96, N a multiple of 256. */
+ * [B*N, H*head_dim]. This build: head_dim_pad == 96, N a multiple of 256.
+ * prof: NULL, or a device buffer of 3*64*8 int64 that receives clock64 stamps of CTA 0 (kernel tuning aid). */
 int l4p_attention(const void* q, const void* k, const void* vt, void* out, int B, int H, int N,
-                  int head_dim, int head_dim_pad, float scale, int bf16, void* stream);
+                  int head_dim, int head_dim_pad, float scale, int bf16, void* stream, void* prof);
 
 /* ---- K11: camera pose from Plücker rays ------------------------------------------------------ */
 /* rays fp32 [B,6,T,h,w] (direction, moment). mode 0: use normalised intrinsics k_norm [B,4,4,T]

@@ -41,6 +41,7 @@ struct AttParams {
   uint16_t* out;
   int B, H, N, head_dim;
   float scale_log2;  // scale * log2(e)
+  long long* prof;   // optional [3 roles][64 iters][8] clock64 stamps of CTA 0 (debug; NULL in production)
 };
 
 L4P_DEVICE float ex2(float x) {
@@ -48,6 +49,9 @@ L4P_DEVICE float ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+
+#define ATT_STAMP(role, it, slot) \
+  do { if (p.prof != nullptr && blockIdx.x == 0 && lane == 0 && (it) < 64) p.prof[((role) * 64 + (it)) * 8 + (slot)] = clock64(); } while (0)
 
 template <bool BF16>
 __global__ void __launch_bounds__(kAttThreads, 1)
@@ -122,31 +126,34 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             tma_load_2d(sV + s * kVBytes + c * (kDPad * 128), &tmV, fb, j * kTileN + c * 64, bh * kDPad);
         }
       }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1) {
       // ---------------------------------------------------------------- UMMA issuer
+      // The whole warp walks the pipeline (warp-uniform control flow keeps descriptors in uniform registers);
+      // one elected lane issues. Descriptor words are precomputed: per UMMA only an add remains.
+      const bool leader = elect_one();
       const uint32_t idesc_s = umma_idesc_f16(BF16, kTileM, kTileN);
       const uint32_t idesc_o = umma_idesc_f16(BF16, kTileM, kDPad);
-      auto issue_s = [&](int t, int j) {
-        const int s = j % kKS;
+      constexpr uint32_t hi64 = umma_desc_hi(64, 4), hi128 = umma_desc_hi(128, 2);
+      const uint32_t q_lo = umma_desc_lo(sQ), k_lo = umma_desc_lo(sK), p_lo = umma_desc_lo(sP), v_lo = umma_desc_lo(sV);
+      auto issue_s = [&](const int t, const int s) {
         const uint32_t d = tmem_base + (t == 0 ? kColS0 : kColS1);
+        const uint32_t qa = q_lo + (uint32_t)t * (kQTileBytes >> 4), ka = k_lo + (uint32_t)s * (kKBytes >> 4);
 #pragma unroll
         for (int kk = 0; kk < kDPad / 16; ++kk) {
-          const uint32_t off = (uint32_t)(kk >> 1) * (kTileM * 64) + (uint32_t)(kk & 1) * 32;
-          const uint64_t da = umma_desc_kmajor(sQ + t * kQTileBytes + off, 64, 4);
-          const uint64_t db = umma_desc_kmajor(sK + s * kKBytes + off, 64, 4);
-          umma_ss(d, da, db, idesc_s, kk != 0 ? 1u : 0u);
+          const uint32_t off = ((uint32_t)(kk >> 1) * (kTileM * 64) + (uint32_t)(kk & 1) * 32) >> 4;
+          umma_ss(d, umma_desc_make(qa + off, hi64), umma_desc_make(ka + off, hi64), idesc_s, kk != 0 ? 1u : 0u);
         }
         umma_commit(smem_u32(&bar_sfull[t]));
       };
-      auto issue_pv = [&](int t, int j) {
-        const int s = j % kVS;
+      auto issue_pv = [&](const int t, const int s, const uint32_t acc) {
         const uint32_t d = tmem_base + (t == 0 ? kColO0 : kColO1);
+        const uint32_t pa = p_lo + (uint32_t)t * (kPBytes >> 4), va = v_lo + (uint32_t)s * (kVBytes >> 4);
 #pragma unroll
         for (int kk = 0; kk < kTileN / 16; ++kk) {
-          const uint32_t c = (uint32_t)(kk >> 2), o = (uint32_t)(kk & 3) * 32;
-          const uint64_t da = umma_desc_kmajor(sP + t * kPBytes + c * (kTileM * 128) + o, 128, 2);
-          const uint64_t db = umma_desc_kmajor(sV + s * kVBytes + c * (kDPad * 128) + o, 128, 2);
-          umma_ss(d, da, db, idesc_o, (j | kk) != 0 ? 1u : 0u);
+          const uint32_t o = ((uint32_t)(kk & 3) * 32) >> 4;
+          umma_ss(d, umma_desc_make(pa + (uint32_t)(kk >> 2) * ((kTileM * 128) >> 4) + o, hi128),
+                  umma_desc_make(va + (uint32_t)(kk >> 2) * ((kDPad * 128) >> 4) + o, hi128), idesc_o,
+                  kk != 0 ? 1u : acc);
         }
         umma_commit(smem_u32(&bar_pvdone[t]));
       };
@@ -154,24 +161,38 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       mbar_wait(smem_u32(&bar_q), 0);
       mbar_wait(smem_u32(&bar_kfull[0]), 0);
       tc_fence_after();
-      issue_s(0, 0);
-      issue_s(1, 0);
-      umma_commit(smem_u32(&bar_kempty[0]));
+      if (leader) {
+        issue_s(0, 0);
+        issue_s(1, 0);
+        umma_commit(smem_u32(&bar_kempty[0]));
+      }
+      __syncwarp();
       for (int j = 0; j < nblk; ++j) {
+        const int jn = j + 1;
+        const int sk = jn % kKS, sv = j % kVS;
+#pragma unroll
         for (int t = 0; t < 2; ++t) {
-          if (j + 1 < nblk) {
-            const int jn = j + 1;
-            if (t == 0) mbar_wait(smem_u32(&bar_kfull[jn % kKS]), ((uint32_t)(jn / kKS)) & 1u);
+          if (jn < nblk) {
+            if (t == 0) mbar_wait(smem_u32(&bar_kfull[sk]), ((uint32_t)(jn / kKS)) & 1u);
             mbar_wait(smem_u32(&bar_sfree[t]), (uint32_t)j & 1u);  // softmax t holds S_t(j) in registers
             tc_fence_after();
-            issue_s(t, jn);
-            if (t == 1) umma_commit(smem_u32(&bar_kempty[jn % kKS]));
+            if (leader) {
+              issue_s(t, sk);
+              if (t == 1) umma_commit(smem_u32(&bar_kempty[sk]));
+            }
+            __syncwarp();
           }
+          ATT_STAMP(2, j, t * 4 + 0);
           mbar_wait(smem_u32(&bar_pfull[t]), (uint32_t)j & 1u);  // P_t(j) in smem (and O_t rescaled)
-          if (t == 0) mbar_wait(smem_u32(&bar_vfull[j % kVS]), ((uint32_t)(j / kVS)) & 1u);
+          ATT_STAMP(2, j, t * 4 + 1);
+          if (t == 0) mbar_wait(smem_u32(&bar_vfull[sv]), ((uint32_t)(j / kVS)) & 1u);
           tc_fence_after();
-          issue_pv(t, j);
-          if (t == 1) umma_commit(smem_u32(&bar_vempty[j % kVS]));
+          if (leader) {
+            issue_pv(t, sv, j != 0 ? 1u : 0u);
+            if (t == 1) umma_commit(smem_u32(&bar_vempty[sv]));
+          }
+          __syncwarp();
+          ATT_STAMP(2, j, t * 4 + 2);
         }
       }
     }
@@ -192,14 +213,17 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     float l = 0.f;
 
     for (int j = 0; j < nblk; ++j) {
+      ATT_STAMP(t, j, 0);
       mbar_wait(smem_u32(&bar_sfull[t]), (uint32_t)j & 1u);
       tc_fence_after();
+      ATT_STAMP(t, j, 1);
       uint32_t s[128];
       tmem_ld32(tS + 0, s + 0);
       tmem_ld32(tS + 32, s + 32);
       tmem_ld32(tS + 64, s + 64);
       tmem_ld32(tS + 96, s + 96);
       tmem_ld_wait();
+      ATT_STAMP(t, j, 2);
       tc_fence_before();
       mbar_arrive(smem_u32(&bar_sfree[t]));
 
@@ -241,6 +265,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
       }
 
+      ATT_STAMP(t, j, 3);
       // p = exp2(s*c - m_used), row sum in fp32, pack pairs in place
       float l0 = 0.f, l1 = 0.f;
       const float nm = -m_used;
@@ -253,8 +278,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         s[i >> 1] = pack2<BF16>(p0, p1);
       }
       l += l0 + l1;
+      ATT_STAMP(t, j, 4);
 
       if (j > 0) mbar_wait(smem_u32(&bar_pvdone[t]), (uint32_t)(j - 1) & 1u);  // P_t smem is free again
+      ATT_STAMP(t, j, 5);
 #pragma unroll
       for (int u = 0; u < 16; ++u) {
         // 16-byte unit u: keys [8u, 8u+8); chunk = u/8; swizzled unit inside the 128-byte row
@@ -265,6 +292,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       }
       fence_proxy_async();
       mbar_arrive(smem_u32(&bar_pfull[t]));
+      ATT_STAMP(t, j, 6);
     }
 
     // ---- epilogue: O_t / l -> global
@@ -306,7 +334,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 using namespace l4p;
 
 extern "C" int l4p_attention(const void* q, const void* k, const void* vt, void* out, int B, int H, int N,
-                             int head_dim, int head_dim_pad, float scale, int bf16, void* stream) {
+                             int head_dim, int head_dim_pad, float scale, int bf16, void* stream, void* prof) {
   L4P_REQUIRE(q && k && vt && out, L4P_ERR_ARG, "l4p_attention: null pointer");
   L4P_REQUIRE(B > 0 && H > 0, L4P_ERR_SHAPE, "l4p_attention: B=%d H=%d", B, H);
   L4P_REQUIRE(head_dim_pad == kDPad && head_dim % 8 == 0 && head_dim > 0 && head_dim <= kDPad, L4P_ERR_SHAPE,
@@ -335,6 +363,7 @@ extern "C" int l4p_attention(const void* q, const void* k, const void* vt, void*
   p.out = (uint16_t*)out;
   p.B = B; p.H = H; p.N = N; p.head_dim = head_dim;
   p.scale_log2 = scale * 1.4426950408889634f;
+  p.prof = (long long*)prof;
   auto kfn = bf16 ? attention_kernel<true> : attention_kernel<false>;
   static bool attr_set[2] = {false, false};
   if (!attr_set[bf16 ? 1 : 0]) {

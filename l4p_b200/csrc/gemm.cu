@@ -5,7 +5,8 @@
 //   warp 0      TMA producer   (A/B tiles -> 128B-swizzled smem ring, mbarrier complete_tx)
 //   warp 1      UMMA issuer    (tcgen05.mma kind::f16, fp32 accumulators in TMEM, 2 accumulator stages)
 //   warp 2      TMEM allocator
-//   warps 4..7  epilogue       (tcgen05.ld -> bias/activation/residual -> global stores)
+//   warps 4..11 epilogue       (tcgen05.ld -> bias/activation/residual -> global stores); two warpgroups interleave
+//               16-column chunks so that the global-latency-bound epilogue of one overlaps the other
 //
 // A-operand modes:
 //   A_MATRIX  plain row-major [M,K] matrix, one 2-D TMA box (64 x 128) per k-block.
@@ -25,7 +26,8 @@ constexpr int kBlockK = 64;                       // 64 x 2 B = one 128 B swizzl
 constexpr int kABytes = kBlockM * kBlockK * 2;    // 16 KiB
 constexpr int kMaxStages = 8;
 constexpr int kAccCols = 256;                     // TMEM columns per accumulator stage
-constexpr int kGemmThreads = 256;
+constexpr int kEpiGroups = 2;                     // epilogue warpgroups: group g handles 16-column chunks c with c % kEpiGroups == g
+constexpr int kGemmThreads = 128 + 128 * kEpiGroups;
 
 struct GemmKParams {
   int M, N, num_kb, block_n, stages;
@@ -85,6 +87,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   __shared__ __align__(8) uint64_t bar_tfull[2];
   __shared__ __align__(8) uint64_t bar_tempty[2];
   __shared__ uint32_t tmem_base_slot;
+  __shared__ float s_head[(kEpiGroups - 1) * 128 * 8];  // cross-warpgroup reduction of the fused head dot products
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -102,7 +105,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&bar_tfull[s]), 1);
-      mbar_init(smem_u32(&bar_tempty[s]), 128);
+      mbar_init(smem_u32(&bar_tempty[s]), 128 * kEpiGroups);
     }
     fence_mbar_init();
   }
@@ -143,37 +146,43 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ UMMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_f16(BF16, kBlockM, (uint32_t)p.block_n);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(smem_u32(&bar_tempty[acc]), acc_phase ^ 1u);
+    // whole warp walks the pipeline (warp-uniform control flow), one elected lane issues
+    const bool leader = elect_one();
+    const uint32_t idesc = umma_idesc_f16(BF16, kBlockM, (uint32_t)p.block_n);
+    constexpr uint32_t hi128 = umma_desc_hi(128, 2);
+    const uint32_t a_lo0 = umma_desc_lo(smem_base), b_lo0 = umma_desc_lo(smem_base + kABytes);
+    const uint32_t stage_step = stage_bytes >> 4;
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(smem_u32(&bar_tempty[acc]), acc_phase ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)acc * kAccCols;
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        mbar_wait(smem_u32(&bar_full[stage]), phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)acc * kAccCols;
-        for (int kb = 0; kb < p.num_kb; ++kb) {
-          mbar_wait(smem_u32(&bar_full[stage]), phase);
-          tc_fence_after();
-          const uint32_t sa = smem_base + stage * stage_bytes;
-          const uint64_t da = umma_desc_kmajor(sa, 128, 2);
-          const uint64_t db = umma_desc_kmajor(sa + kABytes, 128, 2);
+        if (leader) {
+          const uint32_t a_lo = a_lo0 + (uint32_t)stage * stage_step, b_lo = b_lo0 + (uint32_t)stage * stage_step;
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) {
             // advance 16 elements (32 B) along K inside the swizzle row: +2 in the (addr >> 4) field
-            umma_ss(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_ss(d_tmem, umma_desc_make(a_lo + 2 * k, hi128), umma_desc_make(b_lo + 2 * k, hi128), idesc,
+                    (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit(smem_u32(&bar_empty[stage]));
-          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+          if (kb == p.num_kb - 1) umma_commit(smem_u32(&bar_tfull[acc]));
         }
-        umma_commit(smem_u32(&bar_tfull[acc]));
-        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue
     const int q4 = warp & 3;  // TMEM lane quarter owned by this warp
+    const int egrp = (warp - 4) >> 2;  // epilogue warpgroup: interleaved 16-column chunks
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -203,7 +212,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
       for (int c = 0; c < 8; ++c) head_acc[c] = 0.f;
 
-      for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+      const long long rrow = p.res_row_mod > 0 ? row % p.res_row_mod : row;
+      const float* hyper_w = p.store_mode == L4P_STORE_HYPER ? p.w2 + (row / p.rows_per_group) * (long long)(p.c2 * p.ctCout) : nullptr;
+      for (int c0 = egrp * 16; c0 < p.block_n; c0 += 16 * kEpiGroups) {
         uint32_t raw[16];
         __syncwarp();  // tcgen05.ld is warp-collective: reconverge after the per-row store predicate
         tmem_ld16(t_addr + (uint32_t)c0, raw);
@@ -222,7 +233,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
         if (p.act == L4P_ACT_GELU) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = gelu_erf(v[i]);
+          for (int i = 0; i < 16; ++i) v[i] = gelu_erf_fast(v[i]);
         } else if (p.act == L4P_ACT_RELU) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
@@ -231,7 +242,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           // masked row: nothing to store (loads above are warp-collective, stores are per-thread)
         } else if (p.store_mode == L4P_STORE_ROWMAJOR) {
           if (p.res_f32 != nullptr) {
-            const long long rrow = p.res_row_mod > 0 ? row % p.res_row_mod : row;
             const float* rp = p.res_f32 + rrow * p.ld_res + col0;
 #pragma unroll
             for (int i = 0; i < 16; i += 4) {
@@ -334,17 +344,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         } else if (p.store_mode == L4P_STORE_HYPER) {
           // v = act(acc + bias) of one ConvT tap (this N tile); dot with the per-query hyper-network vectors
-          const float* wg = p.w2 + (row / p.rows_per_group) * (long long)(p.c2 * p.ctCout) + c0;
+          const float* wg = hyper_w + c0;
+          float4 wv[4][4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            if (c < p.c2)
+#pragma unroll
+              for (int i = 0; i < 4; ++i) wv[c][i] = *reinterpret_cast<const float4*>(wg + c * p.ctCout + 4 * i);
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             if (c < p.c2) {
-              const float* wr = wg + c * p.ctCout;
               float a = head_acc[c];
 #pragma unroll
-              for (int i = 0; i < 16; i += 4) {
-                const float4 wv = *reinterpret_cast<const float4*>(wr + i);
-                a = fmaf(v[i], wv.x, a); a = fmaf(v[i + 1], wv.y, a);
-                a = fmaf(v[i + 2], wv.z, a); a = fmaf(v[i + 3], wv.w, a);
+              for (int i = 0; i < 4; ++i) {
+                a = fmaf(v[4 * i], wv[c][i].x, a); a = fmaf(v[4 * i + 1], wv[c][i].y, a);
+                a = fmaf(v[4 * i + 2], wv[c][i].z, a); a = fmaf(v[4 * i + 3], wv[c][i].w, a);
               }
               head_acc[c] = a;
             }
@@ -371,7 +385,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       mbar_arrive(smem_u32(&bar_tempty[acc]));
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
 
-      if (p.store_mode == L4P_STORE_HYPER && row_ok) {
+      if (p.store_mode == L4P_STORE_HYPER || p.store_mode == L4P_STORE_HEAD1X1) {
+        // the per-row dot products were accumulated per warpgroup over its chunks: reduce them in group 0
+        if (egrp != 0) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) s_head[(egrp - 1) * 128 * 8 + r * 8 + c] = head_acc[c];
+        }
+        named_bar_sync(1, 128 * kEpiGroups);
+        if (egrp == 0) {
+#pragma unroll
+          for (int g2 = 1; g2 < kEpiGroups; ++g2)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) head_acc[c] += s_head[(g2 - 1) * 128 * 8 + r * 8 + c];
+        }
+        named_bar_sync(1, 128 * kEpiGroups);  // s_head may be overwritten by the next tile
+      }
+
+      if (p.store_mode == L4P_STORE_HYPER && row_ok && egrp == 0) {
         // row = input voxel (g,t,h,w) of the [cB,cT,cH,cW] grid; this N tile = tap (kt,kh,kw)
         long long rr = row;
         const int w_ = (int)(rr % p.cW); rr /= p.cW;
@@ -386,7 +416,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         for (int c = 0; c < 4; ++c)
           if (c < p.c2) p.out_f32[((g_ * p.c2 + c) * oT * oH * oW) + vox] = head_acc[c];
       }
-      if (p.store_mode == L4P_STORE_HEAD1X1 && row_ok) {
+      if (p.store_mode == L4P_STORE_HEAD1X1 && row_ok && egrp == 0) {
         const long long plane = (long long)p.cT * p.cH * p.cW;
         const long long vox = ((long long)ct_ * p.cH + ch_) * p.cW + cw_;
 #pragma unroll
@@ -436,6 +466,15 @@ extern "C" int l4p_gemm(const l4p_gemm_desc* d, void* stream_) {
   p.M = (int)d->M;
   p.N = (int)d->N;
   p.block_n = d->block_n > 0 ? d->block_n : pick_block_n(d->N);
+  if (d->block_n <= 0 && d->store_mode != L4P_STORE_HEAD1X1) {
+    // few output tiles (low-resolution pyramid levels, token-side GEMMs): trade tile width for CTAs so that more
+    // than a handful of SMs work on the (long) K loop
+    const long long tm = d->a_mode == L4P_A_CONV3D
+                             ? (long long)d->cB * ((d->cT + d->bT - 1) / d->bT) * ((d->cH + d->bH - 1) / d->bH) * ((d->cW + d->bW - 1) / d->bW)
+                             : (d->M + kBlockM - 1) / kBlockM;
+    while (p.block_n >= 64 && (p.block_n / 2) % 16 == 0 && tm * ((d->N + p.block_n - 1) / p.block_n) < 96)
+      p.block_n /= 2;
+  }
   L4P_REQUIRE(p.block_n % 16 == 0 && p.block_n >= 16 && p.block_n <= 256, L4P_ERR_SHAPE, "l4p_gemm: block_n=%d",
               p.block_n);
   p.a_mode = d->a_mode;
@@ -545,7 +584,7 @@ extern "C" int l4p_gemm(const l4p_gemm_desc* d, void* stream_) {
   }
 
   const uint32_t stage_bytes = kABytes + (uint32_t)p.block_n * 128u;
-  int stages = (int)((220u * 1024u) / stage_bytes);
+  int stages = (int)((216u * 1024u) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages > p.num_kb) stages = p.num_kb < 2 ? 2 : p.num_kb;
   if (stages > kMaxStages) stages = kMaxStages;
@@ -559,7 +598,7 @@ extern "C" int l4p_gemm(const l4p_gemm_desc* d, void* stream_) {
   auto kfn = d->bf16 ? gemm_kernel<true> : gemm_kernel<false>;
   static bool attr_set[2] = {false, false};
   if (!attr_set[d->bf16 ? 1 : 0]) {
-    L4P_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+    L4P_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 221 * 1024));
     attr_set[d->bf16 ? 1 : 0] = true;
   }
   kfn<<<grid, kGemmThreads, smem, stream>>>(tmA, tmB, p);

@@ -55,10 +55,12 @@ __device__ void jacobi_eig(double* A, double* V) {
   for (int i = 0; i < n; ++i)
     for (int j = 0; j < n; ++j) V[i * n + j] = i == j ? 1.0 : 0.0;
   for (int sweep = 0; sweep < 30; ++sweep) {
-    double off = 0.0;
-    for (int i = 0; i < n; ++i)
+    double off = 0.0, diag = 0.0;
+    for (int i = 0; i < n; ++i) {
+      diag += A[i * n + i] * A[i * n + i];
       for (int j = i + 1; j < n; ++j) off += A[i * n + j] * A[i * n + j];
-    if (off < 1e-300) break;
+    }
+    if (off <= 1e-28 * diag || off < 1e-300) break;  // converged to fp64 round-off (typically 6-9 sweeps)
     for (int p = 0; p < n; ++p)
       for (int q = p + 1; q < n; ++q) {
         const double apq = A[p * n + q];

@@ -249,7 +249,7 @@ layernorm16_kernel(const uint16_t* __restrict__ x, const float* __restrict__ gam
 #pragma unroll
       for (int t = 0; t < 8; ++t) {
         o[t] = (v[i][t] - mean) * rstd * gamma[j * 8 + t] + beta[j * 8 + t];
-        if (gelu) o[t] = gelu_erf(o[t]);
+        if (gelu) o[t] = gelu_erf_fast(o[t]);
       }
       reinterpret_cast<uint4*>(y + row * cols)[j] = make_uint4(pack2<BF16>(o[0], o[1]), pack2<BF16>(o[2], o[3]),
                                                                pack2<BF16>(o[4], o[5]), pack2<BF16>(o[6], o[7]));

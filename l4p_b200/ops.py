@@ -213,7 +213,7 @@ def conv_transpose3d(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, strid
 
 
 def attention(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, out: torch.Tensor, head_dim: int,
-              scale: float) -> None:
+              scale: float, prof: Optional[torch.Tensor] = None) -> None:
     """K4: fused softmax(q k^T scale) v. q,k [B,H,N,dpad]; vt [B,H,dpad,N]; out [B*N, H*head_dim] 16-bit."""
     _dev_init(q)
     for n, t in (("q", q), ("k", k), ("vt", vt), ("out", out)):
@@ -230,7 +230,7 @@ def attention(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, out: torch.Ten
         ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
         ev[0].record()
     _l.check(_l.load().l4p_attention(q.data_ptr(), k.data_ptr(), vt.data_ptr(), out.data_ptr(), B, H, N, head_dim,
-                                     dpad, float(scale), 1 if q.dtype == torch.bfloat16 else 0, _stream()),
+                                     dpad, float(scale), 1 if q.dtype == torch.bfloat16 else 0, _stream(), _ptr(prof)),
              "l4p_attention")
     if ev is not None:
         ev[1].record()

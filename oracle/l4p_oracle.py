@@ -637,3 +637,64 @@ def track_head_window(sd: SD, pre: str, enc_features, queries_bn3, labels_bn, pr
     out["track_2d_vis_est_bn1t"] = logits[:, 1].mean(dim=[-1, -2])[None].unsqueeze(2)
     out["track_2d_depth_est_bn1t"] = torch.exp(logits[:, 2].mean(dim=[-1, -2]))[None].unsqueeze(2)
     return out
+
+
+def track_windowed(sd: SD, pre: str, feats_last_per_window: Sequence[torch.Tensor], queries_bn3: torch.Tensor,
+                   labels_bn: torch.Tensor, starts: Sequence[int], image_size=(16, 224, 224),
+                   patch=(2, 14, 14)) -> Dict[str, torch.Tensor]:
+    """VideoMAETrack2DSamHead.forward_windowed_core, sparse_heads.py:213-495, forward direction (sign = +1), B == 1,
+    with the shipped flags (prompt_using_features, attend_to_past, modify_pointlabels_for_windowing).
+    feats_last_per_window[w]: final-norm encoder tokens [1,P,C] of window w."""
+    Tw = image_size[0]
+    et, eh, ew = image_size[0] // patch[0], image_size[1] // patch[1], image_size[2] // patch[2]
+    B, N = queries_bn3.shape[:2]
+    assert B == 1
+    C = feats_last_per_window[0].shape[-1]
+    Pn = et * eh * ew
+    T = int(starts[-1] + Tw)
+    traj = torch.zeros(B, N, 2, T)
+    vis = -torch.ones(B, N, 1, T) * 10.0
+    dep = torch.zeros(B, N, 1, T)
+    pfeat = torch.zeros(B, N, C)
+    plab = torch.zeros(B, N)
+    mask_tok = sd[pre + "processed_video_mask_token.weight"][0]
+    hist = mask_tok[None, None, None, :].repeat(B, N, Pn, 1)
+    cur_q, cur_lab = queries_bn3.clone(), labels_bn.clone()
+    nW = len(starts)
+    for wi in range(nW):
+        s = int(starts[wi])
+        nxt = int(starts[wi + 1]) if wi < nW - 1 else int(starts[wi - 1])
+        q_off = cur_q.clone()
+        valid_t = (torch.arange(Tw).repeat(B, N, 1) + s + 0.5 - q_off[:, :, 0:1]) >= 0
+        valid_t = valid_t[:, :, None, :]
+        valid = valid_t.sum(dim=-1)[..., 0] > 0
+        q_off[:, :, 0] -= s
+        cur_lab[~valid] = 0
+        cur_lab[valid] = 1
+        same = (cur_q == queries_bn3).sum(dim=-1) > 0
+        cur_lab[same] = 1
+        cur_lab[torch.logical_and(valid, ~same)] = 2
+        enc = feats_last_per_window[wi].unsqueeze(1) + hist
+        out = track_head_window(sd, pre, enc, q_off, cur_lab, pfeat, plab, image_size)
+        sl = slice(s, s + Tw)
+        vis[..., sl][valid_t] = out["track_2d_vis_est_bn1t"][valid_t]
+        traj[..., 0:1, sl][valid_t] = out["track_2d_traj_est_bn2t"][:, :, 0:1][valid_t]
+        traj[..., 1:2, sl][valid_t] = out["track_2d_traj_est_bn2t"][:, :, 1:2][valid_t]
+        dep[..., sl][valid_t] = out["track_2d_depth_est_bn1t"][valid_t]
+        if wi == nW - 1:
+            continue
+        pfeat[valid] = out["track_2d_prompt_features_bnc"][valid]
+        plab[valid] = 1
+        h = out["track_2d_enc_features_with_track_history_bnpc"].reshape(B, N, et, eh * ew, C)
+        pad = mask_tok[None, None, None, None, :].repeat(B, N, et // 2, eh * ew, 1)
+        hist = torch.cat([h[:, :, et // 2:], pad], dim=2).reshape(B, N, Pn, C)
+        ov0, ov1 = nxt, s + Tw
+        best = torch.argmax(vis[..., ov0:ov1], dim=-1)
+        new_q = []
+        for i in range(N):
+            xy = traj[0, i, :, ov0:ov1][:, best[0, i, 0]]
+            new_q.append(torch.tensor([float(best[0, i, 0]) + nxt + 0.5, float(xy[0]), float(xy[1])])[None, None])
+        new_q = torch.cat(new_q, dim=1)
+        later = new_q[0, :, 0] > cur_q[0, :, 0]
+        cur_q[0, later, :] = new_q[0, later, :]
+    return {"track_2d_traj_est_bn2t": traj, "track_2d_vis_est_bn1t": vis, "track_2d_depth_est_bn1t": dep}
