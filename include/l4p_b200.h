@@ -168,6 +168,18 @@ int l4p_affine_align_solve(const float* pred, const float* target, int B, int64_
 /* y = f(s*f(x)+t) (LstSqAffineAligner.apply, aligner.py:59-66); x,y [B,n]. */
 int l4p_affine_align_apply(const float* x, float* y, const float* sol, int B, int64_t n, int inverse, void* stream);
 
+/* ---- K17: joint depth + pose similarity aligner --------------------------------------------------- */
+/* Similarity transform dst ~ s R src + t between the point maps of the overlap frames (every frame_step-th of
+ * `overlap`) of the current window (src) and of the stitched buffer (dst): weighted Umeyama iterated `iters`
+ * times with consensus re-selection at *thr_dev (device scalar). Replaces KabaschUmeyama3DAligner.solve
+ * (l4p/models/aligner.py:177-237: CPU numpy + skimage RANSAC) and generate_point_map (geometry_utils.py:13-53).
+ * depth_* fp32 [T_*,H,W] (one clip), K_* fp32 [4,4,T_*] pixel intrinsics, pose_* fp32 [16,T_*] (cam->world).
+ * Result in ws[17..33]: 4x4 row-major T (doubles) followed by the scale; ws[0..16] is scratch. */
+int l4p_sim3_align(const float* depth_src, const float* K_src, const float* pose_src, int T_src,
+                   const float* depth_dst, const float* K_dst, const float* pose_dst, int T_dst, int overlap,
+                   int frame_step, int H, int W, const float* thr_dev, int iters, int min_points, double* ws,
+                   void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -440,6 +440,111 @@ __global__ void affine_apply_kernel(const float* __restrict__ x, float* __restri
   }
 }
 
+// ---------------------------------------------------------------------------------------------- sim(3) window aligner
+// K17: KabaschUmeyama3DAligner.solve (aligner.py:177-237) on the device. Point maps X = pose [depth K^-1 (u,v,1); 1]
+// (geometry_utils.py:13-53) of every `step`-th overlap frame are formed on the fly for the current window (src) and
+// the stitched buffer (dst); a weighted Umeyama fit is iterated with consensus re-selection
+// (|dst - T src| < thr, thr = 0.01 * q98(depth), aligner.py:187-188) instead of the reference's randomised
+// skimage RANSAC on a 10% subsample: deterministic, uses every point, and equals the closed-form Umeyama
+// solution whenever all points are inliers. The acceptance radius is graduated (2^(iters-1-it) * thr).
+struct Sim3Frame {
+  double Kinv[9];
+  double P[12];  // pose rows 0..2 (3x4)
+};
+__device__ void sim3_point(const Sim3Frame& f, float depth, int u, int v, double* X) {
+  const double cx = (f.Kinv[0] * u + f.Kinv[1] * v + f.Kinv[2]) * depth;
+  const double cy = (f.Kinv[3] * u + f.Kinv[4] * v + f.Kinv[5]) * depth;
+  const double cz = (f.Kinv[6] * u + f.Kinv[7] * v + f.Kinv[8]) * depth;
+  for (int i = 0; i < 3; ++i) X[i] = f.P[i * 4] * cx + f.P[i * 4 + 1] * cy + f.P[i * 4 + 2] * cz + f.P[i * 4 + 3];
+}
+__device__ void sim3_load_frame(const float* K_b44t, const float* pose_b16t, int T, int t, Sim3Frame& f) {
+  double K[9];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) K[i * 3 + j] = (double)K_b44t[(i * 4 + j) * T + t];
+  inv3(K, f.Kinv);
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 4; ++j) f.P[i * 4 + j] = (double)pose_b16t[(i * 4 + j) * T + t];
+}
+
+// sums[17]: n, sum src(3), sum dst(3), sum |src|^2, sum dst src^T (9). Tprev (16 doubles, row-major) or use_prev = 0.
+__global__ void __launch_bounds__(256)
+sim3_reduce_kernel(const float* __restrict__ depth_s, const float* __restrict__ K_s, const float* __restrict__ pose_s, int Ts,
+                   const float* __restrict__ depth_d, const float* __restrict__ K_d, const float* __restrict__ pose_d, int Td,
+                   int nframes, int step, int H, int W, const double* __restrict__ Tprev, int use_prev, const float* thr_ptr,
+                   float thr_scale, double* __restrict__ sums) {
+  __shared__ double red[17 * 32];
+  __shared__ Sim3Frame fs, fd;
+  const int fi = blockIdx.y;
+  const int t = fi * step;
+  if (threadIdx.x == 0) {
+    sim3_load_frame(K_s, pose_s, Ts, t, fs);
+    sim3_load_frame(K_d, pose_d, Td, t, fd);
+  }
+  __syncthreads();
+  const double thr2 = (double)thr_ptr[0] * thr_ptr[0] * (double)thr_scale * (double)thr_scale;
+  double a[17];
+  for (int i = 0; i < 17; ++i) a[i] = 0.0;
+  const int n = H * W;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+    const int v = p / W, u = p - v * W;
+    double S[3], D[3];
+    sim3_point(fs, depth_s[(long long)t * n + p], u, v, S);
+    sim3_point(fd, depth_d[(long long)t * n + p], u, v, D);
+    bool use = true;
+    if (use_prev) {
+      double e2 = 0.0;
+      for (int i = 0; i < 3; ++i) {
+        const double m = Tprev[i * 4] * S[0] + Tprev[i * 4 + 1] * S[1] + Tprev[i * 4 + 2] * S[2] + Tprev[i * 4 + 3];
+        e2 += (D[i] - m) * (D[i] - m);
+      }
+      use = e2 < thr2;
+    }
+    if (use) {
+      a[0] += 1.0;
+      for (int i = 0; i < 3; ++i) { a[1 + i] += S[i]; a[4 + i] += D[i]; }
+      a[7] += S[0] * S[0] + S[1] * S[1] + S[2] * S[2];
+      for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) a[8 + i * 3 + j] += D[i] * S[j];
+    }
+  }
+  block_sum<17>(a, red);
+  if (threadIdx.x == 0)
+    for (int i = 0; i < 17; ++i) atomicAdd(&sums[i], a[i]);
+}
+
+// Umeyama (with scale) from the accumulated moments -> T (4x4 row-major doubles) and scale; keeps Tprev if degenerate.
+__global__ void sim3_solve_kernel(const double* __restrict__ sums, double* __restrict__ Tout, int min_points) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const double n = sums[0];
+  if (n < (double)min_points) return;  // keep the previous estimate (initialised to identity by the host)
+  double ms[3], md[3];
+  for (int i = 0; i < 3; ++i) { ms[i] = sums[1 + i] / n; md[i] = sums[4 + i] / n; }
+  double cov[9];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) cov[i * 3 + j] = sums[8 + i * 3 + j] / n - md[i] * ms[j];
+  const double var_s = sums[7] / n - (ms[0] * ms[0] + ms[1] * ms[1] + ms[2] * ms[2]);
+  double U[9], S[3], V[9];
+  svd3(cov, U, S, V);
+  double Vt[9], UVt[9];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) Vt[i * 3 + j] = V[j * 3 + i];
+  mul3(U, Vt, UVt);
+  const double dsg = det3(cov) < 0 ? -1.0 : 1.0;  // Umeyama: reflect when det(cov) < 0
+  (void)UVt;
+  double Ud[9];
+  for (int i = 0; i < 3; ++i) { Ud[i * 3] = U[i * 3]; Ud[i * 3 + 1] = U[i * 3 + 1]; Ud[i * 3 + 2] = U[i * 3 + 2] * dsg; }
+  double R[9];
+  mul3(Ud, Vt, R);
+  const double scale = var_s > 0 ? (S[0] + S[1] + dsg * S[2]) / var_s : 1.0;
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) Tout[i * 4 + j] = scale * R[i * 3 + j];
+    Tout[i * 4 + 3] = md[i] - scale * (R[i * 3] * ms[0] + R[i * 3 + 1] * ms[1] + R[i * 3 + 2] * ms[2]);
+  }
+  Tout[12] = Tout[13] = Tout[14] = 0.0;
+  Tout[15] = 1.0;
+  Tout[16] = scale;
+}
+
 }  // namespace l4p
 
 using namespace l4p;
@@ -489,5 +594,37 @@ extern "C" int l4p_affine_align_apply(const float* x, float* y, const float* sol
   if (g > 8LL * host_num_sms()) g = 8LL * host_num_sms();
   affine_apply_kernel<<<dim3((unsigned)g, B), 256, 0, (cudaStream_t)stream_>>>(x, y, sol, n, inverse);
   L4P_CHECK_CUDA(cudaGetLastError());
+  return L4P_OK;
+}
+
+extern "C" int l4p_sim3_align(const float* depth_src, const float* K_src, const float* pose_src, int T_src,
+                              const float* depth_dst, const float* K_dst, const float* pose_dst, int T_dst, int overlap,
+                              int frame_step, int H, int W, const float* thr_dev, int iters, int min_points,
+                              double* ws /* 17 + 17 doubles */, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  L4P_REQUIRE(depth_src && K_src && pose_src && depth_dst && K_dst && pose_dst && thr_dev && ws, L4P_ERR_ARG,
+              "l4p_sim3_align: null pointer");
+  L4P_REQUIRE(overlap > 0 && frame_step > 0 && H > 0 && W > 0 && iters >= 1 && overlap <= T_src && overlap <= T_dst,
+              L4P_ERR_SHAPE, "l4p_sim3_align: bad shape");
+  const int nframes = (overlap + frame_step - 1) / frame_step;
+  double* sums = ws;
+  double* Tcur = ws + 17;  // 16 matrix entries + scale
+  const double ident[17] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 1};
+  L4P_CHECK_CUDA(cudaMemcpyAsync(Tcur, ident, sizeof(ident), cudaMemcpyHostToDevice, stream));
+  int gx = (H * W + 255) / 256;
+  if (gx > 64) gx = 64;
+  for (int it = 0; it < iters; ++it) {
+    // graduated consensus: the acceptance radius shrinks by 2x per iteration down to the reference threshold, so a
+    // biased all-points start still keeps the true inliers while gross outliers drop out first
+    const int sh = iters - 1 - it;
+    const float thr_scale = (float)(1u << (sh < 0 ? 0 : (sh > 20 ? 20 : sh)));
+    L4P_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 17, stream));
+    sim3_reduce_kernel<<<dim3(gx, nframes), 256, 0, stream>>>(depth_src, K_src, pose_src, T_src, depth_dst, K_dst, pose_dst,
+                                                              T_dst, nframes, frame_step, H, W, Tcur, it > 0, thr_dev,
+                                                              thr_scale, sums);
+    L4P_CHECK_CUDA(cudaGetLastError());
+    sim3_solve_kernel<<<1, 32, 0, stream>>>(sums, Tcur, min_points);
+    L4P_CHECK_CUDA(cudaGetLastError());
+  }
   return L4P_OK;
 }

@@ -71,3 +71,28 @@ def test_track_readout_peaked():
     assert (traj[:, 0].cpu() - rx).abs().max() < 1e-3 and (traj[:, 1].cpu() - ry).abs().max() < 1e-3
     assert (vis.cpu() - 0.25).abs().max() < 1e-6
     assert (depth.cpu() - torch.exp(torch.tensor(-1.5))).abs().max() < 1e-6
+
+
+def test_track_two_windows_memory_vs_oracle():
+    """Sliding-window memory tracker over T=24 (2 windows, stride 8): history roll, label state machine,
+    argmax-visibility re-query (sparse_heads.py:213-495) against the oracle restatement."""
+    from oracle import l4p_oracle as O
+
+    head = _head()
+    sd = {k: v.clone() for k, v in head.state_dict().items()}
+    g = torch.Generator().manual_seed(9)
+    feats = [torch.randn(1, 2048, 1408, generator=g) for _ in range(2)]
+    q = torch.tensor([[[0.5, 50.5, 60.5], [3.5, 150.5, 100.5], [12.5, 100.5, 180.5], [18.5, 30.5, 200.5]]])
+    lab = torch.ones(1, 4)
+    head = head.cuda()
+    f2d = [[None] * 40 + [f.cuda()] for f in feats]
+    out = head.forward_windowed(f2d, q.cuda(), lab.cuda(), time_strides=torch.tensor([0, 8]))
+    torch.cuda.synchronize()
+    ref = O.track_windowed(sd, "", feats, q, lab, [0, 8])
+    for k in ("track_2d_traj_est_bn2t", "track_2d_vis_est_bn1t", "track_2d_depth_est_bn1t"):
+        a, b = out[k].cpu(), ref[k]
+        assert a.shape == b.shape == (1, 4, b.shape[2], 24)
+        assert torch.equal(a == 0, b == 0) and torch.equal(a == -10, b == -10), f"{k}: written-frame mask differs"
+    assert (out["track_2d_traj_est_bn2t"].cpu() - ref["track_2d_traj_est_bn2t"]).abs().max() < 0.1      # pixels
+    assert (out["track_2d_vis_est_bn1t"].cpu() - ref["track_2d_vis_est_bn1t"]).abs().max() < 1e-2
+    assert rel_l2(out["track_2d_depth_est_bn1t"], ref["track_2d_depth_est_bn1t"]) < 3e-3
