@@ -129,6 +129,131 @@ token_attention_kernel(const float* __restrict__ q, const uint16_t* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------
+// Hot-shape specialisation of token_attention: head_dim D compile-time (88), nq <= 6, many keys.
+//   pass 1  thread-per-key, channel-chunk outer loop: the 6 x 8 query values of a chunk sit in registers and are
+//           reused for the thread's KPT keys; every 16-byte key load is independent (deep memory-level parallelism)
+//   pass 2  half-warps walk the keys, 11 lanes x 16 bytes cover one V row, 48 accumulators per lane
+// ------------------------------------------------------------------------------------------------
+template <bool BF16, int D, int NQ>
+__global__ void __launch_bounds__(256)
+token_attention_fast_kernel(const float* __restrict__ q, const uint16_t* __restrict__ k16, const uint16_t* __restrict__ v16,
+                            float* __restrict__ out, int Nk, int ldq, int ldkv, long long kv_group_rows, float scale) {
+  constexpr int C8 = D / 8;       // 16-byte chunks per row
+  constexpr int KPT = 8;          // keys per thread in pass 1 (Nk <= 256 * KPT)
+  extern __shared__ float sm[];
+  float* s_scores = sm;                 // [NQ][Nk]
+  float* s_q = s_scores + NQ * Nk;      // [NQ][D]
+  float* s_part = s_q + NQ * D;         // [16][NQ][D]
+  __shared__ float s_sum[NQ];
+  const int h = blockIdx.x, g = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* qg = q + ((long long)g * NQ) * ldq + h * D;
+  const uint16_t* kg = k16 + (long long)g * kv_group_rows * ldkv + h * D;
+  const uint16_t* vg = v16 + (long long)g * kv_group_rows * ldkv + h * D;
+  for (int i = tid; i < NQ * D; i += 256) s_q[i] = qg[(i / D) * ldq + (i % D)] * scale;
+  __syncthreads();
+  {
+    float acc[KPT][NQ];
+#pragma unroll
+    for (int kk = 0; kk < KPT; ++kk)
+#pragma unroll
+      for (int j = 0; j < NQ; ++j) acc[kk][j] = 0.f;
+#pragma unroll 1
+    for (int c8 = 0; c8 < C8; ++c8) {
+      float qq[NQ][8];
+#pragma unroll
+      for (int j = 0; j < NQ; ++j) {
+        const float4 a = *reinterpret_cast<const float4*>(s_q + j * D + c8 * 8);
+        const float4 b = *reinterpret_cast<const float4*>(s_q + j * D + c8 * 8 + 4);
+        qq[j][0] = a.x; qq[j][1] = a.y; qq[j][2] = a.z; qq[j][3] = a.w;
+        qq[j][4] = b.x; qq[j][5] = b.y; qq[j][6] = b.z; qq[j][7] = b.w;
+      }
+      uint4 raw[KPT];
+#pragma unroll
+      for (int kk = 0; kk < KPT; ++kk) {
+        const int key = tid + kk * 256;
+        raw[kk] = key < Nk ? *reinterpret_cast<const uint4*>(kg + (long long)key * ldkv + c8 * 8) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int kk = 0; kk < KPT; ++kk) {
+        const uint32_t w[4] = {raw[kk].x, raw[kk].y, raw[kk].z, raw[kk].w};
+        float kv[8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 f = unpack2<BF16>(w[i]);
+          kv[2 * i] = f.x; kv[2 * i + 1] = f.y;
+        }
+#pragma unroll
+        for (int j = 0; j < NQ; ++j)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[kk][j] = fmaf(kv[i], qq[j][i], acc[kk][j]);
+      }
+    }
+#pragma unroll
+    for (int kk = 0; kk < KPT; ++kk) {
+      const int key = tid + kk * 256;
+      if (key < Nk)
+#pragma unroll
+        for (int j = 0; j < NQ; ++j) s_scores[j * Nk + key] = acc[kk][j];
+    }
+  }
+  __syncthreads();
+  if (warp < NQ) {
+    float m = -INFINITY;
+    for (int key = lane; key < Nk; key += 32) m = fmaxf(m, s_scores[warp * Nk + key]);
+    m = warp_max(m);
+    float sum = 0.f;
+    for (int key = lane; key < Nk; key += 32) {
+      const float pv = __expf(s_scores[warp * Nk + key] - m);
+      s_scores[warp * Nk + key] = pv;
+      sum += pv;
+    }
+    sum = warp_sum(sum);
+    if (lane == 0) s_sum[warp] = sum;
+  }
+  __syncthreads();
+  {
+    const int half = lane >> 4, l16 = lane & 15;  // two keys per warp iteration; lanes 0..C8-1 of each half active
+    float o[NQ][8];
+#pragma unroll
+    for (int j = 0; j < NQ; ++j)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[j][i] = 0.f;
+    if (l16 < C8) {
+#pragma unroll 4
+      for (int key = warp * 2 + half; key < Nk; key += 16) {
+        const uint4 raw = *reinterpret_cast<const uint4*>(vg + (long long)key * ldkv + l16 * 8);
+        const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+        float vv[8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 f = unpack2<BF16>(w[i]);
+          vv[2 * i] = f.x; vv[2 * i + 1] = f.y;
+        }
+#pragma unroll
+        for (int j = 0; j < NQ; ++j) {
+          const float pj = s_scores[j * Nk + key];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[j][i] = fmaf(pj, vv[i], o[j][i]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < NQ; ++j)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s_part[((warp * 2 + half) * NQ + j) * D + l16 * 8 + i] = o[j][i];
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < NQ * D; i += 256) {
+    const int j = i / D;
+    float a = 0.f;
+#pragma unroll
+    for (int w = 0; w < 16; ++w) a += s_part[(w * NQ + j) * D + (i % D)];
+    out[((long long)g * NQ + j) * ldq + h * D + (i % D)] = a / s_sum[j];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // q16 [G*Np, H*d] ; k,v fp32 [G, nk, H*d] ; out16 [G*Np, H*d]. One thread per (row, head); block = rows_per_block x H.
 // ------------------------------------------------------------------------------------------------
 template <bool BF16, int D>
@@ -204,23 +329,28 @@ image_attention_kernel(const uint16_t* __restrict__ q16, const float* __restrict
 }
 
 // ------------------------------------------------------------------------------------------------
-// LayerNorm over 16-bit rows (+ optional GELU), one warp per row, cols multiple of 8 and <= 2048.
+// LayerNorm over 16-bit rows (+ optional GELU). LPR lanes cooperate on one row (32/LPR rows per warp in flight,
+// which is what makes short rows like the 352-channel LayerNorm3d bandwidth- instead of latency-bound);
+// cols multiple of 8, cols <= LPR * 8 * kLn16Iters.
 // ------------------------------------------------------------------------------------------------
-template <bool BF16>
+constexpr int kLn16Iters = 8;
+template <bool BF16, int LPR>
 __global__ void __launch_bounds__(256)
 layernorm16_kernel(const uint16_t* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                    uint16_t* __restrict__ y, long long rows, int cols, float eps, int gelu) {
+  constexpr int RPW = 32 / LPR;  // rows per warp
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
-  if (row >= rows) return;
+  const int sub = lane / LPR, l = lane % LPR;
+  const long long row = ((long long)blockIdx.x * (blockDim.x >> 5) + warp) * RPW + sub;
+  const bool ok = row < rows;
   const int nch = cols >> 3;
-  const uint4* xr = reinterpret_cast<const uint4*>(x + row * cols);
-  float v[8][8];
+  const uint4* xr = reinterpret_cast<const uint4*>(x + (ok ? row : 0) * cols);
+  float v[kLn16Iters][8];
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int j = lane + i * 32;
-    if (j < nch) {
+  for (int i = 0; i < kLn16Iters; ++i) {
+    const int j = l + i * LPR;
+    if (ok && j < nch) {
       const uint4 raw = xr[j];
       const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
@@ -231,24 +361,32 @@ layernorm16_kernel(const uint16_t* __restrict__ x, const float* __restrict__ gam
       }
     }
   }
-  const float mean = warp_sum(s) / (float)cols;
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / (float)cols;
   float qq = 0.f;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int j = lane + i * 32;
-    if (j < nch)
+  for (int i = 0; i < kLn16Iters; ++i) {
+    const int j = l + i * LPR;
+    if (ok && j < nch)
 #pragma unroll
       for (int t = 0; t < 8; ++t) { const float dlt = v[i][t] - mean; qq += dlt * dlt; }
   }
-  const float rstd = rsqrtf(warp_sum(qq) / (float)cols + eps);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int j = lane + i * 32;
-    if (j < nch) {
+  for (int o = LPR / 2; o > 0; o >>= 1) qq += __shfl_xor_sync(0xffffffffu, qq, o);
+  const float rstd = rsqrtf(qq / (float)cols + eps);
+#pragma unroll
+  for (int i = 0; i < kLn16Iters; ++i) {
+    const int j = l + i * LPR;
+    if (ok && j < nch) {
+      const float4 g0 = reinterpret_cast<const float4*>(gamma)[2 * j], g1 = reinterpret_cast<const float4*>(gamma)[2 * j + 1];
+      const float4 b0 = reinterpret_cast<const float4*>(beta)[2 * j], b1 = reinterpret_cast<const float4*>(beta)[2 * j + 1];
+      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
       float o[8];
 #pragma unroll
       for (int t = 0; t < 8; ++t) {
-        o[t] = (v[i][t] - mean) * rstd * gamma[j * 8 + t] + beta[j * 8 + t];
+        o[t] = (v[i][t] - mean) * rstd * gg[t] + bb[t];
         if (gelu) o[t] = gelu_erf_fast(o[t]);
       }
       reinterpret_cast<uint4*>(y + row * cols)[j] = make_uint4(pack2<BF16>(o[0], o[1]), pack2<BF16>(o[2], o[3]),
@@ -350,6 +488,15 @@ extern "C" int l4p_token_attention(const float* q, const void* k16, const void* 
               "l4p_token_attention: nq=%d (<=8) Nk=%d d=%d (multiple of 8, <=192)", nq, Nk, d);
   const size_t smem = sizeof(float) * ((size_t)nq * Nk + (size_t)nq * d + 8 * (size_t)nq * d);
   L4P_REQUIRE(smem <= 200 * 1024, L4P_ERR_SHAPE, "l4p_token_attention: Nk=%d too large", Nk);
+  if (d == 88 && nq == 6 && Nk <= 2048 && Nk >= 256) {
+    const size_t sm2 = sizeof(float) * ((size_t)6 * Nk + 6 * 88 + 16 * 6 * 88);
+    auto kf = bf16 ? token_attention_fast_kernel<true, 88, 6> : token_attention_fast_kernel<false, 88, 6>;
+    L4P_CHECK_CUDA(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    kf<<<dim3(H, G), 256, sm2, (cudaStream_t)stream>>>(q, (const uint16_t*)k16, (const uint16_t*)v16, out, Nk, H * d, H * d,
+                                                        kv_group_rows, scale);
+    L4P_CHECK_CUDA(cudaGetLastError());
+    return L4P_OK;
+  }
   auto kfn = bf16 ? token_attention_kernel<true> : token_attention_kernel<false>;
   L4P_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   kfn<<<dim3(H, G), 256, smem, (cudaStream_t)stream>>>(q, (const uint16_t*)k16, (const uint16_t*)v16, out, nq, Nk, d, H * d,
@@ -383,11 +530,18 @@ extern "C" int l4p_layernorm16(const void* x16, const float* gamma, const float*
   L4P_REQUIRE(x16 && gamma && beta && y16, L4P_ERR_ARG, "l4p_layernorm16: null pointer");
   L4P_REQUIRE(rows >= 0 && cols > 0 && cols % 8 == 0 && cols <= 2048, L4P_ERR_SHAPE, "l4p_layernorm16: cols=%d", cols);
   if (rows == 0) return L4P_OK;
-  const unsigned grid = (unsigned)((rows + 7) / 8);
-  if (bf16)
-    layernorm16_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>((const uint16_t*)x16, gamma, beta, (uint16_t*)y16, rows, cols, eps, gelu);
-  else
-    layernorm16_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>((const uint16_t*)x16, gamma, beta, (uint16_t*)y16, rows, cols, eps, gelu);
+  cudaStream_t st = (cudaStream_t)stream;
+  const uint16_t* x = (const uint16_t*)x16;
+  uint16_t* y = (uint16_t*)y16;
+  if (cols <= 8 * 8 * kLn16Iters) {  // short rows: 8 lanes per row, 4 rows per warp
+    const unsigned grid = (unsigned)((rows + 31) / 32);
+    if (bf16) layernorm16_kernel<true, 8><<<grid, 256, 0, st>>>(x, gamma, beta, y, rows, cols, eps, gelu);
+    else layernorm16_kernel<false, 8><<<grid, 256, 0, st>>>(x, gamma, beta, y, rows, cols, eps, gelu);
+  } else {
+    const unsigned grid = (unsigned)((rows + 7) / 8);
+    if (bf16) layernorm16_kernel<true, 32><<<grid, 256, 0, st>>>(x, gamma, beta, y, rows, cols, eps, gelu);
+    else layernorm16_kernel<false, 32><<<grid, 256, 0, st>>>(x, gamma, beta, y, rows, cols, eps, gelu);
+  }
   L4P_CHECK_CUDA(cudaGetLastError());
   return L4P_OK;
 }

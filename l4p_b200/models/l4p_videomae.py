@@ -27,7 +27,8 @@ class L4P_VideoMAE(torch.nn.Module):
                  freeze_video_encoder: bool = False, freeze_heads: Optional[List[str]] = None,
                  unfreeze_blocks: Optional[List[int]] = None, always_use_windowed_version: bool = False,
                  joint_alignment: bool = False, cam_emb_placed_at_enc: Optional[str] = None, cam_emb_type: str = "add",
-                 compute_dtype: torch.dtype = torch.float16, max_windows_per_pass: int = 8, device=None) -> None:
+                 compute_dtype: torch.dtype = torch.float16, max_windows_per_pass: int = 8, parallel_heads: bool = True,
+                 device=None) -> None:
         super().__init__()
         # Same hyper-parameters as the reference (l4p_videomae.py:163-186): ViT-giant, patch 14, tubelet 2.
         self.video_encoder = VideoMAEEncoder(
@@ -48,6 +49,8 @@ class L4P_VideoMAE(torch.nn.Module):
         self.always_use_windowed_version = always_use_windowed_version
         self.joint_alignment = joint_alignment
         self.max_windows_per_pass = max_windows_per_pass
+        self.parallel_heads = parallel_heads  # run independent task heads on concurrent CUDA streams
+        self._streams: Dict[Any, List[torch.cuda.Stream]] = {}
         self.set_compute_dtype(compute_dtype)
         # freeze_* / unfreeze_blocks are training-only knobs: accepted for config compatibility, parameters of
         # this inference-only implementation never require grad.
@@ -95,6 +98,31 @@ class L4P_VideoMAE(torch.nn.Module):
             per_window.append([None if f is None else f[sl] for f in batched])
         return batched, per_window
 
+    def _run_jobs(self, jobs, device):
+        if not self.parallel_heads or len(jobs) < 2 or device.type != "cuda":
+            return [j() for j in jobs]
+        main = torch.cuda.current_stream(device)
+        streams = self._streams.setdefault(device, [])
+        while len(streams) < len(jobs):
+            streams.append(torch.cuda.Stream(device=device))
+        start = torch.cuda.Event()
+        start.record(main)
+        results, done = [], []
+        for job, st in zip(jobs, streams):
+            st.wait_event(start)
+            with torch.cuda.stream(st):
+                res = job()
+                for v in res.values():
+                    if torch.is_tensor(v):
+                        v.record_stream(main)  # the caller consumes the outputs on its own stream
+                e = torch.cuda.Event()
+                e.record(st)
+            results.append(res)
+            done.append(e)
+        for e in done:
+            main.wait_event(e)
+        return results
+
     def forward(self, data: Dict[str, Any], tasks: List[str]) -> Dict[str, Any]:
         """Main forward pass for both single and multi-window inference (l4p_videomae.py:256-330)."""
         B, _, T, H, W = data["rgb_b3thw"].shape
@@ -107,22 +135,22 @@ class L4P_VideoMAE(torch.nn.Module):
         batched, enc_features_bpc_2dlist = self._encode_windows(data["rgb_b3thw"], [int(s) for s in time_strides])
         out: Dict[str, Any] = {"enc_features_bpc_2dlist": enc_features_bpc_2dlist}
 
+        # The heads only read the encoder features: they are independent jobs (the reference runs them one after the
+        # other, l4p_videomae.py:299-328). Each job runs on its own CUDA stream so that the low-occupancy kernels of
+        # one head (low-resolution pyramid levels, token-side GEMMs, small solves) overlap the big kernels of another.
+        common = dict(enc_features_bpc_2dlist=enc_features_bpc_2dlist, time_strides=time_strides, _batched_windows=batched)
+        jobs = []
         joint_alignment_possible = "depth" in tasks and "camray" in tasks
         if self.joint_alignment and joint_alignment_possible:
             for task in ["track_2d", "dyn_mask", "flow_2d_backward"]:
                 if task in tasks:
-                    out.update(self.task_heads[task].forward_windowed(
-                        enc_features_bpc_2dlist=enc_features_bpc_2dlist, time_strides=time_strides,
-                        _batched_windows=batched, **data))
-            assert "depth" in tasks and "camray" in tasks, "Depth and camray must be present for joint alignment"
-            out.update(joint_windowed_estimation(["depth", "camray"], self.task_heads,
-                                                 enc_features_bpc_2dlist=enc_features_bpc_2dlist,
-                                                 time_strides=time_strides, _batched_windows=batched, **data))
+                    jobs.append(lambda task=task: self.task_heads[task].forward_windowed(**common, **data))
+            jobs.append(lambda: joint_windowed_estimation(["depth", "camray"], self.task_heads, **common, **data))
         else:
             if self.joint_alignment:
                 print("Joint alignment is not possible as depth or camray tasks are not present")
             for task in tasks:
-                out.update(self.task_heads[task].forward_windowed(
-                    enc_features_bpc_2dlist=enc_features_bpc_2dlist, time_strides=time_strides,
-                    _batched_windows=batched, **data))
+                jobs.append(lambda task=task: self.task_heads[task].forward_windowed(**common, **data))
+        for res in self._run_jobs(jobs, data["rgb_b3thw"].device):
+            out.update(res)
         return out
