@@ -94,6 +94,7 @@ typedef struct l4p_gemm_desc {
    * out_f32[g, c, t', h', w'] = sum_co act(acc+bias)[tap, co] * w2[g, c, co], g = row / rows_per_group, c < c2 <= 4 */
   int64_t rows_per_group;
   int block_n;         /* N tile (multiple of 16, <= 256); 0 = choose                              */
+  int cta_pair;        /* 0 = auto, 1 = force the 2-CTA (cta_group::2, 256-row tile) kernel, -1 = never */
 } l4p_gemm_desc;
 
 /* Replaces F.linear/addmm (modeling_finetune.py:62-69,171-177,188), the 1x1x1/3x3x3 Conv3d and k==s

@@ -43,6 +43,7 @@ class GemmDesc(C.Structure):
         ("w2", C.c_void_p), ("b2", C.c_void_p), ("c2", C.c_int), ("exp_out", C.c_int),
         ("rows_per_group", C.c_int64),
         ("block_n", C.c_int),
+        ("cta_pair", C.c_int),
     ]
 
 

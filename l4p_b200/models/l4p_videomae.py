@@ -49,7 +49,8 @@ class L4P_VideoMAE(torch.nn.Module):
         self.always_use_windowed_version = always_use_windowed_version
         self.joint_alignment = joint_alignment
         self.max_windows_per_pass = max_windows_per_pass
-        self.parallel_heads = parallel_heads  # run independent task heads on concurrent CUDA streams
+        # run independent task heads on concurrent CUDA streams (L4P_SERIAL_HEADS=1 turns it off for per-op profiling)
+        self.parallel_heads = parallel_heads and __import__("os").environ.get("L4P_SERIAL_HEADS", "0") != "1"
         self._streams: Dict[Any, List[torch.cuda.Stream]] = {}
         self.set_compute_dtype(compute_dtype)
         # freeze_* / unfreeze_blocks are training-only knobs: accepted for config compatibility, parameters of

@@ -17,6 +17,7 @@ _initialised = set()
 # --- instrumentation used by bench.py (never changes results) ------------------------------------------
 LAUNCHES = 0            # kernels launched through this module since import (bench.py reports the delta)
 ATTN_EVENTS = None      # set to a list to record (start, end) CUDA events around every attention launch
+GEMM_PAIR = int(__import__("os").environ.get("L4P_GEMM_PAIR", "0"))  # 0 auto, 1 force 2-CTA tiles, -1 never (tuning/tests)
 
 
 def _dev_init(t: torch.Tensor) -> None:
@@ -77,6 +78,7 @@ def _base_desc(a: torch.Tensor, w: torch.Tensor) -> _l.GemmDesc:
         raise _l.L4PError(f"operand dtypes differ: {a.dtype} vs {w.dtype}")
     d = _l.GemmDesc()
     d.a = a.data_ptr(); d.w = w.data_ptr()
+    d.cta_pair = GEMM_PAIR
     d.bf16 = 1 if a.dtype == torch.bfloat16 else 0
     return d
 
