@@ -20,6 +20,8 @@
 //   Q, K : [B, H, N, dpad]   (dpad = 96, columns >= head_dim are zero)
 //   Vt   : [B, H, dpad, N]
 //   out  : [B*N, H*head_dim] row-major 16-bit (operand of the output projection GEMM)
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace l4p {
@@ -53,7 +55,48 @@ L4P_DEVICE float ex2(float x) {
 #define ATT_STAMP(role, it, slot) \
   do { if (p.prof != nullptr && blockIdx.x == 0 && lane == 0 && (it) < 64) p.prof[((role) * 64 + (it)) * 8 + (slot)] = clock64(); } while (0)
 
-template <bool BF16>
+// ---- packed fp32x2 math (Blackwell FFMA2/FADD2): two elements per FMA-pipe issue slot
+L4P_DEVICE uint64_t pk2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+L4P_DEVICE void upk2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+L4P_DEVICE uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+L4P_DEVICE uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// 2^x for a pair on the FMA/ALU pipes (no MUFU): round-to-nearest split x = n + f, f in [-0.5, 0.5], cubic minimax for
+// 2^f (max rel err 7.6e-5, well below the 16-bit rounding of P), exponent patched in with an integer add.
+L4P_DEVICE uint64_t exp2_poly2(uint64_t t2) {
+  float a, b;
+  upk2(t2, a, b);
+  a = fmaxf(a, -125.0f);
+  b = fmaxf(b, -125.0f);
+  t2 = pk2(a, b);
+  const uint64_t magic = pk2(12582912.0f, 12582912.0f), nmagic = pk2(-12582912.0f, -12582912.0f);
+  const uint64_t mone = pk2(-1.0f, -1.0f);
+  const uint64_t xf = add2(t2, magic);   // low mantissa bits = round(x)
+  const uint64_t n2 = add2(xf, nmagic);
+  const uint64_t f2 = fma2(n2, mone, t2);
+  uint64_t p2 = fma2(pk2(0.05520550534129143f, 0.05520550534129143f), f2, pk2(0.24261397123336792f, 0.24261397123336792f));
+  p2 = fma2(p2, f2, pk2(0.6932547688484192f, 0.6932547688484192f));
+  p2 = fma2(p2, f2, pk2(0.9999276995658875f, 0.9999276995658875f));
+  float pa, pb, xa, xb;
+  upk2(p2, pa, pb);
+  upk2(xf, xa, xb);
+  pa = __int_as_float(__float_as_int(pa) + (__float_as_int(xa) << 23));
+  pb = __int_as_float(__float_as_int(pb) + (__float_as_int(xb) << 23));
+  return pk2(pa, pb);
+}
+
+template <bool BF16, int POLY>
 __global__ void __launch_bounds__(kAttThreads, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const AttParams p) {
@@ -267,17 +310,34 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 
       ATT_STAMP(t, j, 3);
       // p = exp2(s*c - m_used), row sum in fp32, pack pairs in place
-      float l0 = 0.f, l1 = 0.f;
-      const float nm = -m_used;
+      // scale/subtract and the row sum run as packed f32x2; of every 16 scores, 6 take the polynomial exp2 on the
+      // FMA pipe and 10 the MUFU, which balances the two pipes (MUFU alone is the measured bound of this kernel)
+      const uint64_t c2 = pk2(c, c), nm2 = pk2(-m_used, -m_used);
+      uint64_t lsum0 = pk2(0.f, 0.f), lsum1 = pk2(0.f, 0.f);
 #pragma unroll
       for (int i = 0; i < 128; i += 2) {
-        const float p0 = ex2(fmaf(__uint_as_float(s[i]), c, nm));
-        const float p1 = ex2(fmaf(__uint_as_float(s[i + 1]), c, nm));
-        l0 += p0;
-        l1 += p1;
+        const uint64_t t2 = fma2(pk2(__uint_as_float(s[i]), __uint_as_float(s[i + 1])), c2, nm2);
+        uint64_t p2;
+        const int slot = (i >> 1) & 7;  // pair index inside a group of 16 scores
+        if ((POLY == 3 && (slot == 1 || slot == 4 || slot == 6)) || (POLY == 2 && (slot == 1 || slot == 5)) ||
+            (POLY == 1 && slot == 3)) {
+          p2 = exp2_poly2(t2);
+        } else {
+          float a, b;
+          upk2(t2, a, b);
+          p2 = pk2(ex2(a), ex2(b));
+        }
+        if (i & 2) lsum1 = add2(lsum1, p2); else lsum0 = add2(lsum0, p2);
+        float p0, p1;
+        upk2(p2, p0, p1);
         s[i >> 1] = pack2<BF16>(p0, p1);
       }
-      l += l0 + l1;
+      {
+        float a0, a1, b0, b1;
+        upk2(lsum0, a0, a1);
+        upk2(lsum1, b0, b1);
+        l += (a0 + a1) + (b0 + b1);
+      }
       ATT_STAMP(t, j, 4);
 
       if (j > 0) mbar_wait(smem_u32(&bar_pvdone[t]), (uint32_t)(j - 1) & 1u);  // P_t smem is free again
@@ -364,11 +424,22 @@ extern "C" int l4p_attention(const void* q, const void* k, const void* vt, void*
   p.B = B; p.H = H; p.N = N; p.head_dim = head_dim;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.prof = (long long*)prof;
-  auto kfn = bf16 ? attention_kernel<true> : attention_kernel<false>;
-  static bool attr_set[2] = {false, false};
-  if (!attr_set[bf16 ? 1 : 0]) {
+  // POLY = number of score pairs (of every 8) whose exp2 runs as an FMA-pipe polynomial instead of MUFU
+  static int poly = -1;
+  if (poly < 0) {
+    const char* e = getenv("L4P_ATT_POLY");
+    poly = e ? atoi(e) : 2;
+    if (poly < 0 || poly > 3) poly = 0;
+  }
+  typedef void (*KFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const AttParams);
+  static const KFn table[2][4] = {
+      {attention_kernel<false, 0>, attention_kernel<false, 1>, attention_kernel<false, 2>, attention_kernel<false, 3>},
+      {attention_kernel<true, 0>, attention_kernel<true, 1>, attention_kernel<true, 2>, attention_kernel<true, 3>}};
+  KFn kfn = table[bf16 ? 1 : 0][poly];
+  static bool attr_set[2][4] = {};
+  if (!attr_set[bf16 ? 1 : 0][poly]) {
     L4P_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmem));
-    attr_set[bf16 ? 1 : 0] = true;
+    attr_set[bf16 ? 1 : 0][poly] = true;
   }
   const int grid = B * H * (N / (2 * kTileM));
   kfn<<<grid, kAttThreads, kAttSmem, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
