@@ -95,6 +95,7 @@ typedef struct l4p_gemm_desc {
   int64_t rows_per_group;
   int block_n;         /* N tile (multiple of 16, <= 256); 0 = choose                              */
   int cta_pair;        /* 0 = auto, 1 = force the 2-CTA (cta_group::2, 256-row tile) kernel, -1 = never */
+  void* prof;          /* NULL, or device int64[3*512]: clock64 timeline of CTA 0 (producer / MMA / epilogue; tuning aid) */
 } l4p_gemm_desc;
 
 /* Replaces F.linear/addmm (modeling_finetune.py:62-69,171-177,188), the 1x1x1/3x3x3 Conv3d and k==s
@@ -146,7 +147,8 @@ int l4p_track_readout(const float* masks, float* traj, float* vis, float* depth,
  * (l4p/models/VideoMAEv2/models/modeling_finetune.py:180-186); the [B,H,N,N] score tensor is never
  * materialised. q,k: [B,H,N,head_dim_pad]; vt: [B,H,head_dim_pad,N] (pad lanes zero); out 16-bit
  * [B*N, H*head_dim]. This build: head_dim_pad == 96, N a multiple of 256.
- * prof: NULL, or a device buffer of 3*64*8 int64 that receives clock64 stamps of CTA 0 (kernel tuning aid). */
+ * prof: NULL, or a device buffer of 3*64*8 + 5*grid int64 that receives clock64 stamps of CTA 0 followed by
+ * per-CTA {globaltimer start, end, clock64 start, end, smid} (kernel tuning aid). */
 int l4p_attention(const void* q, const void* k, const void* vt, void* out, int B, int H, int N,
                   int head_dim, int head_dim_pad, float scale, int bf16, void* stream, void* prof);
 

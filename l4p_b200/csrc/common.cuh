@@ -338,6 +338,67 @@ L4P_DEVICE float erf_fast(float x) {
 }
 L4P_DEVICE float gelu_erf_fast(float x) { return 0.5f * x * (1.0f + erf_fast(x * 0.70710678118654752440f)); }
 
+L4P_DEVICE float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+L4P_DEVICE float rcp_fast(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// ---- packed fp32x2 math (Blackwell FFMA2/FADD2): two elements per FMA-pipe issue slot
+L4P_DEVICE uint64_t pk2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+L4P_DEVICE void upk2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+L4P_DEVICE uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+L4P_DEVICE uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+L4P_DEVICE uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
+// exact-erf GELU of two values with the arithmetic packed two-wide (A&S 7.1.26 as erf_fast, raw MUFU rcp / ex2 without
+// the denormal range fix-ups: 1 + 0.33|z| >= 1 and the ex2 argument is <= 0, flushing to zero is the right answer)
+L4P_DEVICE void gelu2(float& x0, float& x1) {
+  const uint64_t x = pk2(x0, x1);
+  const uint64_t z = mul2(x, pk2(0.70710678118654752440f, 0.70710678118654752440f));
+  float z0, z1;
+  upk2(z, z0, z1);
+  const uint64_t az = pk2(fabsf(z0), fabsf(z1));
+  float u0, u1;
+  upk2(fma2(az, pk2(0.3275911f, 0.3275911f), pk2(1.0f, 1.0f)), u0, u1);
+  const uint64_t t = pk2(rcp_fast(u0), rcp_fast(u1));
+  uint64_t q = fma2(pk2(-1.061405429f, -1.061405429f), t, pk2(1.453152027f, 1.453152027f));  // -poly(t)
+  q = fma2(q, t, pk2(-1.421413741f, -1.421413741f));
+  q = fma2(q, t, pk2(0.284496736f, 0.284496736f));
+  q = fma2(q, t, pk2(-0.254829592f, -0.254829592f));
+  q = mul2(q, t);
+  float w0, w1;
+  upk2(mul2(mul2(z, z), pk2(-1.4426950408889634f, -1.4426950408889634f)), w0, w1);
+  const uint64_t e = pk2(ex2(w0), ex2(w1));
+  float y0, y1;
+  upk2(fma2(q, e, pk2(1.0f, 1.0f)), y0, y1);  // erf(|z|) = 1 - poly(t) t exp(-z^2)
+  y0 = copysignf(y0, z0);
+  y1 = copysignf(y1, z1);
+  const uint64_t h = mul2(x, pk2(0.5f, 0.5f));
+  upk2(fma2(h, pk2(y0, y1), h), x0, x1);
+}
+
 L4P_DEVICE float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

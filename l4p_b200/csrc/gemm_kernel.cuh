@@ -1,0 +1,795 @@
+// Persistent, warp-specialised tcgen05 GEMM / implicit-GEMM 3-D convolution kernels for sm_100a (device side).
+//
+//   D[M,N] = epilogue(A[M,K] * W[N,K]^T)
+//
+//   warps 0..7  epilogue       (tcgen05.ld -> bias/activation/residual -> global stores); two warpgroups interleave
+//               column chunks so that the latency-bound epilogue of one overlaps the other
+//   warp 8      TMA producer   (A/B tiles -> 128B-swizzled smem ring, mbarrier complete_tx)
+//   warp 9      UMMA issuer    (tcgen05.mma kind::f16, fp32 accumulators in TMEM, 2 accumulator stages)
+//   warp 10     TMEM allocator
+// The two single-thread pipeline warps sit at the HIGHEST warp indices: the SM's issue arbiter favours high warp ids,
+// and a producer / MMA issuer starved by eight busy epilogue warps stalls the tensor pipe.
+//
+// A-operand modes:
+//   A_MATRIX  plain row-major [M,K] matrix, one 2-D TMA box (64 x 128) per k-block.
+//   A_CONV3D  channels-last activations [B,T,H,W,C]; a 128-row tile is a (bT,bH,bW) voxel box and the k-loop
+//             runs over (filter tap, 64-channel block): every tap is the same 5-D TMA box shifted by the tap
+//             offset, the zero padding comes from TMA out-of-bounds fill. No im2col buffer exists.
+//
+// The epilogue is specialised at COMPILE TIME (template parameter EPI, see epi_* below): a single warp executes it
+// row by row with little latency hiding, so every runtime mode test / parameter reload inside its loops costs tens of
+// cycles. gemm.cu maps a descriptor to the matching instance; EPI_GENERIC instances keep all ROWMAJOR options runtime.
+//
+// Reference call sites replaced: modeling_finetune.py:62-69,171-177,188 (Linear), dpt_block.py:29-90,
+// 144-157,255-278,406-414 (Conv3d / ConvTranspose3d), sam/transformer.py:223-245.
+#pragma once
+#include "common.cuh"
+
+namespace l4p {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;                       // 64 x 2 B = one 128 B swizzle row
+constexpr int kABytes = kBlockM * kBlockK * 2;    // 16 KiB
+constexpr int kMaxStages = 8;
+constexpr int kAccCols = 256;                     // TMEM columns per accumulator stage
+constexpr int kEpiGroups = 2;                     // epilogue warpgroups: group g handles chunks c with c % kEpiGroups == g
+constexpr int kGemmThreads = 128 + 128 * kEpiGroups;
+constexpr int kWarpProducer = 4 * kEpiGroups, kWarpMma = kWarpProducer + 1, kWarpAlloc = kWarpProducer + 2;
+constexpr int kEpiChunk = 32;                     // columns per transposed chunk
+constexpr int kEpiStageBytes = 32 * 128;          // per-warp staging: 32 rows x 32 fp32
+constexpr int kEpiSmemBytes = 4 * kEpiGroups * kEpiStageBytes;
+
+// ---- compile-time epilogue configuration -------------------------------------------------------------------------
+//   bits 0-2 store mode (L4P_STORE_*), bits 3-4 activation (L4P_ACT_*), then ROWMAJOR option flags
+constexpr int EPI_RES32 = 1 << 5;    // fp32 residual (optionally a broadcast table: res_row_mod)
+constexpr int EPI_RES16 = 1 << 6;    // one or two 16-bit residuals (null-checked at run time)
+constexpr int EPI_OUT32 = 1 << 7;
+constexpr int EPI_OUT16 = 1 << 8;
+constexpr int EPI_OUT16R = 1 << 9;   // second 16-bit output = relu(out)
+constexpr int EPI_GENERIC = 1 << 10; // activation and ROWMAJOR options decided at run time (slow, always correct)
+constexpr int epi_make(int store, int act, int flags) { return store | (act << 3) | flags; }
+constexpr int epi_store(int e) { return e & 7; }
+constexpr int epi_act(int e) { return (e >> 3) & 3; }
+
+struct GemmKParams {
+  int M, N, num_kb, block_n, stages;
+  int tiles_m, tiles_n;
+  int a_mode;
+  // conv geometry
+  int cB, cT, cH, cW, cCin, kT, kH, kW, bT, bH, bW, ntT, ntH, ntW, cblocks;
+  // epilogue
+  const float* bias;
+  int act;
+  const float* res_f32;
+  const uint16_t* res_16;
+  const uint16_t* res2_16;
+  int ld_res;
+  int res_row_mod;
+  int store_mode;
+  float* out_f32;
+  uint16_t* out_16;
+  uint16_t* out_16_relu;
+  int ld_out;
+  uint16_t *q, *k, *vt;
+  int heads, head_dim, head_dim_pad, tokens;
+  int sT, sH, sW, ctCout;
+  const float* w2;
+  const float* b2;
+  int c2, exp_out;
+  long long rows_per_group;  // STORE_HYPER: w2 is indexed by row / rows_per_group
+  long long* prof;           // optional [3][512] clock64 timeline of CTA 0
+};
+
+#define GEMM_STAMP(role, idx) \
+  do { if (p.prof != nullptr && blockIdx.x == 0 && (idx) < 512) p.prof[(role) * 512 + (idx)] = clock64(); } while (0)
+
+struct TileCoord {
+  int m_blk, n_blk;
+  int b, t0, h0, w0;  // conv mode
+};
+
+L4P_DEVICE TileCoord decode_block(const GemmKParams& p, int m_blk, int n_blk) {
+  TileCoord c;
+  c.n_blk = n_blk;
+  c.m_blk = m_blk;
+  c.b = c.t0 = c.h0 = c.w0 = 0;
+  if (p.a_mode == L4P_A_CONV3D) {
+    int r = c.m_blk;
+    c.w0 = (r % p.ntW) * p.bW; r /= p.ntW;
+    c.h0 = (r % p.ntH) * p.bH; r /= p.ntH;
+    c.t0 = (r % p.ntT) * p.bT; r /= p.ntT;
+    c.b = r;  // may be >= cB for the padding block of an odd tile count (2-CTA mode): TMA zero-fills, rows are masked
+  }
+  return c;
+}
+L4P_DEVICE TileCoord decode_tile(const GemmKParams& p, int tile) {
+  return decode_block(p, tile / p.tiles_n, tile % p.tiles_n);
+}
+
+L4P_DEVICE void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+L4P_DEVICE float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+template <bool BF16>
+L4P_DEVICE void add_res16(float4& a, const uint16_t* p) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  const float2 lo = unpack2<BF16>(u.x), hi = unpack2<BF16>(u.y);
+  a.x += lo.x; a.y += lo.y; a.z += hi.x; a.w += hi.y;
+}
+template <bool BF16>
+L4P_DEVICE void store4_16(uint16_t* p, const float4& v) {
+  *reinterpret_cast<uint2*>(p) = make_uint2(pack2<BF16>(v.x, v.y), pack2<BF16>(v.z, v.w));
+}
+// activation of a pair (the GELU runs two-wide on the packed f32x2 pipe)
+template <int ACT>
+L4P_DEVICE void apply_act2(float& a, float& b) {
+  if constexpr (ACT == L4P_ACT_GELU) gelu2(a, b);
+  else if constexpr (ACT == L4P_ACT_RELU) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+}
+L4P_DEVICE void apply_act2_rt(float& a, float& b, int act) {
+  if (act == L4P_ACT_GELU) gelu2(a, b);
+  else if (act == L4P_ACT_RELU) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Epilogue. One 128-row x block_n accumulator tile: TMEM -> registers -> bias / activation / residual -> global memory.
+// Shared by the 1-CTA and the 2-CTA (cta_group::2) kernels; `release` hands the accumulator stage back to the MMA warp.
+//
+// tcgen05.ld gives every thread ONE ROW of the tile (lane = row), which is the worst possible shape for global memory:
+// a warp-wide 16-byte access touches 32 different rows. The store modes that write the tile out (ROWMAJOR / QKV /
+// CONVT) therefore transpose each 32-row x 32-column fp32 sub-tile through a per-warp 4 KiB swizzled staging buffer:
+//   phase A (lane = row)          raw accumulators -> 8 x st.shared.v4
+//   phase B (8 lanes = one row)   ld.shared.v4 of 4 consecutive columns -> bias, activation, residual -> coalesced
+//                                 128 B (fp32) / 64 B (16-bit) row segments, 4 rows per instruction
+// Residuals are fetched in the phase-B shape too (coalesced) one chunk ahead, so their latency hides behind the
+// previous chunk; the first fetch is issued before the tile's accumulator is even complete.
+// The fused-dot modes (HEAD1X1 / HYPER) keep the row-per-thread form: they reduce along the row and store ~nothing.
+// ------------------------------------------------------------------------------------------------------------------
+template <bool BF16, int EPI, class Release>
+L4P_DEVICE void epilogue_tile(const GemmKParams& p, const TileCoord& tc, const int q4, const int lane, const int egrp,
+                              const uint32_t tfull_bar, const uint32_t tfull_phase, const uint32_t t_acc, float* s_head,
+                              const uint32_t stage, Release release) {
+  constexpr int STORE = epi_store(EPI);
+  constexpr bool GEN = (EPI & EPI_GENERIC) != 0;
+  const int r = q4 * 32 + lane;  // row inside the tile
+  long long row;                 // logical output row
+  bool row_ok;
+  int cb_ = 0, ct_ = 0, ch_ = 0, cw_ = 0;
+  if (p.a_mode == L4P_A_CONV3D) {
+    const int wl = r % p.bW;
+    const int hl = (r / p.bW) % p.bH;
+    const int tl = r / (p.bW * p.bH);
+    ct_ = tc.t0 + tl; ch_ = tc.h0 + hl; cw_ = tc.w0 + wl; cb_ = tc.b;
+    row_ok = (ct_ < p.cT) && (ch_ < p.cH) && (cw_ < p.cW) && (cb_ < p.cB);
+    row = (((long long)cb_ * p.cT + ct_) * p.cH + ch_) * p.cW + cw_;
+  } else {
+    row = (long long)tc.m_blk * kBlockM + r;
+    row_ok = row < p.M;
+  }
+  const int n0 = tc.n_blk * p.block_n;
+  const uint32_t t_addr = t_acc + ((uint32_t)(q4 * 32) << 16);
+
+  if constexpr (STORE == L4P_STORE_ROWMAJOR || STORE == L4P_STORE_QKV || STORE == L4P_STORE_CONVT) {
+    // ---------------------------------------------------------------- transposed (coalesced) store modes
+    const bool res32 = GEN ? (p.res_f32 != nullptr) : ((EPI & EPI_RES32) != 0);
+    const bool res16 = GEN ? (p.res_16 != nullptr || p.res2_16 != nullptr) : ((EPI & EPI_RES16) != 0);
+    const bool out32 = GEN ? (p.out_f32 != nullptr) : ((EPI & EPI_OUT32) != 0);
+    const bool out16 = GEN ? (p.out_16 != nullptr) : ((EPI & EPI_OUT16) != 0);
+    const bool out16r = GEN ? (p.out_16_relu != nullptr) : ((EPI & EPI_OUT16R) != 0);
+    const bool has_res = STORE == L4P_STORE_ROWMAJOR && (res32 || res16);
+
+    // per-row indices, gathered into the phase-B shape: iteration `it` of a lane works on row it*4 + lane/8
+    int my_o, my_r = 0;
+    if constexpr (STORE == L4P_STORE_ROWMAJOR) {
+      my_o = (int)row;
+      my_r = p.res_row_mod > 0 ? (int)(row % p.res_row_mod) : (int)row;
+    } else if constexpr (STORE == L4P_STORE_QKV) {
+      const int bidx = (int)(row / p.tokens);
+      my_o = bidx * p.heads * p.tokens + (int)(row - (long long)bidx * p.tokens);  // row of head 0 in the [B,H,N,dpad] view
+    } else {
+      long long rr = row;
+      const int w_ = (int)(rr % p.cW); rr /= p.cW;
+      const int h_ = (int)(rr % p.cH); rr /= p.cH;
+      const int t_ = (int)(rr % p.cT); rr /= p.cT;
+      my_o = (int)(((rr * (p.cT * p.sT) + (long long)t_ * p.sT) * (p.cH * p.sH) + (long long)h_ * p.sH) * (p.cW * p.sW) +
+                   (long long)w_ * p.sW);  // output voxel of tap (0,0,0)
+    }
+    const int sub = lane & 7, rgrp = lane >> 3;
+    int orow[8], rrow[8];
+    uint32_t okm = 0;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int src = it * 4 + rgrp;
+      orow[it] = __shfl_sync(0xffffffffu, my_o, src);
+      rrow[it] = res32 ? __shfl_sync(0xffffffffu, my_r, src) : 0;
+      okm |= (__shfl_sync(0xffffffffu, row_ok ? 1u : 0u, src) & 1u) << it;
+    }
+    const int ncols = min(p.block_n, p.N - n0);  // valid columns of this tile
+    const int D = p.heads * p.head_dim;
+    const int ld_out = p.ld_out, ld_res = p.ld_res;
+    const float* const res_f32 = p.res_f32;
+    const uint16_t* const res_16 = p.res_16;
+    const uint16_t* const res2_16 = p.res2_16;
+    float* const out_f32 = p.out_f32;
+    uint16_t* const out_16 = p.out_16;
+    uint16_t* const out_16_relu = p.out_16_relu;
+    const int act_rt = p.act;
+
+    // residual of the 4-column group (n0 + c0 + 4*sub) of phase-B row `it`, summed in fp32
+    auto fetch_res = [&](const int c0, const int it) -> float4 {
+      const int colg = c0 + sub * 4;
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (colg < ncols && ((okm >> it) & 1u)) {
+        if (res32) a = *reinterpret_cast<const float4*>(res_f32 + ((long long)rrow[it] * ld_res + (n0 + colg)));
+        if (res16) {
+          const long long o = (long long)orow[it] * ld_res + (n0 + colg);
+          if (res_16 != nullptr) add_res16<BF16>(a, res_16 + o);
+          if (res2_16 != nullptr) add_res16<BF16>(a, res2_16 + o);
+        }
+      }
+      return a;
+    };
+
+    float4 rcur[8];
+    int c0 = egrp * kEpiChunk;
+    if (has_res && c0 < ncols) {  // in flight while the MMA warp finishes the tile
+#pragma unroll
+      for (int it = 0; it < 8; ++it) rcur[it] = fetch_res(c0, it);
+    }
+
+    mbar_wait(tfull_bar, tfull_phase);
+    tc_fence_after();
+
+    for (; c0 < p.block_n; c0 += kEpiChunk * kEpiGroups) {
+      uint32_t raw[32];
+      __syncwarp();  // tcgen05.ld is warp-collective; also orders the previous chunk's staging reads before new writes
+      tmem_ld32(t_addr + (uint32_t)c0, raw);
+      tmem_ld_wait();
+      if (c0 >= ncols) continue;  // uniform across the CTA
+      const int col0 = n0 + c0;
+
+      if constexpr (STORE == L4P_STORE_QKV) {
+        if (col0 + kEpiChunk > 2 * D) {
+          // V section (or a chunk straddling into it): V^T is written keys-contiguous, which the row-per-thread shape
+          // already coalesces (32 lanes = 32 consecutive keys)
+          if (row_ok) {
+            const long long bidx = row / p.tokens;
+            const int tok = (int)(row - bidx * p.tokens);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const int col = col0 + g * 8;
+              if (c0 + g * 8 < ncols) {
+                const int sct = col / D;
+                const int rem = col - sct * D;
+                const int h = rem / p.head_dim;
+                const int e = rem - h * p.head_dim;
+                const long long bh = bidx * p.heads + h;
+                float vv[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) vv[i] = __uint_as_float(raw[g * 8 + i]) + (p.bias ? p.bias[col + i] : 0.f);
+                if (sct < 2) {
+                  uint16_t* dst = (sct == 0 ? p.q : p.k) + (bh * p.tokens + tok) * p.head_dim_pad + e;
+                  *reinterpret_cast<uint4*>(dst) = make_uint4(pack2<BF16>(vv[0], vv[1]), pack2<BF16>(vv[2], vv[3]),
+                                                              pack2<BF16>(vv[4], vv[5]), pack2<BF16>(vv[6], vv[7]));
+                } else {
+                  uint16_t* dst = p.vt + (bh * p.head_dim_pad + e) * (long long)p.tokens + tok;
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) dst[(long long)i * p.tokens] = pack1<BF16>(vv[i]);
+                }
+              }
+            }
+          }
+          continue;
+        }
+      }
+
+      // phase A: lane = row, 16-byte units XOR-swizzled by the row so that both phases are bank-conflict free
+      {
+        const uint32_t wbase = stage + (uint32_t)lane * 128u;
+        const uint32_t sw = (uint32_t)(lane & 7);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) sts128(wbase + ((((uint32_t)u) ^ sw) << 4), raw[4 * u], raw[4 * u + 1], raw[4 * u + 2], raw[4 * u + 3]);
+      }
+      __syncwarp();
+
+      // the next chunk's residual is fetched row by row as soon as the current value has been consumed
+      const int cn = c0 + kEpiChunk * kEpiGroups;
+      const bool more = has_res && cn < ncols;
+
+      // phase B
+      const int colg = c0 + sub * 4;
+      const bool cok = colg < ncols;
+      const int col = n0 + colg;
+      float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p.bias != nullptr && cok) b4 = *reinterpret_cast<const float4*>(p.bias + col);
+
+      // per-lane column decode of the scatter modes (the 4-column group never straddles a head / tap: both are
+      // multiples of 8 wide)
+      long long coff = 0;     // QKV: h * tokens * dpad + e ; CONVT: tap voxel offset * Cout + co
+      uint16_t* sbase = nullptr;
+      int srow_ld = 0;
+      if constexpr (STORE == L4P_STORE_QKV) {
+        const int sct = col / D;
+        const int rem = col - sct * D;
+        const int h = rem / p.head_dim;
+        const int e = rem - h * p.head_dim;
+        sbase = (sct == 0 ? p.q : p.k) + ((long long)h * p.tokens * p.head_dim_pad + e);
+        srow_ld = p.head_dim_pad;
+      } else if constexpr (STORE == L4P_STORE_CONVT) {
+        const int tapi = col / p.ctCout;
+        const int co = col - tapi * p.ctCout;
+        const int kw = tapi % p.sW;
+        const int kh = (tapi / p.sW) % p.sH;
+        const int kt = tapi / (p.sW * p.sH);
+        coff = (((long long)kt * (p.cH * p.sH) + kh) * (p.cW * p.sW) + kw) * p.ctCout + co;
+        sbase = p.out_16 + coff;
+        srow_ld = p.ctCout;
+      }
+      const uint32_t rbase = stage + (uint32_t)rgrp * 128u;
+
+      float4 xs[8];  // all staging reads first: the asm memory clobbers would otherwise serialise them with the stores
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const uint32_t rl = (uint32_t)(it * 4 + rgrp);
+        xs[it] = lds128(rbase + (uint32_t)it * 512u + ((((uint32_t)sub) ^ (rl & 7u)) << 4));
+      }
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        float4 x = xs[it];
+        x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
+        if constexpr (GEN) {
+          apply_act2_rt(x.x, x.y, act_rt); apply_act2_rt(x.z, x.w, act_rt);
+        } else {
+          apply_act2<epi_act(EPI)>(x.x, x.y); apply_act2<epi_act(EPI)>(x.z, x.w);
+        }
+        if (has_res) {
+          x.x += rcur[it].x; x.y += rcur[it].y; x.z += rcur[it].z; x.w += rcur[it].w;
+          if (more) rcur[it] = fetch_res(cn, it);
+        }
+        if (cok && ((okm >> it) & 1u)) {
+          if constexpr (STORE == L4P_STORE_ROWMAJOR) {
+            const long long o = (long long)orow[it] * ld_out + col;
+            if (out32) *reinterpret_cast<float4*>(out_f32 + o) = x;
+            if (out16) store4_16<BF16>(out_16 + o, x);
+            if (out16r)
+              store4_16<BF16>(out_16_relu + o, make_float4(fmaxf(x.x, 0.f), fmaxf(x.y, 0.f), fmaxf(x.z, 0.f), fmaxf(x.w, 0.f)));
+          } else {  // QKV head-major scatter / CONVT pixel shuffle
+            store4_16<BF16>(sbase + (long long)orow[it] * srow_ld, x);
+          }
+        }
+      }
+    }
+    // accumulator stage drained -> hand TMEM back to the MMA warp
+    tc_fence_before();
+    release();
+    return;
+  } else {
+    // ------------------------------------------------------------------ fused-dot modes (row per thread)
+    mbar_wait(tfull_bar, tfull_phase);
+    tc_fence_after();
+
+    float head_acc[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) head_acc[c] = 0.f;
+    const int c2 = p.c2;
+    const int act_rt = p.act;
+
+    const float* hyper_w = STORE == L4P_STORE_HYPER ? p.w2 + (row / p.rows_per_group) * (long long)(c2 * p.ctCout) : nullptr;
+    for (int c0 = egrp * 16; c0 < p.block_n; c0 += 16 * kEpiGroups) {
+      uint32_t raw[16];
+      __syncwarp();  // tcgen05.ld is warp-collective
+      tmem_ld16(t_addr + (uint32_t)c0, raw);
+      tmem_ld_wait();
+      const int col0 = n0 + c0;
+      if (col0 >= p.N) continue;  // uniform across the CTA
+      float v[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(raw[i]);
+      if (p.bias != nullptr) {
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) {
+          const float4 bv = *reinterpret_cast<const float4*>(p.bias + col0 + i);
+          v[i] += bv.x; v[i + 1] += bv.y; v[i + 2] += bv.z; v[i + 3] += bv.w;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 16; i += 2) {
+        if constexpr (GEN) apply_act2_rt(v[i], v[i + 1], act_rt);
+        else apply_act2<epi_act(EPI)>(v[i], v[i + 1]);
+      }
+      if constexpr (STORE == L4P_STORE_HYPER) {
+        // v = act(acc + bias) of one ConvT tap (this N tile); dot with the per-query hyper-network vectors
+        const float* wg = hyper_w + c0;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (c < c2) {
+            float a = head_acc[c];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 wv = *reinterpret_cast<const float4*>(wg + c * p.ctCout + 4 * i);
+              a = fmaf(v[4 * i], wv.x, a); a = fmaf(v[4 * i + 1], wv.y, a);
+              a = fmaf(v[4 * i + 2], wv.z, a); a = fmaf(v[4 * i + 3], wv.w, a);
+            }
+            head_acc[c] = a;
+          }
+        }
+      } else {  // L4P_STORE_HEAD1X1: v already bias+ReLU'd; accumulate the tiny second conv
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          if (c < c2) {
+            const float* wr = p.w2 + (long long)c * p.N + col0;
+            float a = head_acc[c];
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              const float4 wv = *reinterpret_cast<const float4*>(wr + i);
+              a = fmaf(v[i], wv.x, a); a = fmaf(v[i + 1], wv.y, a);
+              a = fmaf(v[i + 2], wv.z, a); a = fmaf(v[i + 3], wv.w, a);
+            }
+            head_acc[c] = a;
+          }
+        }
+      }
+    }
+    // accumulator stage drained -> hand TMEM back to the MMA warp
+    tc_fence_before();
+    release();
+
+    // the per-row dot products were accumulated per warpgroup over its chunks: reduce them in group 0
+    if (egrp != 0) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) s_head[(egrp - 1) * 128 * 8 + r * 8 + c] = head_acc[c];
+    }
+    named_bar_sync(1, 128 * kEpiGroups);
+    if (egrp == 0) {
+#pragma unroll
+      for (int g2 = 1; g2 < kEpiGroups; ++g2)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) head_acc[c] += s_head[(g2 - 1) * 128 * 8 + r * 8 + c];
+    }
+    named_bar_sync(1, 128 * kEpiGroups);  // s_head may be overwritten by the next tile
+
+    if (STORE == L4P_STORE_HYPER && row_ok && egrp == 0) {
+      // row = input voxel (g,t,h,w) of the [cB,cT,cH,cW] grid; this N tile = tap (kt,kh,kw)
+      long long rr = row;
+      const int w_ = (int)(rr % p.cW); rr /= p.cW;
+      const int h_ = (int)(rr % p.cH); rr /= p.cH;
+      const int t_ = (int)(rr % p.cT); rr /= p.cT;
+      const long long g_ = rr;
+      const int tapi = tc.n_blk;
+      const int kw = tapi % p.sW, kh = (tapi / p.sW) % p.sH, kt = tapi / (p.sW * p.sH);
+      const long long oT = (long long)p.cT * p.sT, oH = (long long)p.cH * p.sH, oW = (long long)p.cW * p.sW;
+      const long long vox = ((long long)(t_ * p.sT + kt) * oH + (h_ * p.sH + kh)) * oW + (w_ * p.sW + kw);
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (c < c2) p.out_f32[((g_ * c2 + c) * oT * oH * oW) + vox] = head_acc[c];
+    }
+    if (STORE == L4P_STORE_HEAD1X1 && row_ok && egrp == 0) {
+      const long long plane = (long long)p.cT * p.cH * p.cW;
+      const long long vox = ((long long)ct_ * p.cH + ch_) * p.cW + cw_;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        if (c < c2) {
+          float o = head_acc[c] + p.b2[c];
+          if (p.exp_out) o = expf(o);
+          p.out_f32[((long long)cb_ * c2 + c) * plane + vox] = o;
+        }
+      }
+    }
+  }
+}
+
+template <bool BF16, int EPI>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const GemmKParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_full[kMaxStages];
+  __shared__ __align__(8) uint64_t bar_empty[kMaxStages];
+  __shared__ __align__(8) uint64_t bar_tfull[2];
+  __shared__ __align__(8) uint64_t bar_tempty[2];
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ float s_head[(kEpiGroups - 1) * 128 * 8];  // cross-warpgroup reduction of the fused head dot products
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t b_bytes = (uint32_t)p.block_n * 128u;
+  const uint32_t stage_bytes = kABytes + b_bytes;
+  const int num_tiles = p.tiles_m * p.tiles_n;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(smem_u32(&bar_full[s]), 1);
+      mbar_init(smem_u32(&bar_empty[s]), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&bar_tfull[s]), 1);
+      mbar_init(smem_u32(&bar_tempty[s]), 128 * kEpiGroups);
+    }
+    fence_mbar_init();
+  }
+  if (warp == kWarpAlloc) tmem_alloc(smem_u32(&tmem_base_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == kWarpProducer) {
+    // ------------------------------------------------------------------ TMA producer
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+    if (lane == 0) {
+      int stage = 0, pg = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const TileCoord tc = decode_tile(p, tile);
+        const int n0 = tc.n_blk * p.block_n;
+        // filter-tap walk (cb fastest, then dw, dh, dt) kept as counters: no divisions in the single-thread hot loop
+        int cb = 0, dw = -(p.kW / 2), dh = -(p.kH / 2), dt = -(p.kT / 2);
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
+          const uint32_t full = smem_u32(&bar_full[stage]);
+          const uint32_t sa = smem_base + stage * stage_bytes;
+          const uint32_t sb = sa + kABytes;
+          mbar_expect_tx(full, stage_bytes);
+          if (p.a_mode == L4P_A_MATRIX) {
+            tma_load_2d(sa, &tmA, full, kb * kBlockK, tc.m_blk * kBlockM);
+          } else {
+            tma_load_5d(sa, &tmA, full, cb * kBlockK, tc.w0 + dw, tc.h0 + dh, tc.t0 + dt, tc.b);
+            if (++cb == p.cblocks) {
+              cb = 0;
+              if (++dw > p.kW / 2) {
+                dw = -(p.kW / 2);
+                if (++dh > p.kH / 2) { dh = -(p.kH / 2); ++dt; }
+              }
+            }
+          }
+          tma_load_2d(sb, &tmB, full, kb * kBlockK, n0);
+          GEMM_STAMP(0, pg); ++pg;
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == kWarpMma) {
+    // ------------------------------------------------------------------ UMMA issuer
+    // whole warp walks the pipeline (warp-uniform control flow), one elected lane issues
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+    const bool leader = elect_one();
+    const uint32_t idesc = umma_idesc_f16(BF16, kBlockM, (uint32_t)p.block_n);
+    constexpr uint32_t hi128 = umma_desc_hi(128, 2);
+    const uint32_t a_lo0 = umma_desc_lo(smem_base), b_lo0 = umma_desc_lo(smem_base + kABytes);
+    const uint32_t stage_step = stage_bytes >> 4;
+    int stage = 0, mg = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(smem_u32(&bar_tempty[acc]), acc_phase ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)acc * kAccCols;
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        mbar_wait(smem_u32(&bar_full[stage]), phase);
+        tc_fence_after();
+        if (leader) {
+          GEMM_STAMP(1, mg);
+          const uint32_t a_lo = a_lo0 + (uint32_t)stage * stage_step, b_lo = b_lo0 + (uint32_t)stage * stage_step;
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            // advance 16 elements (32 B) along K inside the swizzle row: +2 in the (addr >> 4) field
+            umma_ss(d_tmem, umma_desc_make(a_lo + 2 * k, hi128), umma_desc_make(b_lo + 2 * k, hi128), idesc,
+                    (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(smem_u32(&bar_empty[stage]));
+          if (kb == p.num_kb - 1) umma_commit(smem_u32(&bar_tfull[acc]));
+        }
+        __syncwarp();
+        ++mg;
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  } else if (warp < 4 * kEpiGroups) {
+    // ------------------------------------------------------------------ epilogue
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");  // the epilogue holds a 32-column sub-tile + prefetched residuals
+    const int q4 = warp & 3;  // TMEM lane quarter owned by this warp
+    const int egrp = warp >> 2;  // epilogue warpgroup: interleaved 16-column chunks
+    int acc = 0, eg = 0;
+    uint32_t acc_phase = 0;
+    if (threadIdx.x == 0) GEMM_STAMP(2, 511);  // kernel-start reference
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const TileCoord tc = decode_tile(p, tile);
+      const uint32_t tempty = smem_u32(&bar_tempty[acc]);
+      epilogue_tile<BF16, EPI>(p, tc, q4, lane, egrp, smem_u32(&bar_tfull[acc]), acc_phase, tmem_base + (uint32_t)acc * kAccCols,
+                          s_head, smem_base + (uint32_t)p.stages * stage_bytes + (uint32_t)warp * kEpiStageBytes,
+                          [&]() { if (threadIdx.x == 0) GEMM_STAMP(2, 2 * eg); mbar_arrive(tempty); });
+      if (threadIdx.x == 0) GEMM_STAMP(2, 2 * eg + 1);
+      ++eg;
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  } else {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kWarpAlloc) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// 2-CTA variant: a CTA pair (cluster of 2, same TPC) owns a 256-row x block_n tile. Each CTA stages its own 128 rows
+// of A and HALF of the B tile per k-block (32 KiB instead of 48 KiB per 128 output rows: 128-row tiles are
+// L2->SM-bandwidth-bound), the leader issues tcgen05.mma.cta_group::2 (M=256) which reads both CTAs' shared memory and
+// writes each CTA's half of the accumulator into that CTA's own TMEM; both epilogues run independently.
+//   full[s]    lives in the leader: 1 arrival (leader's expect_tx of BOTH CTAs' bytes) + the bytes of all four TMA loads
+//   empty[s]   one per CTA, released by a multicast tcgen05.commit
+//   tfull[a]   one per CTA (multicast commit);   tempty[a] in the leader: all epilogue threads of both CTAs arrive
+// ------------------------------------------------------------------------------------------------------------------
+template <bool BF16, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmKParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_full[kMaxStages];
+  __shared__ __align__(8) uint64_t bar_empty[kMaxStages];
+  __shared__ __align__(8) uint64_t bar_tfull[2];
+  __shared__ __align__(8) uint64_t bar_tempty[2];
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ float s_head[(kEpiGroups - 1) * 128 * 8];
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool is_leader = rank == 0;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t half_n = (uint32_t)p.block_n / 2;
+  const uint32_t b_bytes = half_n * 128u;
+  const uint32_t stage_bytes = kABytes + b_bytes;
+  const int tiles_m2 = (p.tiles_m + 1) / 2;
+  const int num_tiles = tiles_m2 * p.tiles_n;
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(smem_u32(&bar_full[s]), 1);
+      mbar_init(smem_u32(&bar_empty[s]), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&bar_tfull[s]), 1);
+      mbar_init(smem_u32(&bar_tempty[s]), 2 * 128 * kEpiGroups);
+    }
+    fence_mbar_init();
+  }
+  if (warp == kWarpAlloc) tmem_alloc2(smem_u32(&tmem_base_slot), 512);
+  tc_fence_before();
+  cluster_sync_all();  // barriers of both CTAs are initialised before any remote arrive / multicast / peer TMA signal
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == kWarpProducer) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+    if (lane == 0) {
+      int stage = 0, pg = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const int n_blk = tile % p.tiles_n;
+        const TileCoord tc = decode_block(p, (tile / p.tiles_n) * 2 + (int)rank, n_blk);
+        const int n0 = n_blk * p.block_n + (int)(rank * half_n);
+        int cb = 0, dw = -(p.kW / 2), dh = -(p.kH / 2), dt = -(p.kT / 2);
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
+          const uint32_t full_leader = mapa_shared(smem_u32(&bar_full[stage]), 0);
+          const uint32_t sa = smem_base + stage * stage_bytes;
+          const uint32_t sb = sa + kABytes;
+          if (is_leader) mbar_expect_tx(smem_u32(&bar_full[stage]), 2 * stage_bytes);
+          if (p.a_mode == L4P_A_MATRIX) {
+            tma2_load_2d(sa, &tmA, full_leader, kb * kBlockK, tc.m_blk * kBlockM);
+          } else {
+            tma2_load_5d(sa, &tmA, full_leader, cb * kBlockK, tc.w0 + dw, tc.h0 + dh, tc.t0 + dt, tc.b);
+            if (++cb == p.cblocks) {
+              cb = 0;
+              if (++dw > p.kW / 2) {
+                dw = -(p.kW / 2);
+                if (++dh > p.kH / 2) { dh = -(p.kH / 2); ++dt; }
+              }
+            }
+          }
+          tma2_load_2d(sb, &tmB, full_leader, kb * kBlockK, n0);
+          GEMM_STAMP(0, pg); ++pg;
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == kWarpMma) {
+    // ------------------------------------------------------------------ UMMA issuer (leader CTA only)
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+    if (is_leader) {
+      const bool leader_lane = elect_one();
+      const uint32_t idesc = umma_idesc_f16(BF16, 2 * kBlockM, (uint32_t)p.block_n);
+      constexpr uint32_t hi128 = umma_desc_hi(128, 2);
+      const uint32_t a_lo0 = umma_desc_lo(smem_base), b_lo0 = umma_desc_lo(smem_base + kABytes);
+      const uint32_t stage_step = stage_bytes >> 4;
+      int stage = 0, mg = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        mbar_wait(smem_u32(&bar_tempty[acc]), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * kAccCols;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(smem_u32(&bar_full[stage]), phase);
+          tc_fence_after();
+          if (leader_lane) {
+            GEMM_STAMP(1, mg);
+            const uint32_t a_lo = a_lo0 + (uint32_t)stage * stage_step, b_lo = b_lo0 + (uint32_t)stage * stage_step;
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k)
+              umma2_ss(d_tmem, umma_desc_make(a_lo + 2 * k, hi128), umma_desc_make(b_lo + 2 * k, hi128), idesc,
+                       (kb | k) != 0 ? 1u : 0u);
+            umma2_commit_mc(smem_u32(&bar_empty[stage]), 3);
+            if (kb == p.num_kb - 1) umma2_commit_mc(smem_u32(&bar_tfull[acc]), 3);
+          }
+          __syncwarp();
+          ++mg;
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else if (warp < 4 * kEpiGroups) {
+    // ------------------------------------------------------------------ epilogue (both CTAs, own 128 rows)
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");  // the epilogue holds a 32-column sub-tile + prefetched residuals
+    const int q4 = warp & 3;
+    const int egrp = warp >> 2;
+    int acc = 0, eg = 0;
+    uint32_t acc_phase = 0;
+    if (threadIdx.x == 0) GEMM_STAMP(2, 511);  // kernel-start reference
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      const TileCoord tc = decode_block(p, (tile / p.tiles_n) * 2 + (int)rank, tile % p.tiles_n);
+      const uint32_t tempty_leader = mapa_shared(smem_u32(&bar_tempty[acc]), 0);
+      epilogue_tile<BF16, EPI>(p, tc, q4, lane, egrp, smem_u32(&bar_tfull[acc]), acc_phase, tmem_base + (uint32_t)acc * kAccCols,
+                          s_head, smem_base + (uint32_t)p.stages * stage_bytes + (uint32_t)warp * kEpiStageBytes,
+                          [&]() { if (threadIdx.x == 0) GEMM_STAMP(2, 2 * eg); mbar_arrive_cluster(tempty_leader); });
+      if (threadIdx.x == 0) GEMM_STAMP(2, 2 * eg + 1);
+      ++eg;
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  } else {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // nobody exits (or frees TMEM) while the peer may still signal / read this CTA
+  if (warp == kWarpAlloc) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, 512);
+  }
+}
+
+typedef void (*GemmKernelFn)(const CUtensorMap, const CUtensorMap, const GemmKParams);
+
+// One entry per compiled epilogue configuration: [bf16][pair]
+struct GemmKernelSet {
+  int epi;
+  GemmKernelFn fn[2][2];
+};
+#define L4P_GEMM_KERNEL_SET(E) \
+  { (E), { { gemm_kernel<false, (E)>, gemm2_kernel<false, (E)> }, { gemm_kernel<true, (E)>, gemm2_kernel<true, (E)> } } }
+
+// instance groups (gemm_inst_*.cu), searched in order by gemm.cu
+const GemmKernelSet* gemm_instances_a(int* n);
+const GemmKernelSet* gemm_instances_b(int* n);
+const GemmKernelSet* gemm_instances_c(int* n);
+const GemmKernelSet* gemm_instances_d(int* n);
+
+}  // namespace l4p

@@ -44,6 +44,7 @@ class GemmDesc(C.Structure):
         ("rows_per_group", C.c_int64),
         ("block_n", C.c_int),
         ("cta_pair", C.c_int),
+        ("prof", C.c_void_p),
     ]
 
 

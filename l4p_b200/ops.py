@@ -96,7 +96,8 @@ def _epilogue(d: _l.GemmDesc, *, bias=None, act=_l.ACT_NONE, res_f32=None, res_1
 
 
 def linear(a: torch.Tensor, w: torch.Tensor, *, bias=None, act=_l.ACT_NONE, res_f32=None, res_16=None,
-           out_f32=None, out_16=None, out_16_relu=None, block_n: int = 0, res_row_mod: int = 0) -> None:
+           out_f32=None, out_16=None, out_16_relu=None, block_n: int = 0, res_row_mod: int = 0,
+           cta_pair: int = 0, prof: Optional[torch.Tensor] = None) -> None:
     """out[M,N] = act(a[M,K] @ w[N,K]^T + bias) (+ residual). Replaces F.linear/addmm call sites."""
     d = _base_desc(a, w)
     K = a.shape[-1]
@@ -110,6 +111,8 @@ def linear(a: torch.Tensor, w: torch.Tensor, *, bias=None, act=_l.ACT_NONE, res_
     d.store_mode = _l.STORE_ROWMAJOR
     d.block_n = block_n
     d.res_row_mod = res_row_mod
+    d.cta_pair = cta_pair
+    d.prof = _ptr(prof)
     _epilogue(d, bias=bias, act=act, res_f32=res_f32, res_16=res_16, out_f32=out_f32, out_16=out_16,
               out_16_relu=out_16_relu)
     _l.check(_l.load().l4p_gemm(C.byref(d), _stream()), "l4p_gemm(linear)")

@@ -20,6 +20,11 @@ w3 = t(6144, 1408) * 0.03; b3 = torch.zeros(6144, device=dev); o3 = torch.empty(
 cases["fc1"] = lambda: ops.linear(a2, w3, bias=b3, act=lib.ACT_GELU, out_16=o3)
 a4 = t(G * 2048, 1408); w4 = t(704, 1408) * 0.03; b4 = torch.zeros(704, device=dev); o4 = torch.empty(G * 2048, 704, device=dev, dtype=dt)
 cases["kproj"] = lambda: ops.linear(a4, w4, bias=b4, out_16=o4)
+w5 = t(4224, 1408) * 0.03; b5 = torch.zeros(4224, device=dev)
+q5 = torch.empty(1, 16, 2048, 96, device=dev, dtype=dt); k5 = torch.empty_like(q5); v5 = torch.empty(1, 16, 96, 2048, device=dev, dtype=dt)
+cases["qkv"] = lambda: ops.linear_qkv(a2, w5, b5, q5, k5, v5, 16, 88, 2048)
+a6 = t(2048, 6144); w6 = t(1408, 6144) * 0.02
+cases["fc2"] = lambda: ops.linear(a6, w6, bias=b1, res_f32=r2, out_f32=r2)
 for f in cases.values():
     f()
 torch.cuda.synchronize()
