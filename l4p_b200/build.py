@@ -23,7 +23,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC",
     "--expt-relaxed-constexpr",
     "-Xptxas", "-v",
-]
+] + os.environ.get("L4P_NVCC_EXTRA", "").split()  # e.g. -DL4P_GEMM_FINE_PROF=1 for tools/gemm_prof2.py
 
 
 def _nvcc() -> str:

@@ -161,31 +161,45 @@ extern "C" int l4p_gemm(const l4p_gemm_desc* d, void* stream_) {
       L4P_REQUIRE(d->a_mode == L4P_A_CONV3D, L4P_ERR_ARG, "l4p_gemm(head1x1): conv mode only");
       L4P_REQUIRE(d->out_f32 && d->w2 && d->b2 && d->c2 >= 1 && d->c2 <= 8, L4P_ERR_ARG, "l4p_gemm(head1x1): args");
       L4P_REQUIRE(p.tiles_n == 1, L4P_ERR_SHAPE, "l4p_gemm(head1x1): N=%lld must fit one tile", (long long)d->N);
+      L4P_REQUIRE((1 + d->c2) * p.block_n * 4 <= kEpiStageBytes, L4P_ERR_SHAPE,
+                  "l4p_gemm(head1x1): (1+c2)*N = %d floats exceed the %d-byte epilogue staging", (1 + d->c2) * p.block_n, kEpiStageBytes);
       p.w2 = d->w2; p.b2 = d->b2; p.c2 = d->c2; p.exp_out = d->exp_out;
+      L4P_REQUIRE((long long)d->cT * d->cH * d->cW < (1ll << 31), L4P_ERR_SHAPE, "l4p_gemm(head1x1): volume too large");
+      p.fd_bW = make_fastdiv(d->bW); p.fd_bH = make_fastdiv(d->bH);
       break;
     case L4P_STORE_HYPER:
       L4P_REQUIRE(d->out_f32 && d->w2 && d->c2 >= 1 && d->c2 <= 4, L4P_ERR_ARG, "l4p_gemm(hyper): args");
       L4P_REQUIRE(d->ctCout % 16 == 0 && d->N == (int64_t)d->sT * d->sH * d->sW * d->ctCout, L4P_ERR_SHAPE,
                   "l4p_gemm(hyper): N != sT*sH*sW*Cout");
       L4P_REQUIRE(p.block_n == d->ctCout, L4P_ERR_SHAPE, "l4p_gemm(hyper): block_n must equal Cout (one tap per tile)");
+      L4P_REQUIRE(d->rows_per_group % kBlockM == 0 && (1 + d->c2) * p.block_n * 4 <= kEpiStageBytes, L4P_ERR_SHAPE,
+                  "l4p_gemm(hyper): rows_per_group=%lld must be a multiple of 128 and (1+c2)*Cout <= 1024", (long long)d->rows_per_group);
       L4P_REQUIRE(d->M == (int64_t)d->cB * d->cT * d->cH * d->cW && d->rows_per_group > 0, L4P_ERR_SHAPE,
                   "l4p_gemm(hyper): M mismatch");
       p.cB = d->cB; p.cT = d->cT; p.cH = d->cH; p.cW = d->cW;
       p.sT = d->sT; p.sH = d->sH; p.sW = d->sW; p.ctCout = d->ctCout;
       p.w2 = d->w2; p.c2 = d->c2; p.rows_per_group = d->rows_per_group;
+      L4P_REQUIRE(d->M < (1ll << 31) && d->rows_per_group < (1ll << 31), L4P_ERR_SHAPE, "l4p_gemm(hyper): M too large");
+      p.fd_cW = make_fastdiv(d->cW); p.fd_cH = make_fastdiv(d->cH); p.fd_cT = make_fastdiv(d->cT);
+      p.fd_rpg = make_fastdiv((int)d->rows_per_group);
       break;
     default:
       return host_set_error(L4P_ERR_ARG, "l4p_gemm: store_mode=%d", d->store_mode);
   }
 
   const uint32_t stage_bytes = kABytes + (uint32_t)p.block_n * 128u;
-  constexpr uint32_t kRingBudget = 216u * 1024u - (uint32_t)kEpiSmemBytes;  // the epilogue staging lives behind the ring
+  const bool fused_dot = d->store_mode == L4P_STORE_HEAD1X1 || d->store_mode == L4P_STORE_HYPER;
+  const int threads = gemm_threads(d->store_mode);  // epi_groups() only looks at the store-mode bits
+  // store modes: per-warp transposition buffers behind the ring (dynamic); fused-dot modes: the DotShared block (static)
+  const uint32_t epi_bytes = fused_dot ? 0u : (uint32_t)epi_smem_bytes(epi_groups(d->store_mode));
+  // 227 KiB per CTA = ring + 1 KiB alignment + epilogue staging + static (barriers, DotShared ~25 KiB in the fused-dot modes)
+  const uint32_t kRingBudget = (fused_dot ? 196u : 190u) * 1024u;
   int stages = (int)(kRingBudget / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages > p.num_kb) stages = p.num_kb < 2 ? 2 : p.num_kb;
   if (stages > kMaxStages) stages = kMaxStages;
   p.stages = stages;
-  const size_t smem = (size_t)stages * stage_bytes + 1024 + kEpiSmemBytes;
+  const size_t smem = (size_t)stages * stage_bytes + 1024 + epi_bytes;
 
   const int num_tiles = p.tiles_m * p.tiles_n;
   int grid = host_num_sms();
@@ -210,20 +224,20 @@ extern "C" int l4p_gemm(const l4p_gemm_desc* d, void* stream_) {
     if (st2 > p.num_kb) st2 = p.num_kb < 2 ? 2 : p.num_kb;
     if (st2 > kMaxStages) st2 = kMaxStages;
     p.stages = st2;
-    const size_t smem2 = (size_t)st2 * sb2 + 1024 + kEpiSmemBytes;
+    const size_t smem2 = (size_t)st2 * sb2 + 1024 + epi_bytes;
     int g2 = pairs < pair_tiles ? pairs : pair_tiles;
     GemmKernelFn k2 = select_kernel(d, true);
     L4P_REQUIRE(k2 != nullptr, L4P_ERR_ARG, "l4p_gemm: no kernel instance for store_mode=%d", d->store_mode);
-    L4P_CHECK_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, 221 * 1024));
-    k2<<<2 * g2, kGemmThreads, smem2, stream>>>(tmA, tmB, p);
+    L4P_CHECK_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kRingBudget + 1024 + epi_bytes)));
+    k2<<<2 * g2, threads, smem2, stream>>>(tmA, tmB, p);
     L4P_CHECK_CUDA(cudaGetLastError());
     return L4P_OK;
   }
 
   GemmKernelFn kfn = select_kernel(d, false);
   L4P_REQUIRE(kfn != nullptr, L4P_ERR_ARG, "l4p_gemm: no kernel instance for store_mode=%d", d->store_mode);
-  L4P_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 221 * 1024));
-  kfn<<<grid, kGemmThreads, smem, stream>>>(tmA, tmB, p);
+  L4P_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kRingBudget + 1024 + epi_bytes)));
+  kfn<<<grid, threads, smem, stream>>>(tmA, tmB, p);
   L4P_CHECK_CUDA(cudaGetLastError());
   return L4P_OK;
 }

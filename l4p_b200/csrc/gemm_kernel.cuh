@@ -23,6 +23,8 @@
 // Reference call sites replaced: modeling_finetune.py:62-69,171-177,188 (Linear), dpt_block.py:29-90,
 // 144-157,255-278,406-414 (Conv3d / ConvTranspose3d), sam/transformer.py:223-245.
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace l4p {
@@ -32,12 +34,10 @@ constexpr int kBlockK = 64;                       // 64 x 2 B = one 128 B swizzl
 constexpr int kABytes = kBlockM * kBlockK * 2;    // 16 KiB
 constexpr int kMaxStages = 8;
 constexpr int kAccCols = 256;                     // TMEM columns per accumulator stage
-constexpr int kEpiGroups = 2;                     // epilogue warpgroups: group g handles chunks c with c % kEpiGroups == g
-constexpr int kGemmThreads = 128 + 128 * kEpiGroups;
-constexpr int kWarpProducer = 4 * kEpiGroups, kWarpMma = kWarpProducer + 1, kWarpAlloc = kWarpProducer + 2;
+constexpr int kMaxEpiGroups = 4;
 constexpr int kEpiChunk = 32;                     // columns per transposed chunk
 constexpr int kEpiStageBytes = 32 * 128;          // per-warp staging: 32 rows x 32 fp32
-constexpr int kEpiSmemBytes = 4 * kEpiGroups * kEpiStageBytes;
+constexpr int epi_smem_bytes(int groups) { return 4 * groups * kEpiStageBytes; }
 
 // ---- compile-time epilogue configuration -------------------------------------------------------------------------
 //   bits 0-2 store mode (L4P_STORE_*), bits 3-4 activation (L4P_ACT_*), then ROWMAJOR option flags
@@ -49,7 +49,35 @@ constexpr int EPI_OUT16R = 1 << 9;   // second 16-bit output = relu(out)
 constexpr int EPI_GENERIC = 1 << 10; // activation and ROWMAJOR options decided at run time (slow, always correct)
 constexpr int epi_make(int store, int act, int flags) { return store | (act << 3) | flags; }
 constexpr int epi_store(int e) { return e & 7; }
+// Epilogue warpgroups (group g handles column chunks c with c % groups == g). The fused-dot modes are bound by the
+// instruction throughput of their epilogue (GELU + per-row dot products) and need few registers: four groups (640
+// threads); the store modes keep two groups with 200 registers each for the transposed sub-tile and its residuals.
+constexpr int epi_groups(int e) { return (epi_store(e) == L4P_STORE_HEAD1X1 || epi_store(e) == L4P_STORE_HYPER) ? 4 : 2; }
+constexpr int gemm_threads(int e) { return 128 + 128 * epi_groups(e); }
 constexpr int epi_act(int e) { return (e >> 3) & 3; }
+
+// n / d for 0 <= n < 2^31 by multiply-high + shift (host-initialised, CUTLASS FastDivmod construction)
+struct FastDiv {
+  uint32_t mul, shr;
+  int d;
+#ifdef __CUDACC__
+  L4P_DEVICE uint32_t div(uint32_t n) const { return d != 1 ? (__umulhi(n, mul) >> shr) : n; }
+  L4P_DEVICE void divmod(uint32_t n, uint32_t& q, uint32_t& r) const { q = div(n); r = n - q * (uint32_t)d; }
+#endif
+};
+inline FastDiv make_fastdiv(int d) {
+  FastDiv f;
+  f.d = d;
+  f.mul = 0; f.shr = 0;
+  if (d > 1) {
+    int lg = 0;
+    while ((1ll << lg) < d) ++lg;
+    const int pw = 31 + lg;
+    f.mul = (uint32_t)(((1ull << pw) + (unsigned long long)d - 1) / (unsigned long long)d);
+    f.shr = (uint32_t)(pw - 32);
+  }
+  return f;
+}
 
 struct GemmKParams {
   int M, N, num_kb, block_n, stages;
@@ -77,11 +105,50 @@ struct GemmKParams {
   const float* b2;
   int c2, exp_out;
   long long rows_per_group;  // STORE_HYPER: w2 is indexed by row / rows_per_group
+  FastDiv fd_cW, fd_cH, fd_cT, fd_rpg;  // HYPER finalisation: row -> (g,t,h,w), row -> hyper group
+  FastDiv fd_bW, fd_bH;                 // HEAD1X1 finalisation: row in tile -> (tl,hl,wl)
   long long* prof;           // optional [3][512] clock64 timeline of CTA 0
 };
 
 #define GEMM_STAMP(role, idx) \
   do { if (p.prof != nullptr && blockIdx.x == 0 && (idx) < 512) p.prof[(role) * 512 + (idx)] = clock64(); } while (0)
+// fine-grained epilogue stamps of thread 0 (slots 64.. of role 2); compiled in only for tuning builds
+#ifndef L4P_GEMM_FINE_PROF
+#define L4P_GEMM_FINE_PROF 0
+#endif
+#if L4P_GEMM_FINE_PROF
+// stamps are collected in shared memory (a global read-modify-write per stamp would cost ~1000 cycles and distort the
+// timeline) and flushed by FINE_FLUSH() at kernel end: role 2 slots 64.. (epilogue thread 0), role 0 slots 300.. (helper)
+__shared__ long long g_fine[2][200];
+__shared__ int g_fine_n[2];
+#define FINE_INIT() do { if (threadIdx.x == 0) { g_fine_n[0] = 0; g_fine_n[1] = 0; } } while (0)
+#define EPI_STAMP()                                                                       \
+  do {                                                                                    \
+    if (threadIdx.x == 0 && blockIdx.x == 0 && p.prof != nullptr) {                       \
+      const int n_ = g_fine_n[0];                                                         \
+      if (n_ < 200) { g_fine[0][n_] = clock64(); g_fine_n[0] = n_ + 1; }                  \
+    }                                                                                     \
+  } while (0)
+#define HELPER_STAMP()                                                                    \
+  do {                                                                                    \
+    if (lane == 0 && blockIdx.x == 0 && p.prof != nullptr) {                              \
+      const int n_ = g_fine_n[1];                                                         \
+      if (n_ < 200) { g_fine[1][n_] = clock64(); g_fine_n[1] = n_ + 1; }                  \
+    }                                                                                     \
+  } while (0)
+#define FINE_FLUSH()                                                                      \
+  do {                                                                                    \
+    if (threadIdx.x == 0 && blockIdx.x == 0 && p.prof != nullptr) {                       \
+      for (int i_ = 0; i_ < g_fine_n[0]; ++i_) p.prof[2 * 512 + 64 + i_] = g_fine[0][i_]; \
+      for (int i_ = 0; i_ < g_fine_n[1]; ++i_) p.prof[0 * 512 + 300 + i_] = g_fine[1][i_]; \
+    }                                                                                     \
+  } while (0)
+#else
+#define EPI_STAMP() do { } while (0)
+#define HELPER_STAMP() do { } while (0)
+#define FINE_INIT() do { } while (0)
+#define FINE_FLUSH() do { } while (0)
+#endif
 
 struct TileCoord {
   int m_blk, n_blk;
@@ -136,6 +203,187 @@ L4P_DEVICE void apply_act2_rt(float& a, float& b, int act) {
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// Fused-dot modes (HEAD1X1 / HYPER): shared state between the epilogue warps and the HELPER warp (4th pipeline warp).
+// A single epilogue warp pays a full L1/L2 round trip for every global access it makes, so everything that touches
+// global memory is moved off the critical warps:
+//   helper: stage(i)     bias + second-stage weights of tile i -> opnd[i & 1]      (sfull / sempty, one tile ahead)
+//           finalize(i)  sum the per-warpgroup partial dot products of tile i, index math, global stores (pfull / pfree)
+//   epilogue warp: TMEM -> +bias -> activation -> dot with the staged weights (all from shared memory) -> partials
+// ------------------------------------------------------------------------------------------------------------------
+struct DotShared {
+  uint64_t sfull[2], sempty[2], pfull, pfree;
+  float opnd[2][1024];                     // [1 + c2][block_n] floats per buffer: row 0 = bias, rows 1.. = weights
+  float part[kMaxEpiGroups][8][128];       // partial dot products [warpgroup][channel][row] (conflict-free both ways)
+};
+struct DotSharedNone { int unused; };
+
+struct RowInfo {
+  long long row;  // logical output row
+  bool ok;
+  int cb, ct, ch, cw;
+};
+L4P_DEVICE RowInfo row_info(const GemmKParams& p, const TileCoord& tc, const int r) {
+  RowInfo ri;
+  ri.cb = ri.ct = ri.ch = ri.cw = 0;
+  if (p.a_mode == L4P_A_CONV3D) {
+    const int wl = r % p.bW;
+    const int hl = (r / p.bW) % p.bH;
+    const int tl = r / (p.bW * p.bH);
+    ri.ct = tc.t0 + tl; ri.ch = tc.h0 + hl; ri.cw = tc.w0 + wl; ri.cb = tc.b;
+    ri.ok = (ri.ct < p.cT) && (ri.ch < p.cH) && (ri.cw < p.cW) && (ri.cb < p.cB);
+    ri.row = (((long long)ri.cb * p.cT + ri.ct) * p.cH + ri.ch) * p.cW + ri.cw;
+  } else {
+    ri.row = (long long)tc.m_blk * kBlockM + r;
+    ri.ok = ri.row < p.M;
+  }
+  return ri;
+}
+
+// helper warp: bias and second-stage weights of one tile -> opnd buffer (all loads in flight at once)
+template <int STORE>
+L4P_DEVICE void dot_stage(const GemmKParams& p, const TileCoord& tc, float* opnd, const int lane) {
+  const int c2 = p.c2, bn = p.block_n;
+  const int n0 = tc.n_blk * bn;
+  const float* wsrc;   // row c of the second-stage weights of this tile starts at wsrc + c * wld
+  int wld;
+  if constexpr (STORE == L4P_STORE_HYPER) {
+    const unsigned grp = p.fd_rpg.div((unsigned)(tc.m_blk * kBlockM));
+    wsrc = p.w2 + (long long)grp * (c2 * p.ctCout);
+    wld = p.ctCout;
+  } else {
+    wsrc = p.w2 + n0;
+    wld = p.N;
+  }
+  const int nb4 = bn >> 2;  // float4 per row (<= 64: two per lane)
+  // rows 0..4 first (bias + up to 4 weight rows: everything the mask decoder needs), then rows 5..8 if present;
+  // every pass has all its loads in flight before the first store
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    if (pass == 1 && c2 <= 4) break;
+    float4 sv[5][2];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      const int rw = pass * 5 + j;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c4 = lane + 32 * h;
+        sv[j][h] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (rw <= c2 && rw < 9 && c4 < nb4 && n0 + 4 * c4 < p.N) {
+          if (rw == 0) { if (p.bias != nullptr) sv[j][h] = *reinterpret_cast<const float4*>(p.bias + n0 + 4 * c4); }
+          else sv[j][h] = *reinterpret_cast<const float4*>(wsrc + (long long)(rw - 1) * wld + 4 * c4);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      const int rw = pass * 5 + j;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c4 = lane + 32 * h;
+        if (rw <= c2 && rw < 9 && c4 < nb4) reinterpret_cast<float4*>(opnd + rw * bn)[c4] = sv[j][h];
+      }
+    }
+  }
+}
+
+// helper warp: reduce the warpgroups' partials of one tile and store the results (4 rows per lane). A lone warp runs
+// dependent integer code at ~6 cycles per instruction, so everything tile-uniform is hoisted and the per-row index
+// math uses the host-prepared multiply-shift divisions.
+template <int STORE, int GROUPS>
+L4P_DEVICE void dot_finalize(const GemmKParams& p, const TileCoord& tc, const DotShared& ds, const uint32_t pfree_bar,
+                             const int lane) {
+  const int c2 = p.c2;
+  float acc[4][8];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int r = lane + 32 * k;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      float a = 0.f;
+      if (c < c2) {
+#pragma unroll
+        for (int g = 0; g < GROUPS; ++g) a += ds.part[g][c][r];
+      }
+      acc[k][c] = a;
+    }
+  }
+  mbar_arrive(pfree_bar);  // the partials are in registers: the epilogue warps may overwrite them
+  if constexpr (STORE == L4P_STORE_HYPER) {
+    // rows are input voxels (g,t,h,w) of the [cB,cT,cH,cW] grid (matrix mode); this N tile = tap (kt,kh,kw)
+    const int tapi = tc.n_blk;
+    const int kw = tapi % p.sW, kh = (tapi / p.sW) % p.sH, kt = tapi / (p.sW * p.sH);
+    const int oH = p.cH * p.sH, oW = p.cW * p.sW;
+    const long long plane = (long long)(p.cT * p.sT) * oH * oW;
+    const int tapoff = (kt * oH + kh) * oW + kw;
+    const uint32_t row0 = (uint32_t)tc.m_blk * kBlockM;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t row = row0 + (uint32_t)(lane + 32 * k);
+      if (row >= (uint32_t)p.M) continue;
+      uint32_t q_, w_, h_, t_;
+      p.fd_cW.divmod(row, q_, w_);
+      p.fd_cH.divmod(q_, q_, h_);
+      p.fd_cT.divmod(q_, q_, t_);
+      float* dst = p.out_f32 + ((long long)q_ * c2 * plane + (long long)((int)(t_ * p.sT * oH + h_ * p.sH) * oW + (int)(w_ * p.sW) + tapoff));
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (c < c2) dst[c * plane] = acc[k][c];
+    }
+  } else {
+    // conv mode: the tile is a (bT,bH,bW) voxel box
+    const long long plane = (long long)p.cT * p.cH * p.cW;
+    float b2v[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) b2v[c] = c < c2 ? p.b2[c] : 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      uint32_t q_, wl, hl, tl;
+      p.fd_bW.divmod((uint32_t)(lane + 32 * k), q_, wl);
+      p.fd_bH.divmod(q_, tl, hl);
+      const int ct = tc.t0 + (int)tl, ch = tc.h0 + (int)hl, cw = tc.w0 + (int)wl;
+      if (!(ct < p.cT && ch < p.cH && cw < p.cW && tc.b < p.cB)) continue;
+      float* dst = p.out_f32 + ((long long)tc.b * c2 * plane + (long long)((ct * p.cH + ch) * p.cW + cw));
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        if (c < c2) {
+          float o = acc[k][c] + b2v[c];
+          if (p.exp_out) o = expf(o);
+          dst[c * plane] = o;
+        }
+      }
+    }
+  }
+}
+
+// helper warp main loop. `next(tc)` yields this CTA's tiles in epilogue order and returns false when exhausted.
+template <int EPI, class NextTile>
+L4P_DEVICE void dot_helper_loop(const GemmKParams& p, DotShared& ds, const int lane, NextTile next) {
+  constexpr int STORE = epi_store(EPI);
+  TileCoord tc, prev;
+  bool have = next(tc);
+  for (int i = 0;; ++i) {
+    if (have) {
+      const int b = i & 1;
+      HELPER_STAMP();
+      mbar_wait(smem_u32(&ds.sempty[b]), (((uint32_t)i >> 1) & 1u) ^ 1u);
+      HELPER_STAMP();
+      dot_stage<STORE>(p, tc, ds.opnd[b], lane);
+      mbar_arrive(smem_u32(&ds.sfull[b]));
+      HELPER_STAMP();
+    }
+    if (i >= 1) {
+      mbar_wait(smem_u32(&ds.pfull), (uint32_t)(i - 1) & 1u);
+      HELPER_STAMP();
+      dot_finalize<STORE, epi_groups(EPI)>(p, prev, ds, smem_u32(&ds.pfree), lane);
+      HELPER_STAMP();
+    }
+    if (!have) break;
+    prev = tc;
+    have = next(tc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // Epilogue. One 128-row x block_n accumulator tile: TMEM -> registers -> bias / activation / residual -> global memory.
 // Shared by the 1-CTA and the 2-CTA (cta_group::2) kernels; `release` hands the accumulator stage back to the MMA warp.
 //
@@ -151,30 +399,20 @@ L4P_DEVICE void apply_act2_rt(float& a, float& b, int act) {
 // ------------------------------------------------------------------------------------------------------------------
 template <bool BF16, int EPI, class Release>
 L4P_DEVICE void epilogue_tile(const GemmKParams& p, const TileCoord& tc, const int q4, const int lane, const int egrp,
-                              const uint32_t tfull_bar, const uint32_t tfull_phase, const uint32_t t_acc, float* s_head,
-                              const uint32_t stage, Release release) {
+                              const uint32_t tfull_bar, const uint32_t tfull_phase, const uint32_t t_acc, void* dot_shared,
+                              const int tile_ord, const uint32_t stage, Release release) {
   constexpr int STORE = epi_store(EPI);
   constexpr bool GEN = (EPI & EPI_GENERIC) != 0;
+  constexpr int kEpiGroups = epi_groups(EPI);
   const int r = q4 * 32 + lane;  // row inside the tile
-  long long row;                 // logical output row
-  bool row_ok;
-  int cb_ = 0, ct_ = 0, ch_ = 0, cw_ = 0;
-  if (p.a_mode == L4P_A_CONV3D) {
-    const int wl = r % p.bW;
-    const int hl = (r / p.bW) % p.bH;
-    const int tl = r / (p.bW * p.bH);
-    ct_ = tc.t0 + tl; ch_ = tc.h0 + hl; cw_ = tc.w0 + wl; cb_ = tc.b;
-    row_ok = (ct_ < p.cT) && (ch_ < p.cH) && (cw_ < p.cW) && (cb_ < p.cB);
-    row = (((long long)cb_ * p.cT + ct_) * p.cH + ch_) * p.cW + cw_;
-  } else {
-    row = (long long)tc.m_blk * kBlockM + r;
-    row_ok = row < p.M;
-  }
   const int n0 = tc.n_blk * p.block_n;
   const uint32_t t_addr = t_acc + ((uint32_t)(q4 * 32) << 16);
 
   if constexpr (STORE == L4P_STORE_ROWMAJOR || STORE == L4P_STORE_QKV || STORE == L4P_STORE_CONVT) {
     // ---------------------------------------------------------------- transposed (coalesced) store modes
+    const RowInfo ri = row_info(p, tc, r);
+    const long long row = ri.row;
+    const bool row_ok = ri.ok;
     const bool res32 = GEN ? (p.res_f32 != nullptr) : ((EPI & EPI_RES32) != 0);
     const bool res16 = GEN ? (p.res_16 != nullptr || p.res2_16 != nullptr) : ((EPI & EPI_RES16) != 0);
     const bool out32 = GEN ? (p.out_f32 != nullptr) : ((EPI & EPI_OUT32) != 0);
@@ -369,130 +607,90 @@ L4P_DEVICE void epilogue_tile(const GemmKParams& p, const TileCoord& tc, const i
     return;
   } else {
     // ------------------------------------------------------------------ fused-dot modes (row per thread)
+    // bias and second-stage weights come from the helper warp's shared-memory staging (see DotShared): no global
+    // access on this warp's critical path
+    DotShared& ds = *reinterpret_cast<DotShared*>(dot_shared);
+    const int c2 = p.c2;
+    const int act_rt = p.act;
+    const int bn = p.block_n;
+    const int b = tile_ord & 1;
+    const uint32_t opnd = smem_u32(ds.opnd[b]);
+    mbar_wait(smem_u32(&ds.sfull[b]), ((uint32_t)tile_ord >> 1) & 1u);
+    EPI_STAMP();
+
     mbar_wait(tfull_bar, tfull_phase);
     tc_fence_after();
+    EPI_STAMP();
 
     float head_acc[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) head_acc[c] = 0.f;
-    const int c2 = p.c2;
-    const int act_rt = p.act;
 
-    const float* hyper_w = STORE == L4P_STORE_HYPER ? p.w2 + (row / p.rows_per_group) * (long long)(c2 * p.ctCout) : nullptr;
-    for (int c0 = egrp * 16; c0 < p.block_n; c0 += 16 * kEpiGroups) {
+    for (int c0 = egrp * 16; c0 < bn; c0 += 16 * kEpiGroups) {
       uint32_t raw[16];
       __syncwarp();  // tcgen05.ld is warp-collective
       tmem_ld16(t_addr + (uint32_t)c0, raw);
       tmem_ld_wait();
-      const int col0 = n0 + c0;
-      if (col0 >= p.N) continue;  // uniform across the CTA
+      EPI_STAMP();
+      if (n0 + c0 >= p.N) continue;  // uniform across the CTA
       float v[16];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(raw[i]);
-      if (p.bias != nullptr) {
-#pragma unroll
-        for (int i = 0; i < 16; i += 4) {
-          const float4 bv = *reinterpret_cast<const float4*>(p.bias + col0 + i);
-          v[i] += bv.x; v[i + 1] += bv.y; v[i + 2] += bv.z; v[i + 3] += bv.w;
-        }
+      for (int i = 0; i < 16; i += 4) {
+        const float4 bv = lds128(opnd + (uint32_t)(c0 + i) * 4u);
+        v[i] = __uint_as_float(raw[i]) + bv.x; v[i + 1] = __uint_as_float(raw[i + 1]) + bv.y;
+        v[i + 2] = __uint_as_float(raw[i + 2]) + bv.z; v[i + 3] = __uint_as_float(raw[i + 3]) + bv.w;
       }
 #pragma unroll
       for (int i = 0; i < 16; i += 2) {
         if constexpr (GEN) apply_act2_rt(v[i], v[i + 1], act_rt);
         else apply_act2<epi_act(EPI)>(v[i], v[i + 1]);
       }
-      if constexpr (STORE == L4P_STORE_HYPER) {
-        // v = act(acc + bias) of one ConvT tap (this N tile); dot with the per-query hyper-network vectors
-        const float* wg = hyper_w + c0;
+      // HYPER: dot with the per-query hyper-network vectors; HEAD1X1: the tiny second conv
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          if (c < c2) {
-            float a = head_acc[c];
+      for (int c = 0; c < (STORE == L4P_STORE_HYPER ? 4 : 8); ++c) {
+        if (c < c2) {
+          float a[4];  // four independent chains instead of one 16-deep dependent FMA chain
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float4 wv = *reinterpret_cast<const float4*>(wg + c * p.ctCout + 4 * i);
-              a = fmaf(v[4 * i], wv.x, a); a = fmaf(v[4 * i + 1], wv.y, a);
-              a = fmaf(v[4 * i + 2], wv.z, a); a = fmaf(v[4 * i + 3], wv.w, a);
-            }
-            head_acc[c] = a;
+          for (int i = 0; i < 4; ++i) {
+            const float4 wv = lds128(opnd + (uint32_t)((1 + c) * bn + c0 + 4 * i) * 4u);
+            a[i] = fmaf(v[4 * i + 3], wv.w, fmaf(v[4 * i + 2], wv.z, fmaf(v[4 * i + 1], wv.y, v[4 * i] * wv.x)));
           }
-        }
-      } else {  // L4P_STORE_HEAD1X1: v already bias+ReLU'd; accumulate the tiny second conv
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          if (c < c2) {
-            const float* wr = p.w2 + (long long)c * p.N + col0;
-            float a = head_acc[c];
-#pragma unroll
-            for (int i = 0; i < 16; i += 4) {
-              const float4 wv = *reinterpret_cast<const float4*>(wr + i);
-              a = fmaf(v[i], wv.x, a); a = fmaf(v[i + 1], wv.y, a);
-              a = fmaf(v[i + 2], wv.z, a); a = fmaf(v[i + 3], wv.w, a);
-            }
-            head_acc[c] = a;
-          }
+          head_acc[c] += (a[0] + a[1]) + (a[2] + a[3]);
         }
       }
     }
-    // accumulator stage drained -> hand TMEM back to the MMA warp
+    // accumulator stage drained -> hand TMEM back to the MMA warp; the operand buffer back to the helper
+    EPI_STAMP();
     tc_fence_before();
     release();
+    mbar_arrive(smem_u32(&ds.sempty[b]));
 
-    // the per-row dot products were accumulated per warpgroup over its chunks: reduce them in group 0
-    if (egrp != 0) {
+    // per-warpgroup partial dot products -> helper warp (which has consumed the previous tile's partials)
+    mbar_wait(smem_u32(&ds.pfree), ((uint32_t)tile_ord & 1u) ^ 1u);
 #pragma unroll
-      for (int c = 0; c < 8; ++c) s_head[(egrp - 1) * 128 * 8 + r * 8 + c] = head_acc[c];
-    }
-    named_bar_sync(1, 128 * kEpiGroups);
-    if (egrp == 0) {
-#pragma unroll
-      for (int g2 = 1; g2 < kEpiGroups; ++g2)
-#pragma unroll
-        for (int c = 0; c < 8; ++c) head_acc[c] += s_head[(g2 - 1) * 128 * 8 + r * 8 + c];
-    }
-    named_bar_sync(1, 128 * kEpiGroups);  // s_head may be overwritten by the next tile
-
-    if (STORE == L4P_STORE_HYPER && row_ok && egrp == 0) {
-      // row = input voxel (g,t,h,w) of the [cB,cT,cH,cW] grid; this N tile = tap (kt,kh,kw)
-      long long rr = row;
-      const int w_ = (int)(rr % p.cW); rr /= p.cW;
-      const int h_ = (int)(rr % p.cH); rr /= p.cH;
-      const int t_ = (int)(rr % p.cT); rr /= p.cT;
-      const long long g_ = rr;
-      const int tapi = tc.n_blk;
-      const int kw = tapi % p.sW, kh = (tapi / p.sW) % p.sH, kt = tapi / (p.sW * p.sH);
-      const long long oT = (long long)p.cT * p.sT, oH = (long long)p.cH * p.sH, oW = (long long)p.cW * p.sW;
-      const long long vox = ((long long)(t_ * p.sT + kt) * oH + (h_ * p.sH + kh)) * oW + (w_ * p.sW + kw);
-#pragma unroll
-      for (int c = 0; c < 4; ++c)
-        if (c < c2) p.out_f32[((g_ * c2 + c) * oT * oH * oW) + vox] = head_acc[c];
-    }
-    if (STORE == L4P_STORE_HEAD1X1 && row_ok && egrp == 0) {
-      const long long plane = (long long)p.cT * p.cH * p.cW;
-      const long long vox = ((long long)ct_ * p.cH + ch_) * p.cW + cw_;
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        if (c < c2) {
-          float o = head_acc[c] + p.b2[c];
-          if (p.exp_out) o = expf(o);
-          p.out_f32[((long long)cb_ * c2 + c) * plane + vox] = o;
-        }
-      }
-    }
+    for (int c = 0; c < 8; ++c)
+      if (c < c2) ds.part[egrp][c][r] = head_acc[c];
+    mbar_arrive(smem_u32(&ds.pfull));
+    EPI_STAMP();
   }
 }
 
 template <bool BF16, int EPI>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(gemm_threads(EPI), 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const GemmKParams p) {
+  constexpr int kEpiGroups = epi_groups(EPI);
+  constexpr int kWarpProducer = 4 * kEpiGroups, kWarpMma = kWarpProducer + 1, kWarpAlloc = kWarpProducer + 2;
+  constexpr bool kRepartition = kEpiGroups == 2;  // setmaxnreg: 96 registers for the pipeline warps, 200 for the epilogue
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[kMaxStages];
   __shared__ __align__(8) uint64_t bar_empty[kMaxStages];
   __shared__ __align__(8) uint64_t bar_tfull[2];
   __shared__ __align__(8) uint64_t bar_tempty[2];
   __shared__ uint32_t tmem_base_slot;
-  __shared__ float s_head[(kEpiGroups - 1) * 128 * 8];  // cross-warpgroup reduction of the fused head dot products
+  constexpr bool kFusedDot = epi_store(EPI) == L4P_STORE_HEAD1X1 || epi_store(EPI) == L4P_STORE_HYPER;
+  typedef typename std::conditional<kFusedDot, DotShared, DotSharedNone>::type DotSh;
+  __shared__ __align__(16) DotSh dot_sh;  // fused-dot modes: operand staging + partials shared with the helper warp
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -512,8 +710,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       mbar_init(smem_u32(&bar_tfull[s]), 1);
       mbar_init(smem_u32(&bar_tempty[s]), 128 * kEpiGroups);
     }
+    if constexpr (kFusedDot) {
+      DotShared& ds = reinterpret_cast<DotShared&>(dot_sh);
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(smem_u32(&ds.sfull[s]), 32);
+        mbar_init(smem_u32(&ds.sempty[s]), 128 * kEpiGroups);
+      }
+      mbar_init(smem_u32(&ds.pfull), 128 * kEpiGroups);
+      mbar_init(smem_u32(&ds.pfree), 32);
+    }
     fence_mbar_init();
   }
+  FINE_INIT();
   if (warp == kWarpAlloc) tmem_alloc(smem_u32(&tmem_base_slot), 512);
   tc_fence_before();
   __syncthreads();
@@ -522,7 +730,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   if (warp == kWarpProducer) {
     // ------------------------------------------------------------------ TMA producer
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+    if constexpr (kRepartition) asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
     if (lane == 0) {
       int stage = 0, pg = 0;
       uint32_t phase = 0;
@@ -558,7 +766,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   } else if (warp == kWarpMma) {
     // ------------------------------------------------------------------ UMMA issuer
     // whole warp walks the pipeline (warp-uniform control flow), one elected lane issues
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+    if constexpr (kRepartition) asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
     const bool leader = elect_one();
     const uint32_t idesc = umma_idesc_f16(BF16, kBlockM, (uint32_t)p.block_n);
     constexpr uint32_t hi128 = umma_desc_hi(128, 2);
@@ -595,7 +803,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else if (warp < 4 * kEpiGroups) {
     // ------------------------------------------------------------------ epilogue
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");  // the epilogue holds a 32-column sub-tile + prefetched residuals
+    if constexpr (kRepartition) asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");  // 32-column sub-tile + prefetched residuals
     const int q4 = warp & 3;  // TMEM lane quarter owned by this warp
     const int egrp = warp >> 2;  // epilogue warpgroup: interleaved 16-column chunks
     int acc = 0, eg = 0;
@@ -605,18 +813,30 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const TileCoord tc = decode_tile(p, tile);
       const uint32_t tempty = smem_u32(&bar_tempty[acc]);
       epilogue_tile<BF16, EPI>(p, tc, q4, lane, egrp, smem_u32(&bar_tfull[acc]), acc_phase, tmem_base + (uint32_t)acc * kAccCols,
-                          s_head, smem_base + (uint32_t)p.stages * stage_bytes + (uint32_t)warp * kEpiStageBytes,
+                          &dot_sh, eg, smem_base + (uint32_t)p.stages * stage_bytes + (uint32_t)warp * kEpiStageBytes,
                           [&]() { if (threadIdx.x == 0) GEMM_STAMP(2, 2 * eg); mbar_arrive(tempty); });
       if (threadIdx.x == 0) GEMM_STAMP(2, 2 * eg + 1);
       ++eg;
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
+  } else if (kFusedDot && warp == kWarpAlloc + 1) {
+    // ------------------------------------------------------------------ fused-dot helper (operand staging + finalisation)
+    if constexpr (kFusedDot) {
+      int tile = blockIdx.x;
+      dot_helper_loop<EPI>(p, reinterpret_cast<DotShared&>(dot_sh), lane, [&](TileCoord& tc) {
+        if (tile >= num_tiles) return false;
+        tc = decode_tile(p, tile);
+        tile += gridDim.x;
+        return true;
+      });
+    }
   } else {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+    if constexpr (kRepartition) asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
   }
 
   tc_fence_before();
   __syncthreads();
+  FINE_FLUSH();
   if (warp == kWarpAlloc) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
@@ -633,15 +853,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 //   tfull[a]   one per CTA (multicast commit);   tempty[a] in the leader: all epilogue threads of both CTAs arrive
 // ------------------------------------------------------------------------------------------------------------------
 template <bool BF16, int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemm_threads(EPI), 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmKParams p) {
+  constexpr int kEpiGroups = epi_groups(EPI);
+  constexpr int kWarpProducer = 4 * kEpiGroups, kWarpMma = kWarpProducer + 1, kWarpAlloc = kWarpProducer + 2;
+  constexpr bool kRepartition = kEpiGroups == 2;  // setmaxnreg: 96 registers for the pipeline warps, 200 for the epilogue
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[kMaxStages];
   __shared__ __align__(8) uint64_t bar_empty[kMaxStages];
   __shared__ __align__(8) uint64_t bar_tfull[2];
   __shared__ __align__(8) uint64_t bar_tempty[2];
   __shared__ uint32_t tmem_base_slot;
-  __shared__ float s_head[(kEpiGroups - 1) * 128 * 8];
+  constexpr bool kFusedDot = epi_store(EPI) == L4P_STORE_HEAD1X1 || epi_store(EPI) == L4P_STORE_HYPER;
+  typedef typename std::conditional<kFusedDot, DotShared, DotSharedNone>::type DotSh;
+  __shared__ __align__(16) DotSh dot_sh;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -666,8 +891,18 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       mbar_init(smem_u32(&bar_tfull[s]), 1);
       mbar_init(smem_u32(&bar_tempty[s]), 2 * 128 * kEpiGroups);
     }
+    if constexpr (kFusedDot) {
+      DotShared& ds = reinterpret_cast<DotShared&>(dot_sh);
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(smem_u32(&ds.sfull[s]), 32);
+        mbar_init(smem_u32(&ds.sempty[s]), 128 * kEpiGroups);
+      }
+      mbar_init(smem_u32(&ds.pfull), 128 * kEpiGroups);
+      mbar_init(smem_u32(&ds.pfree), 32);
+    }
     fence_mbar_init();
   }
+  FINE_INIT();
   if (warp == kWarpAlloc) tmem_alloc2(smem_u32(&tmem_base_slot), 512);
   tc_fence_before();
   cluster_sync_all();  // barriers of both CTAs are initialised before any remote arrive / multicast / peer TMA signal
@@ -676,7 +911,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 
   if (warp == kWarpProducer) {
     // ------------------------------------------------------------------ TMA producer (both CTAs)
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+    if constexpr (kRepartition) asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
     if (lane == 0) {
       int stage = 0, pg = 0;
       uint32_t phase = 0;
@@ -711,7 +946,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
   } else if (warp == kWarpMma) {
     // ------------------------------------------------------------------ UMMA issuer (leader CTA only)
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+    if constexpr (kRepartition) asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
     if (is_leader) {
       const bool leader_lane = elect_one();
       const uint32_t idesc = umma_idesc_f16(BF16, 2 * kBlockM, (uint32_t)p.block_n);
@@ -748,7 +983,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
   } else if (warp < 4 * kEpiGroups) {
     // ------------------------------------------------------------------ epilogue (both CTAs, own 128 rows)
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");  // the epilogue holds a 32-column sub-tile + prefetched residuals
+    if constexpr (kRepartition) asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");  // 32-column sub-tile + prefetched residuals
     const int q4 = warp & 3;
     const int egrp = warp >> 2;
     int acc = 0, eg = 0;
@@ -758,18 +993,30 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const TileCoord tc = decode_block(p, (tile / p.tiles_n) * 2 + (int)rank, tile % p.tiles_n);
       const uint32_t tempty_leader = mapa_shared(smem_u32(&bar_tempty[acc]), 0);
       epilogue_tile<BF16, EPI>(p, tc, q4, lane, egrp, smem_u32(&bar_tfull[acc]), acc_phase, tmem_base + (uint32_t)acc * kAccCols,
-                          s_head, smem_base + (uint32_t)p.stages * stage_bytes + (uint32_t)warp * kEpiStageBytes,
+                          &dot_sh, eg, smem_base + (uint32_t)p.stages * stage_bytes + (uint32_t)warp * kEpiStageBytes,
                           [&]() { if (threadIdx.x == 0) GEMM_STAMP(2, 2 * eg); mbar_arrive_cluster(tempty_leader); });
       if (threadIdx.x == 0) GEMM_STAMP(2, 2 * eg + 1);
       ++eg;
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
+  } else if (kFusedDot && warp == kWarpAlloc + 1) {
+    // ------------------------------------------------------------------ fused-dot helper (own CTA's 128 rows)
+    if constexpr (kFusedDot) {
+      int tile = pair;
+      dot_helper_loop<EPI>(p, reinterpret_cast<DotShared&>(dot_sh), lane, [&](TileCoord& tc) {
+        if (tile >= num_tiles) return false;
+        tc = decode_block(p, (tile / p.tiles_n) * 2 + (int)rank, tile % p.tiles_n);
+        tile += num_pairs;
+        return true;
+      });
+    }
   } else {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+    if constexpr (kRepartition) asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
   }
 
   tc_fence_before();
   cluster_sync_all();  // nobody exits (or frees TMEM) while the peer may still signal / read this CTA
+  FINE_FLUSH();
   if (warp == kWarpAlloc) {
     tc_fence_after();
     tmem_dealloc2(tmem_base, 512);

@@ -161,7 +161,8 @@ def pick_box(T: int, H: int, W: int) -> Tuple[int, int, int]:
 
 def conv3d(x: torch.Tensor, w: torch.Tensor, *, ksize: Tuple[int, int, int], bias=None, act=_l.ACT_NONE,
            res_16=None, res2_16=None, out_16=None, out_16_relu=None, out_f32=None,
-           head_w2=None, head_b2=None, head_exp=False, block_n: int = 0) -> None:
+           head_w2=None, head_b2=None, head_exp=False, block_n: int = 0, cta_pair: int = 0,
+           prof: Optional[torch.Tensor] = None) -> None:
     """K8: stride-1 'same' Conv3d as implicit GEMM.
 
     x channels-last [B,T,H,W,Cin] (16-bit); w [Cout, kT*kH*kW*Cin] with the K axis ordered (kt,kh,kw,cin).
@@ -179,6 +180,8 @@ def conv3d(x: torch.Tensor, w: torch.Tensor, *, ksize: Tuple[int, int, int], bia
     d.kT, d.kH, d.kW = kT, kH, kW
     d.bT, d.bH, d.bW = pick_box(T, H, W)
     d.block_n = block_n
+    d.cta_pair = cta_pair
+    d.prof = _ptr(prof)
     if head_w2 is not None:
         _chk(head_w2, "head_w2", torch.float32); _chk(head_b2, "head_b2", torch.float32)
         _chk(out_f32, "out_f32", torch.float32); _chk(bias, "bias", torch.float32)
@@ -292,7 +295,8 @@ def im2col3(x: torch.Tensor, out: torch.Tensor, stride: Tuple[int, int, int]) ->
 
 
 def conv_transpose3d_hyper(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, stride: Tuple[int, int, int],
-                           hyper: torch.Tensor, out_f32: torch.Tensor, act=_l.ACT_GELU) -> None:
+                           hyper: torch.Tensor, out_f32: torch.Tensor, act=_l.ACT_GELU,
+                           prof: Optional[torch.Tensor] = None) -> None:
     """K14: last ConvTranspose3d of the mask decoder fused with its activation and the hyper-network dot.
 
     x channels-last [G,T,H,W,Cin]; w [sT*sH*sW*Cout, Cin] rows (kt,kh,kw,co); bias tiled likewise;
@@ -315,6 +319,7 @@ def conv_transpose3d_hyper(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor,
     d.rows_per_group = T * H * W
     d.out_f32 = out_f32.data_ptr()
     d.block_n = Cout
+    d.prof = _ptr(prof)
     _l.check(_l.load().l4p_gemm(C.byref(d), _stream()), "l4p_gemm(hyper)")
     _count()
 

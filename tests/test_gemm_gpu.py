@@ -172,6 +172,27 @@ def test_conv_transpose(dtype, stride):
 
 
 @pytest.mark.parametrize("dtype", DT)
+def test_conv_transpose_hyper(dtype):
+    """Mask-decoder tail (sam/mask_decoder.py:62-66,137-139): ConvT(k==s) -> GELU -> per-query hyper-network dot."""
+    ops = _ops()
+    from l4p_b200 import lib
+    G, T, H, W, Cin, Cout, C2 = 3, 2, 8, 8, 352, 176, 3
+    stride = (1, 2, 2)
+    x = _rand((G, T, H, W, Cin), dtype, 40)
+    wt = _rand((Cin, Cout, *stride), dtype, 41, Cin ** -0.5)
+    b = _rand((Cout,), torch.float32, 42)
+    hyper = _rand((G, C2, Cout), torch.float32, 43, Cout ** -0.5)
+    wk = wt.permute(2, 3, 4, 1, 0).reshape(-1, Cin).contiguous()
+    bk = b.repeat(stride[0] * stride[1] * stride[2]).contiguous()
+    out = torch.empty(G, C2, T * stride[0], H * stride[1], W * stride[2], device="cuda", dtype=torch.float32)
+    ops.conv_transpose3d_hyper(x, wk, bk, stride, hyper, out, act=lib.ACT_GELU)
+    torch.cuda.synchronize()
+    up = F.gelu(F.conv_transpose3d(x.float().permute(0, 4, 1, 2, 3), wt.float(), b, stride=stride))  # [G,Cout,T',H',W']
+    ref = torch.einsum("gcthw,gkc->gkthw", up, hyper)
+    _close(out, ref, 2e-4)
+
+
+@pytest.mark.parametrize("dtype", DT)
 def test_layernorm(dtype):
     ops = _ops()
     x = _rand((2048, 1408), torch.float32, 29, 3.0) + 0.5
