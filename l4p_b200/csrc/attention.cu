@@ -125,6 +125,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
+  pdl_launch_dependents();
+  pdl_wait();  // Q/K/V are the previous kernel's outputs
 
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
@@ -433,7 +435,6 @@ extern "C" int l4p_attention(const void* q, const void* k, const void* vt, void*
     attr_set[bf16 ? 1 : 0][poly] = true;
   }
   const int grid = B * H * (N / (2 * kTileM));
-  kfn<<<grid, kAttThreads, kAttSmem, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
-  L4P_CHECK_CUDA(cudaGetLastError());
+  L4P_CHECK_CUDA(launch_pdl(kfn, dim3(grid), dim3(kAttThreads), (size_t)kAttSmem, (cudaStream_t)stream, tmQ, tmK, tmV, p));
   return L4P_OK;
 }

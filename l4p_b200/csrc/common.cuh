@@ -38,6 +38,15 @@ L4P_DEVICE bool elect_one() {
 }
 
 // ----------------------------------------------------------------------------------------
+// programmatic dependent launch (PDL): a kernel launched with launch_pdl() may start while its stream predecessor is
+// still running; pdl_wait() blocks until the predecessor grid has completed and its memory is visible. Everything
+// before pdl_wait() (barrier init, TMEM allocation, descriptor prefetch) overlaps the predecessor's tail and hides
+// the ~3 us launch latency. pdl_launch_dependents() lets the NEXT kernel's CTAs be scheduled as SMs free up.
+// ----------------------------------------------------------------------------------------
+L4P_DEVICE void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+L4P_DEVICE void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// ----------------------------------------------------------------------------------------
 // mbarrier
 // ----------------------------------------------------------------------------------------
 L4P_DEVICE void mbar_init(uint32_t bar, uint32_t count) {
@@ -421,6 +430,25 @@ int host_check_cuda(cudaError_t e, const char* what); // L4P_OK or L4P_ERR_CUDA
 int host_make_tmap_16b(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                        const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes);
 int host_num_sms();
+bool host_pdl_enabled();  // false when L4P_NO_PDL=1
+
+// Launch with the programmatic-stream-serialization attribute (see pdl_wait above). The kernel MUST call pdl_wait()
+// before its first global-memory access.
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = host_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
 
 #define L4P_CHECK_CUDA(expr)                                  \
   do {                                                        \

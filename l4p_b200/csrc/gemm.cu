@@ -229,15 +229,13 @@ extern "C" int l4p_gemm(const l4p_gemm_desc* d, void* stream_) {
     GemmKernelFn k2 = select_kernel(d, true);
     L4P_REQUIRE(k2 != nullptr, L4P_ERR_ARG, "l4p_gemm: no kernel instance for store_mode=%d", d->store_mode);
     L4P_CHECK_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kRingBudget + 1024 + epi_bytes)));
-    k2<<<2 * g2, threads, smem2, stream>>>(tmA, tmB, p);
-    L4P_CHECK_CUDA(cudaGetLastError());
+    L4P_CHECK_CUDA(launch_pdl(k2, dim3(2 * g2), dim3(threads), smem2, stream, tmA, tmB, p));
     return L4P_OK;
   }
 
   GemmKernelFn kfn = select_kernel(d, false);
   L4P_REQUIRE(kfn != nullptr, L4P_ERR_ARG, "l4p_gemm: no kernel instance for store_mode=%d", d->store_mode);
   L4P_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kRingBudget + 1024 + epi_bytes)));
-  kfn<<<grid, threads, smem, stream>>>(tmA, tmB, p);
-  L4P_CHECK_CUDA(cudaGetLastError());
+  L4P_CHECK_CUDA(launch_pdl(kfn, dim3(grid), dim3(threads), smem, stream, tmA, tmB, p));
   return L4P_OK;
 }

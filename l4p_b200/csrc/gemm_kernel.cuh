@@ -727,6 +727,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
+  pdl_launch_dependents();  // single-wave persistent grid: the next kernel's CTAs may queue up behind ours right away
+  pdl_wait();               // everything above overlapped the previous kernel's tail; from here on we touch its outputs
 
   if (warp == kWarpProducer) {
     // ------------------------------------------------------------------ TMA producer
@@ -908,6 +910,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   cluster_sync_all();  // barriers of both CTAs are initialised before any remote arrive / multicast / peer TMA signal
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp == kWarpProducer) {
     // ------------------------------------------------------------------ TMA producer (both CTAs)

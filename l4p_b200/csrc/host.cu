@@ -4,6 +4,8 @@
 #include <cstring>
 #include <mutex>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "../../include/l4p_b200.h"
 
@@ -85,6 +87,15 @@ int host_num_sms() {
     if (g_num_sms <= 0) g_num_sms = 148;
   }
   return g_num_sms;
+}
+
+bool host_pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("L4P_NO_PDL");
+    on = (e != nullptr && e[0] == '1') ? 0 : 1;
+  }
+  return on != 0;
 }
 
 }  // namespace l4p

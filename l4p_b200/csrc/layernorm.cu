@@ -14,6 +14,8 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
                  uint16_t* __restrict__ y16, float* __restrict__ y32, long long rows, int cols, float eps) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+  pdl_launch_dependents();
+  pdl_wait();
   if (row >= rows) return;
   const int nvec = cols >> 2;  // float4 per row
   const float4* xr = reinterpret_cast<const float4*>(x + row * cols);
@@ -68,6 +70,16 @@ extern "C" int l4p_layernorm(const float* x, const float* gamma, const float* be
   if (rows == 0) return L4P_OK;
   const int wpb = 8;
   const unsigned grid = (unsigned)((rows + wpb - 1) / wpb);
+  // small row counts (the encoder: 2048 rows = one wave) are launch-latency-bound: PDL; large ones launch normally so
+  // that an early-scheduled successor cannot take SM slots from this kernel's later waves
+  const long long llrows = rows;
+  if (grid <= 2048u) {
+    if (bf16)
+      L4P_CHECK_CUDA(launch_pdl(layernorm_kernel<true>, dim3(grid), dim3(wpb * 32), 0, (cudaStream_t)stream, x, gamma, beta, (uint16_t*)y16, y32, llrows, cols, eps));
+    else
+      L4P_CHECK_CUDA(launch_pdl(layernorm_kernel<false>, dim3(grid), dim3(wpb * 32), 0, (cudaStream_t)stream, x, gamma, beta, (uint16_t*)y16, y32, llrows, cols, eps));
+    return L4P_OK;
+  }
   if (bf16)
     layernorm_kernel<true><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>(x, gamma, beta, (uint16_t*)y16, y32, rows, cols, eps);
   else
