@@ -254,13 +254,15 @@ token_attention_fast_kernel(const float* __restrict__ q, const uint16_t* __restr
 }
 
 // ------------------------------------------------------------------------------------------------
-// q16 [G*Np, H*d] ; k,v fp32 [G, nk, H*d] ; out16 [G*Np, H*d]. One thread per (row, head); block = rows_per_block x H.
+// q16 [G*Np, H*d] ; k,v fp32 [G, nk, H*d] ; out16 [G*Np, H*d]. One thread per (row, head): warp = head, lane = row, so
+// that every shared-memory read of k / v is a warp-wide broadcast (one wavefront) and the 2 * nk * d FMAs per thread
+// run two-wide on the packed f32x2 pipe. blockDim = 32 * H.
 // ------------------------------------------------------------------------------------------------
 template <bool BF16, int D>
 __global__ void __launch_bounds__(256)
 image_attention_kernel(const uint16_t* __restrict__ q16, const float* __restrict__ kf, const float* __restrict__ vf,
                        uint16_t* __restrict__ out16, int Np, int nk, int H, float scale, int rows_per_block) {
-  extern __shared__ float sm[];  // k [nk][H*D], v [nk][H*D]
+  extern __shared__ float sm[];  // k [nk][H*D] (pre-scaled), v [nk][H*D]
   const int ld = H * D;
   const long long row0 = (long long)blockIdx.x * rows_per_block;
   const int g = (int)(row0 / Np);
@@ -271,13 +273,12 @@ image_attention_kernel(const uint16_t* __restrict__ q16, const float* __restrict
     s_v[i] = vf[(long long)g * nk * ld + i];
   }
   __syncthreads();
-  const int h = threadIdx.x % H;
-  const int rsub = threadIdx.x / H;
-  const int rstep = blockDim.x / H;
-  for (int rr = rsub; rr < rows_per_block; rr += rstep) {
+  const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int NP = D / 2;  // channel pairs
+  for (int rr = lane; rr < rows_per_block; rr += 32) {
     const long long row = row0 + rr;
     const uint4* qr = reinterpret_cast<const uint4*>(q16 + row * ld + h * D);
-    float qv[D];
+    uint64_t qv[NP];
 #pragma unroll
     for (int c8 = 0; c8 < D / 8; ++c8) {
       const uint4 raw = qr[c8];
@@ -285,7 +286,7 @@ image_attention_kernel(const uint16_t* __restrict__ q16, const float* __restrict
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const float2 f = unpack2<BF16>(w[i]);
-        qv[c8 * 8 + 2 * i] = f.x; qv[c8 * 8 + 2 * i + 1] = f.y;
+        qv[c8 * 4 + i] = pk2(f.x, f.y);
       }
     }
     float sc[kTokMaxQ];
@@ -294,12 +295,18 @@ image_attention_kernel(const uint16_t* __restrict__ q16, const float* __restrict
     for (int j = 0; j < kTokMaxQ; ++j) {
       sc[j] = -INFINITY;
       if (j < nk) {
-        const float* kk = s_k + j * ld + h * D;
-        float a = 0.f;
+        const float4* kk = reinterpret_cast<const float4*>(s_k + j * ld + h * D);
+        uint64_t a0 = pk2(0.f, 0.f), a1 = pk2(0.f, 0.f);
 #pragma unroll
-        for (int c = 0; c < D; ++c) a = fmaf(qv[c], kk[c], a);
-        sc[j] = a;
-        mx = fmaxf(mx, a);
+        for (int c = 0; c < NP / 2; ++c) {
+          const float4 k4 = kk[c];
+          a0 = fma2(qv[2 * c], pk2(k4.x, k4.y), a0);
+          a1 = fma2(qv[2 * c + 1], pk2(k4.z, k4.w), a1);
+        }
+        float e0, e1;
+        upk2(add2(a0, a1), e0, e1);
+        sc[j] = e0 + e1;
+        mx = fmaxf(mx, sc[j]);
       }
     }
     float sum = 0.f;
@@ -310,21 +317,29 @@ image_attention_kernel(const uint16_t* __restrict__ q16, const float* __restrict
     }
     const float inv = 1.f / sum;
 #pragma unroll
-    for (int c = 0; c < D; ++c) qv[c] = 0.f;
+    for (int c = 0; c < NP; ++c) qv[c] = pk2(0.f, 0.f);
 #pragma unroll
     for (int j = 0; j < kTokMaxQ; ++j) {
       if (j < nk) {
-        const float p = sc[j] * inv;
-        const float* vv = s_v + j * ld + h * D;
+        const float pj = sc[j] * inv;
+        const uint64_t p2 = pk2(pj, pj);
+        const float4* vv = reinterpret_cast<const float4*>(s_v + j * ld + h * D);
 #pragma unroll
-        for (int c = 0; c < D; ++c) qv[c] = fmaf(p, vv[c], qv[c]);
+        for (int c = 0; c < NP / 2; ++c) {
+          const float4 v4 = vv[c];
+          qv[2 * c] = fma2(p2, pk2(v4.x, v4.y), qv[2 * c]);
+          qv[2 * c + 1] = fma2(p2, pk2(v4.z, v4.w), qv[2 * c + 1]);
+        }
       }
     }
     uint4* orow = reinterpret_cast<uint4*>(out16 + row * ld + h * D);
 #pragma unroll
-    for (int c8 = 0; c8 < D / 8; ++c8)
-      orow[c8] = make_uint4(pack2<BF16>(qv[c8 * 8], qv[c8 * 8 + 1]), pack2<BF16>(qv[c8 * 8 + 2], qv[c8 * 8 + 3]),
-                            pack2<BF16>(qv[c8 * 8 + 4], qv[c8 * 8 + 5]), pack2<BF16>(qv[c8 * 8 + 6], qv[c8 * 8 + 7]));
+    for (int c8 = 0; c8 < D / 8; ++c8) {
+      float f[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) upk2(qv[c8 * 4 + i], f[2 * i], f[2 * i + 1]);
+      orow[c8] = make_uint4(pack2<BF16>(f[0], f[1]), pack2<BF16>(f[2], f[3]), pack2<BF16>(f[4], f[5]), pack2<BF16>(f[6], f[7]));
+    }
   }
 }
 
@@ -385,9 +400,10 @@ layernorm16_kernel(const uint16_t* __restrict__ x, const float* __restrict__ gam
       const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
       float o[8];
 #pragma unroll
-      for (int t = 0; t < 8; ++t) {
-        o[t] = (v[i][t] - mean) * rstd * gg[t] + bb[t];
-        if (gelu) o[t] = gelu_erf_fast(o[t]);
+      for (int t = 0; t < 8; ++t) o[t] = (v[i][t] - mean) * rstd * gg[t] + bb[t];
+      if (gelu) {
+#pragma unroll
+        for (int t = 0; t < 8; t += 2) gelu2(o[t], o[t + 1]);
       }
       reinterpret_cast<uint4*>(y + row * cols)[j] = make_uint4(pack2<BF16>(o[0], o[1]), pack2<BF16>(o[2], o[3]),
                                                                pack2<BF16>(o[4], o[5]), pack2<BF16>(o[6], o[7]));
@@ -399,77 +415,115 @@ layernorm16_kernel(const uint16_t* __restrict__ x, const float* __restrict__ gam
 // masks fp32 [G, 3, T, h, w] (low-res logits) -> traj [G,2,T], vis [G,1,T], depth [G,1,T]. One block per (g,t).
 // Spatial bilinear upsample to (H,W) with align_corners=False; T is not resampled (T_in == T_out).
 // ------------------------------------------------------------------------------------------------
-L4P_DEVICE float bilerp(const float* s, int h, int w, int y, int x, int H, int W) {
-  float sy = ((float)y + 0.5f) * ((float)h / (float)H) - 0.5f;
-  float sx = ((float)x + 0.5f) * ((float)w / (float)W) - 0.5f;
-  sy = sy < 0.f ? 0.f : sy;
-  sx = sx < 0.f ? 0.f : sx;
-  const int y0 = (int)sy, x0 = (int)sx;
-  const int y1 = y0 + 1 < h ? y0 + 1 : h - 1, x1 = x0 + 1 < w ? x0 + 1 : w - 1;
-  const float wy = sy - (float)y0, wx = sx - (float)x0;
-  const float a = s[y0 * w + x0], b = s[y0 * w + x1], c = s[y1 * w + x0], d = s[y1 * w + x1];
-  return (1.f - wy) * ((1.f - wx) * a + wx * b) + wy * ((1.f - wx) * c + wx * d);
+// align_corners=False source coordinate of output index o: (i0, i1, fraction)
+L4P_DEVICE void src_coord(int o, int n_in, int n_out, int& i0, int& i1, float& f) {
+  float sc = ((float)o + 0.5f) * ((float)n_in / (float)n_out) - 0.5f;
+  sc = sc < 0.f ? 0.f : sc;
+  i0 = (int)sc;
+  i1 = i0 + 1 < n_in ? i0 + 1 : n_in - 1;
+  f = sc - (float)i0;
 }
 
+// One block per (g,t). The upsampled logits are never formed for the two MEAN channels (visibility, depth): the mean
+// of a bilinear upsample is a separable weighted sum of the h x w source (weights = how much every source row /
+// column contributes to all output rows / columns). The soft-argmax channel evaluates the H x W upsample row by row
+// (row interpolation hoisted, per-column (x0, x1, fx) from a shared table) with ONE exp per pixel: the source maximum
+// bounds every interpolated value, so it is a valid softmax stabiliser and no online rescaling is needed.
 __global__ void __launch_bounds__(256)
 track_readout_kernel(const float* __restrict__ masks, float* __restrict__ traj, float* __restrict__ vis,
                      float* __restrict__ depth, int T, int h, int w, int H, int W, int has_vis, int has_depth,
                      int nch) {
-  extern __shared__ float sm[];  // [h*w]
-  __shared__ float red[4 * 32];
+  extern __shared__ float sm[];  // src [h*w] | wy [h] | wx [w] | fx [W] | x0x1 [W] (int)
+  __shared__ float red[4 * 8];
+  float* s_src = sm;
+  float* s_wy = s_src + h * w;
+  float* s_wx = s_wy + h;
+  float* s_fx = s_wx + w;
+  int* s_x01 = reinterpret_cast<int*>(s_fx + W);
   const int g = blockIdx.x / T, t = blockIdx.x % T;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  const int npix = H * W;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+
+  for (int i = tid; i < h + w; i += blockDim.x) s_wy[i] = 0.f;  // wy and wx are contiguous
+  __syncthreads();
+  for (int y = tid; y < H; y += blockDim.x) {
+    int y0, y1; float fy;
+    src_coord(y, h, H, y0, y1, fy);
+    atomicAdd(&s_wy[y0], 1.f - fy);
+    atomicAdd(&s_wy[y1], fy);
+  }
+  for (int x = tid; x < W; x += blockDim.x) {
+    int x0, x1; float fx;
+    src_coord(x, w, W, x0, x1, fx);
+    atomicAdd(&s_wx[x0], 1.f - fx);
+    atomicAdd(&s_wx[x1], fx);
+    s_fx[x] = fx;
+    s_x01[x] = x0 | (x1 << 16);
+  }
+
   for (int ch = 0; ch < nch; ++ch) {
     const float* src = masks + (((long long)g * nch + ch) * T + t) * (long long)(h * w);
-    __syncthreads();
-    for (int i = threadIdx.x; i < h * w; i += blockDim.x) sm[i] = src[i];
+    __syncthreads();  // previous channel done with s_src (and, first time, the weight tables are complete)
+    float lmax = -INFINITY;
+    for (int i = tid; i < h * w; i += blockDim.x) {
+      const float v = src[i];
+      s_src[i] = v;
+      lmax = fmaxf(lmax, v);
+    }
+    if (ch == 0) {
+      lmax = warp_max(lmax);
+      if (lane == 0) red[warp] = lmax;
+    }
     __syncthreads();
     if (ch == 0) {
-      // online soft-argmax: per-thread (m, s, sx, sy), merged across the block
-      float m = -INFINITY, s = 0.f, sx = 0.f, sy = 0.f;
-      for (int p = threadIdx.x; p < npix; p += blockDim.x) {
-        const int y = p / W, x = p - y * W;
-        const float v = bilerp(sm, h, w, y, x, H, W);
-        if (v > m) {
-          const float r = __expf(m - v);
-          s *= r; sx *= r; sy *= r;
-          m = v;
+      float m = red[0];
+      for (int i = 1; i < nwarps; ++i) m = fmaxf(m, red[i]);
+      const float ml2 = m * 1.4426950408889634f;
+      float s = 0.f, sx = 0.f, sy = 0.f;
+      for (int y = warp; y < H; y += nwarps) {
+        int y0, y1; float fy;
+        src_coord(y, h, H, y0, y1, fy);
+        const float* r0 = s_src + y0 * w;
+        const float* r1 = s_src + y1 * w;
+        float rs = 0.f, rsx = 0.f;
+        for (int x = lane; x < W; x += 32) {
+          const int x01 = s_x01[x];
+          const int x0 = x01 & 0xffff, x1 = x01 >> 16;
+          const float fx = s_fx[x];
+          const float top = fmaf(fx, r0[x1] - r0[x0], r0[x0]);
+          const float bot = fmaf(fx, r1[x1] - r1[x0], r1[x0]);
+          const float v = fmaf(fy, bot - top, top);
+          const float e = ex2(fmaf(v, 1.4426950408889634f, -ml2));
+          rs += e;
+          rsx = fmaf(e, (float)x + 0.5f, rsx);
         }
-        const float e = __expf(v - m);
-        s += e;
-        sx = fmaf(e, (float)x + 0.5f, sx);
-        sy = fmaf(e, (float)y + 0.5f, sy);
+        s += rs;
+        sx += rsx;
+        sy = fmaf(rs, (float)y + 0.5f, sy);
       }
-      const float bm = warp_max(m);
-      const float r = (m == -INFINITY) ? 0.f : __expf(m - bm);
-      s = warp_sum(s * r); sx = warp_sum(sx * r); sy = warp_sum(sy * r);
-      if (lane == 0) { red[warp] = bm; red[32 + warp] = s; red[64 + warp] = sx; red[96 + warp] = sy; }
+      s = warp_sum(s); sx = warp_sum(sx); sy = warp_sum(sy);
+      __syncthreads();  // everybody has read red[] (the maximum)
+      if (lane == 0) { red[warp] = s; red[8 + warp] = sx; red[16 + warp] = sy; }
       __syncthreads();
-      if (threadIdx.x == 0) {
-        float gm = -INFINITY;
-        for (int i = 0; i < nwarps; ++i) gm = fmaxf(gm, red[i]);
+      if (tid == 0) {
         float ts = 0.f, tx = 0.f, ty = 0.f;
-        for (int i = 0; i < nwarps; ++i) {
-          const float rr = __expf(red[i] - gm);
-          ts += red[32 + i] * rr; tx += red[64 + i] * rr; ty += red[96 + i] * rr;
-        }
+        for (int i = 0; i < nwarps; ++i) { ts += red[i]; tx += red[8 + i]; ty += red[16 + i]; }
         traj[((long long)g * 2 + 0) * T + t] = tx / ts;
         traj[((long long)g * 2 + 1) * T + t] = ty / ts;
       }
     } else {
       float a = 0.f;
-      for (int p = threadIdx.x; p < npix; p += blockDim.x) {
-        const int y = p / W, x = p - y * W;
-        a += bilerp(sm, h, w, y, x, H, W);
+      for (int i = tid; i < h * w; i += blockDim.x) {
+        const int sy_ = i / w, sx_ = i - sy_ * w;
+        a = fmaf(s_src[i], s_wy[sy_] * s_wx[sx_], a);
       }
       a = warp_sum(a);
+      __syncthreads();
       if (lane == 0) red[warp] = a;
       __syncthreads();
-      if (threadIdx.x == 0) {
+      if (tid == 0) {
         float tot = 0.f;
         for (int i = 0; i < nwarps; ++i) tot += red[i];
-        const float mean = tot / (float)npix;
+        const float mean = tot / (float)(H * W);
         if (ch == 1 && has_vis) vis[(long long)g * T + t] = mean;
         else if (has_depth) depth[(long long)g * T + t] = expf(mean);
       }
@@ -509,18 +563,15 @@ extern "C" int l4p_image_attention(const void* q16, const float* k, const float*
                                    int H, int d, float scale, int bf16, void* stream) {
   L4P_REQUIRE(q16 && k && v && out16, L4P_ERR_ARG, "l4p_image_attention: null pointer");
   L4P_REQUIRE(d == 88, L4P_ERR_SHAPE, "l4p_image_attention: head_dim=%d (this build: 88)", d);
-  L4P_REQUIRE(G > 0 && nk > 0 && nk <= kTokMaxQ && H > 0 && 256 % H == 0, L4P_ERR_SHAPE, "l4p_image_attention: nk=%d H=%d", nk, H);
+  L4P_REQUIRE(G > 0 && nk > 0 && nk <= kTokMaxQ && H > 0 && H <= 8, L4P_ERR_SHAPE, "l4p_image_attention: nk=%d H=%d (<= 8)", nk, H);
   const int rows_per_block = 128;
   L4P_REQUIRE(Np % rows_per_block == 0, L4P_ERR_SHAPE, "l4p_image_attention: Np=%d must be a multiple of %d", Np, rows_per_block);
   const size_t smem = sizeof(float) * 2 * (size_t)nk * H * d;
   const unsigned grid = (unsigned)(((long long)G * Np) / rows_per_block);
-  if (bf16) {
-    L4P_CHECK_CUDA(cudaFuncSetAttribute(image_attention_kernel<true, 88>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    image_attention_kernel<true, 88><<<grid, 256, smem, (cudaStream_t)stream>>>((const uint16_t*)q16, k, v, (uint16_t*)out16, Np, nk, H, scale, rows_per_block);
-  } else {
-    L4P_CHECK_CUDA(cudaFuncSetAttribute(image_attention_kernel<false, 88>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    image_attention_kernel<false, 88><<<grid, 256, smem, (cudaStream_t)stream>>>((const uint16_t*)q16, k, v, (uint16_t*)out16, Np, nk, H, scale, rows_per_block);
-  }
+  typedef void (*KFn)(const uint16_t*, const float*, const float*, uint16_t*, int, int, int, float, int);
+  KFn kfn = bf16 ? image_attention_kernel<true, 88> : image_attention_kernel<false, 88>;
+  L4P_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+  kfn<<<grid, 32 * H, smem, (cudaStream_t)stream>>>((const uint16_t*)q16, k, v, (uint16_t*)out16, Np, nk, H, scale, rows_per_block);
   L4P_CHECK_CUDA(cudaGetLastError());
   return L4P_OK;
 }
@@ -549,11 +600,12 @@ extern "C" int l4p_layernorm16(const void* x16, const float* gamma, const float*
 extern "C" int l4p_track_readout(const float* masks, float* traj, float* vis, float* depth, int G, int nch, int T, int h,
                                  int w, int H, int W, void* stream) {
   L4P_REQUIRE(masks && traj, L4P_ERR_ARG, "l4p_track_readout: null pointer");
-  L4P_REQUIRE(G > 0 && nch >= 1 && nch <= 3 && T > 0 && h > 0 && w > 0 && H > 0 && W > 0 && (size_t)h * w * 4 <= 160 * 1024,
+  L4P_REQUIRE(G > 0 && nch >= 1 && nch <= 3 && T > 0 && h > 0 && w > 0 && H > 0 && W > 0 && ((size_t)h * w + h + w + 2 * (size_t)W) * 4 <= 160 * 1024,
               L4P_ERR_SHAPE, "l4p_track_readout: bad shape");
   L4P_REQUIRE((nch < 2 || vis) && (nch < 3 || depth), L4P_ERR_ARG, "l4p_track_readout: missing output");
   L4P_CHECK_CUDA(cudaFuncSetAttribute(track_readout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-  track_readout_kernel<<<G * T, 256, (size_t)h * w * 4, (cudaStream_t)stream>>>(masks, traj, vis, depth, T, h, w, H, W,
+  L4P_REQUIRE(h < 65536 && w < 65536, L4P_ERR_SHAPE, "l4p_track_readout: source too large");
+  track_readout_kernel<<<G * T, 256, ((size_t)h * w + h + w + 2 * (size_t)W) * 4, (cudaStream_t)stream>>>(masks, traj, vis, depth, T, h, w, H, W,
                                                                                 nch >= 2, nch >= 3, nch);
   L4P_CHECK_CUDA(cudaGetLastError());
   return L4P_OK;

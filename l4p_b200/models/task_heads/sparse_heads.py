@@ -331,7 +331,8 @@ class VideoMAETrack2DSamHead(nn.Module):
             ops.token_attention(q, k16, v16, o, a["heads"], shared_kv=shared_now, scale=1.0 / math.sqrt(a["hd"]))
             return self._lin32(o.view(-1, o.shape[-1]), a["o"], res32=queries.view(-1, C).contiguous()).view(G, nt, C)
 
-        for w in pk["layers"]:
+        n_layers = len(pk["layers"])
+        for li, w in enumerate(pk["layers"]):
             # (1) token self attention
             if w["skip_pe"]:
                 o = self._token_attn(w["sa"], queries.view(-1, C), queries.view(-1, C), queries.view(-1, C), G)
@@ -359,9 +360,13 @@ class VideoMAETrack2DSamHead(nn.Module):
             ops.image_attention(q16.contiguous(), k.contiguous(), v.contiguous(), ao, G, a["heads"], 1.0 / math.sqrt(a["hd"]))
             new32 = torch.empty(G * Pn, C, device=dev, dtype=torch.float32)
             ops.linear(ao, a["o"]["w"], bias=a["o"]["b"], res_f32=keys32, res_row_mod=Pn if shared else 0, out_f32=new32)
-            keys32 = new32
             keys16 = torch.empty(G * Pn, C, device=dev, dtype=dt)
-            ops.layernorm(new32, w["n4"][0], w["n4"][1], w["n4"][2], out16=keys16, out32=keys32)
+            if li + 1 < n_layers:
+                keys32 = new32   # the fp32 LN output is the next layer's residual (written in place)
+                ops.layernorm(new32, w["n4"][0], w["n4"][1], w["n4"][2], out16=keys16, out32=keys32)
+            else:
+                keys32 = None    # after the last layer only the 16-bit operand copy is consumed (1.5 GB of HBM writes saved)
+                ops.layernorm(new32, w["n4"][0], w["n4"][1], w["n4"][2], out16=keys16)
             shared = False
         # final token -> image attention (transformer.py:104-109)
         queries = self._ln32(t2i(pk["final"], queries, keys16, shared), pk["nf"])
