@@ -96,6 +96,14 @@ typedef struct l4p_gemm_desc {
   int block_n;         /* N tile (multiple of 16, <= 256); 0 = choose                              */
   int cta_pair;        /* 0 = auto, 1 = force the 2-CTA (cta_group::2, 256-row tile) kernel, -1 = never */
   void* prof;          /* NULL, or device int64[3*512]: clock64 timeline of CTA 0 (producer / MMA / epilogue; tuning aid) */
+  /* Split-K (ROWMAJOR only): problems with few output tiles and a long K loop (low-resolution conv pyramid levels)
+   * are cut along K into split_k slices whose fp32 partial sums are atomically accumulated into splitk_ws, followed by
+   * a finalize kernel (bias / activation / residual / stores) that also re-zeroes the workspace.
+   * splitk_ws: NULL (never split) or a ZERO-FILLED device buffer of splitk_ws_bytes >= M*N*4 that no concurrently
+   * running l4p_gemm uses; split_k: 0 = choose, 1 = off, >1 = forced slice count. */
+  void* splitk_ws;
+  int64_t splitk_ws_bytes;
+  int split_k;
 } l4p_gemm_desc;
 
 /* Replaces F.linear/addmm (modeling_finetune.py:62-69,171-177,188), the 1x1x1/3x3x3 Conv3d and k==s

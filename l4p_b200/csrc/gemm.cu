@@ -60,7 +60,29 @@ extern "C" int l4p_gemm(const l4p_gemm_desc* d, void* stream_) {
   p.M = (int)d->M;
   p.N = (int)d->N;
   p.block_n = d->block_n > 0 ? d->block_n : pick_block_n(d->N);
-  if (d->block_n <= 0 && d->store_mode != L4P_STORE_HEAD1X1) {
+  // split-K decision (needs the tile and k-block counts up front)
+  int split_k = 1;
+  {
+    const long long tm = d->a_mode == L4P_A_CONV3D
+                             ? (long long)d->cB * ((d->cT + d->bT - 1) / d->bT) * ((d->cH + d->bH - 1) / d->bH) * ((d->cW + d->bW - 1) / d->bW)
+                             : (d->M + kBlockM - 1) / kBlockM;
+    const long long tiles = tm * ((d->N + p.block_n - 1) / p.block_n);
+    const long long nkb = d->a_mode == L4P_A_CONV3D ? (long long)d->kT * d->kH * d->kW * (d->cCin / kBlockK) : (d->K + kBlockK - 1) / kBlockK;
+    const bool can = d->store_mode == L4P_STORE_ROWMAJOR && d->splitk_ws != nullptr && d->splitk_ws_bytes >= d->M * d->N * 4 &&
+                     d->split_k != 1 && d->block_n <= 0;
+    if (can) {
+      if (d->split_k > 1) {
+        split_k = d->split_k;
+      } else if (tiles <= 48 && nkb >= 16) {
+        long long s_ = host_num_sms() / tiles;          // fill the machine ...
+        if (s_ > nkb / 4) s_ = nkb / 4;                  // ... with at least 4 k-blocks per slice
+        if (s_ >= 2) split_k = (int)s_;
+      }
+      if (split_k > nkb) split_k = (int)nkb;
+      if (split_k < 1) split_k = 1;
+    }
+  }
+  if (d->block_n <= 0 && d->store_mode != L4P_STORE_HEAD1X1 && split_k == 1) {
     // few output tiles (low-resolution pyramid levels, token-side GEMMs): trade tile width for CTAs so that more
     // than a handful of SMs work on the (long) K loop
     const long long tm = d->a_mode == L4P_A_CONV3D
@@ -201,9 +223,24 @@ extern "C" int l4p_gemm(const l4p_gemm_desc* d, void* stream_) {
   p.stages = stages;
   const size_t smem = (size_t)stages * stage_bytes + 1024 + epi_bytes;
 
-  const int num_tiles = p.tiles_m * p.tiles_n;
+  p.split_k = split_k;
+  p.splitk_ws = (float*)d->splitk_ws;
+  const int num_tiles = p.tiles_m * p.tiles_n * split_k;
   int grid = host_num_sms();
   if (grid > num_tiles) grid = num_tiles;
+
+  if (split_k > 1) {
+    // K slices accumulate into the fp32 workspace; the finalize kernel applies the epilogue and re-zeroes it
+    GemmKernelFn ks = find_kernel(epi_make(kStoreSplitK, L4P_ACT_NONE, 0), d->bf16 != 0, false);
+    L4P_REQUIRE(ks != nullptr, L4P_ERR_ARG, "l4p_gemm: split-K kernel instance missing");
+    L4P_CHECK_CUDA(cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kRingBudget + 1024 + epi_bytes)));
+    L4P_CHECK_CUDA(launch_pdl(ks, dim3(grid), dim3(threads), smem, stream, tmA, tmB, p));
+    const long long n4 = (long long)p.M * (p.N / 4);
+    long long fgrid = (n4 + 255) / 256;
+    if (fgrid > 8ll * host_num_sms()) fgrid = 8ll * host_num_sms();
+    L4P_CHECK_CUDA(launch_pdl(gemm_splitk_finalize(d->bf16 != 0), dim3((unsigned)fgrid), dim3(256), 0, stream, p));
+    return L4P_OK;
+  }
 
   // CTA pairs (256-row tiles) when the problem is large enough to fill the machine with pair tiles
   const int pair_tiles = ((p.tiles_m + 1) / 2) * p.tiles_n;

@@ -16,4 +16,8 @@ const GemmKernelSet* gemm_instances_d(int* n) {
   return sets;
 }
 
+void (*gemm_splitk_finalize(bool bf16))(const GemmKParams) {
+  return bf16 ? splitk_finalize_kernel<true> : splitk_finalize_kernel<false>;
+}
+
 }  // namespace l4p

@@ -47,6 +47,7 @@ constexpr int EPI_OUT32 = 1 << 7;
 constexpr int EPI_OUT16 = 1 << 8;
 constexpr int EPI_OUT16R = 1 << 9;   // second 16-bit output = relu(out)
 constexpr int EPI_GENERIC = 1 << 10; // activation and ROWMAJOR options decided at run time (slow, always correct)
+constexpr int kStoreSplitK = 5;      // internal store mode: fp32 atomic accumulation of a K-slice into the split-K workspace
 constexpr int epi_make(int store, int act, int flags) { return store | (act << 3) | flags; }
 constexpr int epi_store(int e) { return e & 7; }
 // Epilogue warpgroups (group g handles column chunks c with c % groups == g). The fused-dot modes are bound by the
@@ -107,6 +108,8 @@ struct GemmKParams {
   long long rows_per_group;  // STORE_HYPER: w2 is indexed by row / rows_per_group
   FastDiv fd_cW, fd_cH, fd_cT, fd_rpg;  // HYPER finalisation: row -> (g,t,h,w), row -> hyper group
   FastDiv fd_bW, fd_bH;                 // HEAD1X1 finalisation: row in tile -> (tl,hl,wl)
+  int split_k;               // >1: work unit = (tile, k-range); partial sums are atomically added to splitk_ws [M,N] fp32
+  float* splitk_ws;
   long long* prof;           // optional [3][512] clock64 timeline of CTA 0
 };
 
@@ -408,7 +411,7 @@ L4P_DEVICE void epilogue_tile(const GemmKParams& p, const TileCoord& tc, const i
   const int n0 = tc.n_blk * p.block_n;
   const uint32_t t_addr = t_acc + ((uint32_t)(q4 * 32) << 16);
 
-  if constexpr (STORE == L4P_STORE_ROWMAJOR || STORE == L4P_STORE_QKV || STORE == L4P_STORE_CONVT) {
+  if constexpr (STORE == L4P_STORE_ROWMAJOR || STORE == L4P_STORE_QKV || STORE == L4P_STORE_CONVT || STORE == kStoreSplitK) {
     // ---------------------------------------------------------------- transposed (coalesced) store modes
     const RowInfo ri = row_info(p, tc, r);
     const long long row = ri.row;
@@ -422,7 +425,9 @@ L4P_DEVICE void epilogue_tile(const GemmKParams& p, const TileCoord& tc, const i
 
     // per-row indices, gathered into the phase-B shape: iteration `it` of a lane works on row it*4 + lane/8
     int my_o, my_r = 0;
-    if constexpr (STORE == L4P_STORE_ROWMAJOR) {
+    if constexpr (STORE == kStoreSplitK) {
+      my_o = (int)row;
+    } else if constexpr (STORE == L4P_STORE_ROWMAJOR) {
       my_o = (int)row;
       my_r = p.res_row_mod > 0 ? (int)(row % p.res_row_mod) : (int)row;
     } else if constexpr (STORE == L4P_STORE_QKV) {
@@ -569,6 +574,19 @@ L4P_DEVICE void epilogue_tile(const GemmKParams& p, const TileCoord& tc, const i
       }
       const uint32_t rbase = stage + (uint32_t)rgrp * 128u;
 
+      if constexpr (STORE == kStoreSplitK) {
+        // K-slice partial sums -> fp32 workspace [M, N]; bias / activation / residuals are applied by the finalize kernel
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const uint32_t rl = (uint32_t)(it * 4 + rgrp);
+          const float4 x = lds128(rbase + (uint32_t)it * 512u + ((((uint32_t)sub) ^ (rl & 7u)) << 4));
+          if (cok && ((okm >> it) & 1u)) {
+            float* dst = p.splitk_ws + ((long long)orow[it] * p.N + col);
+            atomicAdd(dst, x.x); atomicAdd(dst + 1, x.y); atomicAdd(dst + 2, x.z); atomicAdd(dst + 3, x.w);
+          }
+        }
+        continue;
+      }
       float4 xs[8];  // all staging reads first: the asm memory clobbers would otherwise serialise them with the stores
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
@@ -697,7 +715,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t b_bytes = (uint32_t)p.block_n * 128u;
   const uint32_t stage_bytes = kABytes + b_bytes;
-  const int num_tiles = p.tiles_m * p.tiles_n;
+  const int num_tiles = p.tiles_m * p.tiles_n * p.split_k;  // work units: (tile, K slice); split_k == 1 outside split-K mode
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
@@ -737,11 +755,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       int stage = 0, pg = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const TileCoord tc = decode_tile(p, tile);
+        const TileCoord tc = decode_tile(p, tile / p.split_k);
+        const int split = tile % p.split_k;
+        const int kb0 = (int)((long long)split * p.num_kb / p.split_k), kb1 = (int)((long long)(split + 1) * p.num_kb / p.split_k);
         const int n0 = tc.n_blk * p.block_n;
         // filter-tap walk (cb fastest, then dw, dh, dt) kept as counters: no divisions in the single-thread hot loop
         int cb = 0, dw = -(p.kW / 2), dh = -(p.kH / 2), dt = -(p.kT / 2);
-        for (int kb = 0; kb < p.num_kb; ++kb) {
+        if (p.a_mode == L4P_A_CONV3D && kb0 > 0) {
+          const int tapi = kb0 / p.cblocks;
+          cb = kb0 - tapi * p.cblocks;
+          dw = tapi % p.kW - p.kW / 2;
+          dh = (tapi / p.kW) % p.kH - p.kH / 2;
+          dt = tapi / (p.kW * p.kH) - p.kT / 2;
+        }
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
           const uint32_t full = smem_u32(&bar_full[stage]);
           const uint32_t sa = smem_base + stage * stage_bytes;
@@ -782,7 +809,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       mbar_wait(smem_u32(&bar_tempty[acc]), acc_phase ^ 1u);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)acc * kAccCols;
-      for (int kb = 0; kb < p.num_kb; ++kb) {
+      const int split = tile % p.split_k;
+      const int kb0 = (int)((long long)split * p.num_kb / p.split_k), kb1 = (int)((long long)(split + 1) * p.num_kb / p.split_k);
+      for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(smem_u32(&bar_full[stage]), phase);
         tc_fence_after();
         if (leader) {
@@ -792,10 +821,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           for (int k = 0; k < kBlockK / 16; ++k) {
             // advance 16 elements (32 B) along K inside the swizzle row: +2 in the (addr >> 4) field
             umma_ss(d_tmem, umma_desc_make(a_lo + 2 * k, hi128), umma_desc_make(b_lo + 2 * k, hi128), idesc,
-                    (kb | k) != 0 ? 1u : 0u);
+                    (kb > kb0 || k != 0) ? 1u : 0u);
           }
           umma_commit(smem_u32(&bar_empty[stage]));
-          if (kb == p.num_kb - 1) umma_commit(smem_u32(&bar_tfull[acc]));
+          if (kb == kb1 - 1) umma_commit(smem_u32(&bar_tfull[acc]));
         }
         __syncwarp();
         ++mg;
@@ -812,7 +841,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     uint32_t acc_phase = 0;
     if (threadIdx.x == 0) GEMM_STAMP(2, 511);  // kernel-start reference
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const TileCoord tc = decode_tile(p, tile);
+      const TileCoord tc = decode_tile(p, tile / p.split_k);
       const uint32_t tempty = smem_u32(&bar_tempty[acc]);
       epilogue_tile<BF16, EPI>(p, tc, q4, lane, egrp, smem_u32(&bar_tfull[acc]), acc_phase, tmem_base + (uint32_t)acc * kAccCols,
                           &dot_sh, eg, smem_base + (uint32_t)p.stages * stage_bytes + (uint32_t)warp * kEpiStageBytes,
@@ -827,7 +856,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       int tile = blockIdx.x;
       dot_helper_loop<EPI>(p, reinterpret_cast<DotShared&>(dot_sh), lane, [&](TileCoord& tc) {
         if (tile >= num_tiles) return false;
-        tc = decode_tile(p, tile);
+        tc = decode_tile(p, tile / p.split_k);
         tile += gridDim.x;
         return true;
       });
@@ -1027,6 +1056,40 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   }
 }
 
+// split-K finalisation: out = epilogue(workspace), workspace re-zeroed for the next split-K launch (4 columns per thread)
+template <bool BF16>
+__global__ void __launch_bounds__(256)
+splitk_finalize_kernel(const GemmKParams p) {
+  pdl_wait();
+  const long long n4 = p.N >> 2;
+  const long long total = (long long)p.M * n4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / n4;
+    const int col = (int)(i - row * n4) * 4;
+    float4* w = reinterpret_cast<float4*>(p.splitk_ws + row * p.N + col);
+    float4 x = *w;
+    *w = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.bias != nullptr) {
+      const float4 b4 = *reinterpret_cast<const float4*>(p.bias + col);
+      x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
+    }
+    apply_act2_rt(x.x, x.y, p.act);
+    apply_act2_rt(x.z, x.w, p.act);
+    if (p.res_f32 != nullptr) {
+      const long long rrow = p.res_row_mod > 0 ? row % p.res_row_mod : row;
+      const float4 r4 = *reinterpret_cast<const float4*>(p.res_f32 + rrow * p.ld_res + col);
+      x.x += r4.x; x.y += r4.y; x.z += r4.z; x.w += r4.w;
+    }
+    if (p.res_16 != nullptr) add_res16<BF16>(x, p.res_16 + row * p.ld_res + col);
+    if (p.res2_16 != nullptr) add_res16<BF16>(x, p.res2_16 + row * p.ld_res + col);
+    const long long o = row * p.ld_out + col;
+    if (p.out_f32 != nullptr) *reinterpret_cast<float4*>(p.out_f32 + o) = x;
+    if (p.out_16 != nullptr) store4_16<BF16>(p.out_16 + o, x);
+    if (p.out_16_relu != nullptr)
+      store4_16<BF16>(p.out_16_relu + o, make_float4(fmaxf(x.x, 0.f), fmaxf(x.y, 0.f), fmaxf(x.z, 0.f), fmaxf(x.w, 0.f)));
+  }
+}
+
 typedef void (*GemmKernelFn)(const CUtensorMap, const CUtensorMap, const GemmKParams);
 
 // One entry per compiled epilogue configuration: [bf16][pair]
@@ -1042,5 +1105,6 @@ const GemmKernelSet* gemm_instances_a(int* n);
 const GemmKernelSet* gemm_instances_b(int* n);
 const GemmKernelSet* gemm_instances_c(int* n);
 const GemmKernelSet* gemm_instances_d(int* n);
+void (*gemm_splitk_finalize(bool bf16))(const GemmKParams);
 
 }  // namespace l4p

@@ -45,6 +45,7 @@ class GemmDesc(C.Structure):
         ("block_n", C.c_int),
         ("cta_pair", C.c_int),
         ("prof", C.c_void_p),
+        ("splitk_ws", C.c_void_p), ("splitk_ws_bytes", C.c_int64), ("split_k", C.c_int),
     ]
 
 

@@ -6,7 +6,7 @@ nothing here computes on the CPU or falls back to ATen.
 from __future__ import annotations
 
 import ctypes as C
-from typing import Optional, Tuple
+from typing import Dict, Optional, Tuple
 
 import torch
 
@@ -71,6 +71,22 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
     _count()
 
 
+# zero-filled fp32 split-K workspaces, one per (device, stream): kernels on different streams may run concurrently.
+# l4p_gemm's finalize kernel re-zeroes what it used, so a buffer stays valid for the next call on the same stream.
+_SPLITK_WS: Dict[Tuple[int, int], torch.Tensor] = {}
+SPLITK_WS_BYTES = 8 << 20   # covers M*N*4 of every low-resolution pyramid level (largest: 4096 x 256 fp32 = 4 MiB)
+SPLITK = True
+
+
+def _splitk_ws(dev: torch.device) -> torch.Tensor:
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), _stream() or 0)
+    ws = _SPLITK_WS.get(key)
+    if ws is None:
+        ws = torch.zeros(SPLITK_WS_BYTES // 4, device=dev, dtype=torch.float32)
+        _SPLITK_WS[key] = ws
+    return ws
+
+
 def _base_desc(a: torch.Tensor, w: torch.Tensor) -> _l.GemmDesc:
     _dev_init(a)
     _chk(a, "a", sixteen=True); _chk(w, "w", sixteen=True)
@@ -80,6 +96,11 @@ def _base_desc(a: torch.Tensor, w: torch.Tensor) -> _l.GemmDesc:
     d.a = a.data_ptr(); d.w = w.data_ptr()
     d.cta_pair = GEMM_PAIR
     d.bf16 = 1 if a.dtype == torch.bfloat16 else 0
+    if SPLITK:
+        ws = _splitk_ws(a.device)
+        d.splitk_ws, d.splitk_ws_bytes, d.split_k = ws.data_ptr(), ws.numel() * 4, 0
+    else:
+        d.split_k = 1
     return d
 
 

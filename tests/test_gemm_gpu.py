@@ -172,6 +172,45 @@ def test_conv_transpose(dtype, stride):
 
 
 @pytest.mark.parametrize("dtype", DT)
+def test_splitk_conv_and_linear(dtype):
+    """Few output tiles + long K (low-resolution DPT pyramid levels): the split-K path (fp32 atomics into the per-stream
+    workspace + finalize kernel) must match the fused single-pass epilogue, and leave its workspace zeroed."""
+    ops = _ops()
+    from l4p_b200 import ops as O
+    B, T, H, W, Cin, Cout = 1, 4, 8, 8, 1024, 256
+    x = _rand((B, T, H, W, Cin), dtype, 50)
+    w = _rand((Cout, 27 * Cin), dtype, 51, (27 * Cin) ** -0.5)
+    b = _rand((Cout,), torch.float32, 52)
+    r1 = _rand((B, T, H, W, Cout), dtype, 53)
+    o = torch.empty(B, T, H, W, Cout, device="cuda", dtype=dtype)
+    orl = torch.empty_like(o)
+    ops.conv3d(x, w, ksize=(3, 3, 3), bias=b, res_16=r1, out_16=o, out_16_relu=orl)
+    torch.cuda.synchronize()
+    ref = _conv_ref(x, w, (3, 3, 3), b) + r1.float()
+    tol = 2 ** -8 if dtype == torch.bfloat16 else 2 ** -10
+    _close(o, ref, tol)
+    _close(orl, ref.clamp_min(0), tol)
+    assert all(float(ws.abs().max()) == 0.0 for ws in O._SPLITK_WS.values()), "split-K workspace not re-zeroed"
+    # same problem with split-K disabled: results agree to fp32 summation-order noise
+    O.SPLITK = False
+    try:
+        o2 = torch.empty_like(o)
+        ops.conv3d(x, w, ksize=(3, 3, 3), bias=b, res_16=r1, out_16=o2)
+    finally:
+        O.SPLITK = True
+    torch.cuda.synchronize()
+    _close(o, o2.float(), 2 * tol)  # two independently rounded 16-bit results may differ by one ulp
+    M, N, K = 256, 1024, 27648
+    a = _rand((M, K), dtype, 54)
+    wl = _rand((N, K), dtype, 55, K ** -0.5)
+    y = torch.empty(M, N, device="cuda", dtype=dtype)
+    ops.linear(a, wl, bias=_rand((N,), torch.float32, 56), act=2, out_16=y)
+    torch.cuda.synchronize()
+    refl = (a.float() @ wl.float().t() + _rand((N,), torch.float32, 56)).clamp_min(0)
+    _close(y, refl, tol)
+
+
+@pytest.mark.parametrize("dtype", DT)
 def test_conv_transpose_hyper(dtype):
     """Mask-decoder tail (sam/mask_decoder.py:62-66,137-139): ConvT(k==s) -> GELU -> per-query hyper-network dot."""
     ops = _ops()
