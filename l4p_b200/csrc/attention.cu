@@ -8,13 +8,14 @@
 //   warp 1       UMMA issuer (one thread): S_t = Q_t K_j^T (M128 N128 K96) into TMEM, O_t += P_t V_j
 //                (M128 N96 K128) into TMEM; S_t(j+1) is issued before P_t(j) V_j so the tensor pipe
 //                works while the softmax warps run
-//   warp 2       TMEM allocator (512 columns: S0 | S1 | O0 | O1)
+//   warp 2       TMEM allocator (512 columns: S0 | S1 | O0 | O1 | P0)
 //   warps 4..7   softmax warpgroup for tile 0, one query row per thread
 //   warps 8..11  softmax warpgroup for tile 1
 //
 // Softmax: fp32 scores from TMEM, running max with lazy rescale (O is only rescaled in TMEM when the row max
 // grew by more than 2^8), exp2 with the scale folded into one FFMA, fp32 row sums, P rounded to the operand
-// type and written to 128B-swizzled smem as the A operand of the PV UMMA.
+// type; tile 0's P goes back to TMEM (64 spare columns) as the A operand of a TS-mode PV UMMA, tile 1's P to
+// 128B-swizzled smem (SS mode).
 //
 // Layouts (produced by the QKV GEMM epilogue, see gemm.cu L4P_STORE_QKV):
 //   Q, K : [B, H, N, dpad]   (dpad = 96, columns >= head_dim are zero)
@@ -36,8 +37,12 @@ constexpr int kVBytes = kDPad * kTileN * 2;      // 24576: 2 chunks x (96 rows x
 constexpr int kPBytes = kTileM * kTileN * 2;     // 32768: 2 chunks x (128 rows x 128 B)
 constexpr int kKS = 2, kVS = 2;
 constexpr int kAttSmem = 2 * kQTileBytes + kKS * kKBytes + kVS * kVBytes + 2 * kPBytes + 1024;
-constexpr uint32_t kColS0 = 0, kColS1 = 128, kColO0 = 256, kColO1 = 384;
+constexpr uint32_t kColS0 = 0, kColS1 = 128, kColO0 = 256, kColO1 = 352, kColP0 = 448;  // P0: tile 0's probabilities (64 columns)
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
+#ifndef L4P_ATT_P_TMEM
+#define L4P_ATT_P_TMEM 1
+#endif
+constexpr bool kPTmem = L4P_ATT_P_TMEM != 0;  // tile 0's P through the 64 spare TMEM columns (TS-mode UMMA)
 
 struct AttParams {
   uint16_t* out;
@@ -160,6 +165,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       // ---------------------------------------------------------------- UMMA issuer
       // The whole warp walks the pipeline (warp-uniform control flow keeps descriptors in uniform registers);
       // one elected lane issues. Descriptor words are precomputed: per UMMA only an add remains.
+      // Measured (tools/ubench/umma_bench.cu): an SS-mode UMMA costs ~43 + N/2 cycles (the 128 x 16 A operand is
+      // fetched from shared memory before B streams), a TS-mode one ~10 + N/2, and one thread issues at most one per
+      // ~93 cycles. The 12 + 16 UMMAs of a key block therefore occupy the tensor pipe for ~2700 cycles against 1536
+      // cycles of arithmetic - that, not the softmax, bounds this kernel. A second issuer warp (one per query tile)
+      // was tried: the pipe speeds up ~10 % but both softmax warpgroups then run their exp phases in lockstep and the
+      // kernel gets slower.
       const bool leader = elect_one();
       const uint32_t idesc_s = umma_idesc_f16(BF16, kTileM, kTileN);
       const uint32_t idesc_o = umma_idesc_f16(BF16, kTileM, kDPad);
@@ -181,9 +192,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 #pragma unroll
         for (int kk = 0; kk < kTileN / 16; ++kk) {
           const uint32_t o = ((uint32_t)(kk & 3) * 32) >> 4;
-          umma_ss(d, umma_desc_make(pa + (uint32_t)(kk >> 2) * ((kTileM * 128) >> 4) + o, hi128),
-                  umma_desc_make(va + (uint32_t)(kk >> 2) * ((kDPad * 128) >> 4) + o, hi128), idesc_o,
-                  kk != 0 ? 1u : acc);
+          const uint64_t vdesc = umma_desc_make(va + (uint32_t)(kk >> 2) * ((kDPad * 128) >> 4) + o, hi128);
+          if (kPTmem && t == 0)  // P_0 is the TMEM A operand: 8 columns per K = 16 step, no shared-memory traffic for P
+            umma_ts(d, tmem_base + kColP0 + (uint32_t)kk * 8u, vdesc, idesc_o, kk != 0 ? 1u : acc);
+          else
+            umma_ss(d, umma_desc_make(pa + (uint32_t)(kk >> 2) * ((kTileM * 128) >> 4) + o, hi128), vdesc, idesc_o,
+                    kk != 0 ? 1u : acc);
         }
         umma_commit(smem_u32(&bar_pvdone[t]));
       };
@@ -213,7 +227,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             __syncwarp();
           }
           ATT_STAMP(2, j, t * 4 + 0);
-          mbar_wait(smem_u32(&bar_pfull[t]), (uint32_t)j & 1u);  // P_t(j) in smem (and O_t rescaled)
+          mbar_wait(smem_u32(&bar_pfull[t]), (uint32_t)j & 1u);  // P_t(j) ready (and O_t rescaled)
           ATT_STAMP(2, j, t * 4 + 1);
           if (t == 0) mbar_wait(smem_u32(&bar_vfull[sv]), ((uint32_t)(j / kVS)) & 1u);
           tc_fence_after();
@@ -329,15 +343,26 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 
       if (j > 0) mbar_wait(smem_u32(&bar_pvdone[t]), (uint32_t)(j - 1) & 1u);  // P_t smem is free again
       ATT_STAMP(t, j, 5);
+      if (kPTmem && t == 0) {
+        // tile 0: P goes straight back to TMEM (row = lane, two probabilities per 32-bit column) as the A operand of PV
+        const uint32_t tP = tmem_base + lane_addr + kColP0;
+        tmem_st16(tP + 0, s + 0);
+        tmem_st16(tP + 16, s + 16);
+        tmem_st16(tP + 32, s + 32);
+        tmem_st16(tP + 48, s + 48);
+        tmem_st_wait();
+        tc_fence_before();
+      } else {
 #pragma unroll
-      for (int u = 0; u < 16; ++u) {
-        // 16-byte unit u: keys [8u, 8u+8); chunk = u/8; swizzled unit inside the 128-byte row
-        const uint32_t addr = pRow + (uint32_t)(u >> 3) * (kTileM * 128) + ((((uint32_t)u & 7u) ^ swz) << 4);
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(s[4 * u]), "r"(s[4 * u + 1]),
-                     "r"(s[4 * u + 2]), "r"(s[4 * u + 3])
-                     : "memory");
+        for (int u = 0; u < 16; ++u) {
+          // 16-byte unit u: keys [8u, 8u+8); chunk = u/8; swizzled unit inside the 128-byte row
+          const uint32_t addr = pRow + (uint32_t)(u >> 3) * (kTileM * 128) + ((((uint32_t)u & 7u) ^ swz) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(s[4 * u]), "r"(s[4 * u + 1]),
+                       "r"(s[4 * u + 2]), "r"(s[4 * u + 3])
+                       : "memory");
+        }
+        fence_proxy_async();
       }
-      fence_proxy_async();
       mbar_arrive(smem_u32(&bar_pfull[t]));
       ATT_STAMP(t, j, 6);
     }
