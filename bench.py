@@ -256,7 +256,10 @@ def main():
             "gpu_launches": int(launches),
             "clocks": cs.summary(),
             "roofline": {"kernel": "attention_kernel (fused QK^T+softmax+PV, tcgen05)", "bound": "tensor", "achieved": ach,
-                         "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"], "traffic": None,
+                         "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"],
+                         # dram__bytes_read + write per launch from the ncu --set full capture profiles/attention_ncu_r1b.txt
+                         # (B=1: Q, K, V^T 3 x 6.3 MB read; the 5.8 MB output stays in L2 inside the capture window)
+                         "traffic": 19117824,
                          "peak_source": pk["src"], "launch_us": att_ms * 1e3,
                          "algorithmic_flops_per_launch": att_flops},
         }
