@@ -52,6 +52,11 @@ class L4P_VideoMAE(torch.nn.Module):
         # run independent task heads on concurrent CUDA streams (L4P_SERIAL_HEADS=1 turns it off for per-op profiling)
         self.parallel_heads = parallel_heads and __import__("os").environ.get("L4P_SERIAL_HEADS", "0") != "1"
         self._streams: Dict[Any, List[torch.cuda.Stream]] = {}
+        # multi-GPU long-video mode (cfg 4): set by enable_window_sharding(); every rank encodes and
+        # decodes only its contiguous block of windows, one all-gather per head assembles the per-window outputs and
+        # the (cheap, sequential) stitching / alignment chain runs redundantly on every rank
+        self.window_shard_group: Any = None
+        self.shard_windows: bool = False
         self.set_compute_dtype(compute_dtype)
         # freeze_* / unfreeze_blocks are training-only knobs: accepted for config compatibility, parameters of
         # this inference-only implementation never require grad.
@@ -64,6 +69,12 @@ class L4P_VideoMAE(torch.nn.Module):
         for head in self.task_heads.values():
             if hasattr(head, "compute_dtype"):
                 head.compute_dtype = dtype
+
+    def enable_window_sharding(self, enabled: bool = True, group: Any = None) -> None:
+        """Shard the windows of a long video across the ranks of `group` (default: the world group). Dense tasks only
+        (depth / flow / dyn-mask / camray incl. joint alignment): the track head's window memory is sequential."""
+        self.shard_windows = bool(enabled)
+        self.window_shard_group = group
 
     def encode_features(self, data: Dict[str, Any]):
         """Generates video encoder features for a single window (l4p_videomae.py:222-232)."""
@@ -133,13 +144,30 @@ class L4P_VideoMAE(torch.nn.Module):
         assert T % self.window_stride_T == 0, "Temporal window needs to be a multiple of window stride, for now!"
         time_strides = torch.arange(0, T - self.window_size[0] + 1, self.window_stride_T)
 
-        batched, enc_features_bpc_2dlist = self._encode_windows(data["rgb_b3thw"], [int(s) for s in time_strides])
+        starts = [int(s) for s in time_strides]
+        shard = None
+        if self.shard_windows:
+            import torch.distributed as dist
+            from ..parallel import WindowShard
+            assert dist.is_initialized(), "window sharding needs an initialised torch.distributed process group"
+            assert "track_2d" not in tasks, "the track head's window memory is sequential: not window-shardable (SURVEY §8e)"
+            assert B == 1, "window sharding: one video at a time"
+            shard = WindowShard.for_rank(len(starts), self.window_shard_group)
+            local_starts = starts[shard.start:shard.start + shard.count]
+            if shard.count > 0:
+                batched, enc_features_bpc_2dlist = self._encode_windows(data["rgb_b3thw"], local_starts)
+            else:
+                batched, enc_features_bpc_2dlist = None, []
+        else:
+            batched, enc_features_bpc_2dlist = self._encode_windows(data["rgb_b3thw"], starts)
         out: Dict[str, Any] = {"enc_features_bpc_2dlist": enc_features_bpc_2dlist}
 
         # The heads only read the encoder features: they are independent jobs (the reference runs them one after the
         # other, l4p_videomae.py:299-328). Each job runs on its own CUDA stream so that the low-occupancy kernels of
         # one head (low-resolution pyramid levels, token-side GEMMs, small solves) overlap the big kernels of another.
         common = dict(enc_features_bpc_2dlist=enc_features_bpc_2dlist, time_strides=time_strides, _batched_windows=batched)
+        if shard is not None:
+            common["_window_shard"] = shard
         jobs = []
         joint_alignment_possible = "depth" in tasks and "camray" in tasks
         if self.joint_alignment and joint_alignment_possible:

@@ -86,8 +86,17 @@ class VideoMAEFlowDPTHead(nn.Module):
         """Per-window `forward` outputs. Windows are independent here, so this is the hook where a batched
         encoder result (L4P_VideoMAE passes `_batched_windows`) is consumed in one DPT launch sequence."""
         batched = kwargs.pop("_batched_windows", None)
+        shard = kwargs.pop("_window_shard", None)
         window_size = img_info[0] if self.output_size is None else self.output_size[0]
         key = f"{self.task_name}_est_{self.task_suffix}"
+        if shard is not None:
+            # multi-GPU: this rank holds the features of windows [shard.start, shard.start + shard.count) only
+            from ...parallel import gather_window_outputs
+            local = []
+            if shard.count > 0:
+                out = self.forward(batched, img_info=img_info, **kwargs)[key]
+                local = list(out.reshape(shard.count, -1, *out.shape[1:]).unbind(0))
+            return gather_window_outputs([local], shard)[0]
         if batched is not None:
             nW = len(enc_features_bpc_2dlist)
             out = self.forward(batched, img_info=img_info, **kwargs)[key]  # [(B*nW), C, T, H, W], window-major
@@ -225,13 +234,21 @@ class VideoMAETraj3DDPTHead(VideoMAEFlowDPTHead):
     def forward_windowed(self, enc_features_bpc_2dlist, img_info=(16, 224, 224), time_strides=None,
                          intrinsics_b44t=None, **kwargs):
         batched = kwargs.pop("_batched_windows", None)
+        shard = kwargs.pop("_window_shard", None)
         if time_strides is None:
             return self.forward(enc_features_bpc_2dlist[0], img_info=img_info, intrinsics_b44t=intrinsics_b44t, **kwargs)
         window_size = self.output_size[0] if self.output_size is not None else img_info[0]
         T = int(time_strides[-1] + window_size)
         nW = time_strides.shape[0]
         rays_all = None
-        if batched is not None:
+        if shard is not None:
+            from ...parallel import gather_window_outputs
+            local = []
+            if shard.count > 0:
+                r = self.rays(batched, img_info)
+                local = list(r.reshape(shard.count, -1, *r.shape[1:]).unbind(0))
+            rays_all = gather_window_outputs([local], shard)[0]
+        elif batched is not None:
             r = self.rays(batched, img_info)
             rays_all = r.reshape(nW, -1, *r.shape[1:])
         key = f"{self.task_name}_est_{self.task_suffix}"
@@ -259,6 +276,7 @@ def joint_windowed_estimation(task_names: List[str], task_heads: nn.ModuleDict, 
     (dense_heads.py:360-492). Per-window head outputs are computed as one batch; the alignment chain is
     sequential across windows and runs on the device (KabaschUmeyama3DAligner)."""
     batched = kwargs.pop("_batched_windows", None)
+    shard = kwargs.pop("_window_shard", None)
     out_all_tasks: Dict[str, torch.Tensor] = {}
     if time_strides is None:
         for task_name in task_names:
@@ -275,7 +293,17 @@ def joint_windowed_estimation(task_names: List[str], task_heads: nn.ModuleDict, 
     ikey = f"{cam_head.task_name}_intrinsics_est_{cam_head.task_suffix}"
 
     # independent per-window network outputs, batched over windows when the encoder result is batched
-    if batched is not None:
+    if shard is not None:
+        # multi-GPU (cfg 4): depth maps and ray maps of this rank's windows -> ONE all-gather -> every rank runs the chain
+        from ...parallel import gather_window_outputs
+        dl, rl = [], []
+        if shard.count > 0:
+            d = depth_head.forward(batched, img_info=img_info)[dkey]
+            dl = list(d.reshape(shard.count, -1, *d.shape[1:]).unbind(0))
+            r = cam_head.rays(batched, img_info)
+            rl = list(r.reshape(shard.count, -1, *r.shape[1:]).unbind(0))
+        depth_w, rays_w = gather_window_outputs([dl, rl], shard)
+    elif batched is not None:
         d = depth_head.forward(batched, img_info=img_info)[dkey]
         depth_w = list(d.reshape(nW, -1, *d.shape[1:]).unbind(0))
         r = cam_head.rays(batched, img_info)

@@ -1,0 +1,97 @@
+"""Multi-GPU sharding of the hot path: one process per GPU, weights replicated, independent units
+(clips, windows of a long video) partitioned across ranks, ONE all-gather of the packed per-unit outputs per step.
+The sequential parts (alignment chains, the sliding-window track memory) run after the gather, redundantly on
+every rank, so every rank ends up with the full result (like the reference's single-process output).
+
+Only `torch.distributed` plumbing lives here (NCCL over NVLink on the GPU box, gloo in the CPU tests); no kernel
+of the path has a collective inside."""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Any, Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def contiguous_partition(n_units: int, world: int) -> List[Tuple[int, int]]:
+    """(start, count) per rank: contiguous blocks of ceil(n/world) units, so that overlap neighbours of a long video
+    are mostly local (cfg 4); trailing ranks may get fewer (or zero) units."""
+    per = -(-n_units // world)
+    return [(min(r * per, n_units), max(0, min(n_units, (r + 1) * per) - r * per)) for r in range(world)]
+
+
+def round_robin_partition(n_units: int, world: int) -> List[List[int]]:
+    """clip i -> rank i mod N (cfg 3)."""
+    return [[i for i in range(n_units) if i % world == r] for r in range(world)]
+
+
+@dataclass
+class WindowShard:
+    """This rank's slice of the windows of one long video."""
+    start: int
+    count: int
+    n_windows: int
+    group: Optional[Any] = None
+
+    @property
+    def world(self) -> int:
+        return dist.get_world_size(self.group)
+
+    @property
+    def per_rank(self) -> int:
+        return -(-self.n_windows // self.world)
+
+    @staticmethod
+    def for_rank(n_windows: int, group=None) -> "WindowShard":
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        start, count = contiguous_partition(n_windows, world)[rank]
+        return WindowShard(start, count, n_windows, group)
+
+
+def gather_window_outputs(local: Sequence[Sequence[torch.Tensor]], shard: WindowShard) -> List[List[torch.Tensor]]:
+    """local[k][w]: output k (e.g. depth, rays) of this rank's w-th window. Returns the same structure for ALL
+    windows of the video, identical on every rank. All outputs of all local windows travel in ONE
+    all_gather_into_tensor (packed fp32 buffer, padded to ceil(nW/world) windows per rank)."""
+    per, world = shard.per_rank, shard.world
+    # shapes come from whatever rank has at least one window; every rank has the same per-window shapes by construction
+    ref = [o[0] for o in local] if shard.count > 0 else None
+    meta = [None]
+    if ref is not None:
+        meta = [[(tuple(t.shape), t.dtype) for t in ref]]
+    if ref is None or world > 1:
+        metas = [None] * world
+        dist.all_gather_object(metas, meta[0], group=shard.group)
+        meta0 = next(m for m in metas if m is not None)
+    else:
+        meta0 = meta[0]
+    sizes = [int(torch.tensor(s).prod()) if len(s) else 1 for s, _ in meta0]
+    unit = sum(sizes)
+    dev = ref[0].device if ref is not None else torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
+    packed = torch.zeros(per, unit, device=dev, dtype=torch.float32)
+    for w in range(shard.count):
+        off = 0
+        for k, n in enumerate(sizes):
+            packed[w, off:off + n] = local[k][w].reshape(-1).float()
+            off += n
+    gathered = torch.empty(world * per, unit, device=dev, dtype=torch.float32)
+    dist.all_gather_into_tensor(gathered, packed, group=shard.group)
+    parts = contiguous_partition(shard.n_windows, world)
+    out: List[List[torch.Tensor]] = [[] for _ in sizes]
+    for r, (_, cnt) in enumerate(parts):
+        for w in range(cnt):
+            row = gathered[r * per + w]
+            off = 0
+            for k, (n, (shape, dtype)) in enumerate(zip(sizes, meta0)):
+                out[k].append(row[off:off + n].reshape(shape).to(dtype))
+                off += n
+    return out
+
+
+def gather_clip_outputs(packed: torch.Tensor, group=None) -> torch.Tensor:
+    """cfg 3: every rank contributes the packed head outputs of its clips ([clips_per_rank, unit]); returns
+    [world, clips_per_rank, unit] on every rank (clip i sits at [i % world, i // world])."""
+    world = dist.get_world_size(group)
+    out = torch.empty(world, *packed.shape, device=packed.device, dtype=packed.dtype)
+    dist.all_gather_into_tensor(out.view(world * packed.shape[0], *packed.shape[1:]), packed.contiguous(), group=group)
+    return out

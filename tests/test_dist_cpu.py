@@ -40,3 +40,41 @@ def test_two_rank_shard_and_gather(tmp_path):
     for c in range(clips):
         r, slot = c % world, c // world
         assert torch.equal(gathered[r, slot], _clip_result(c)), f"clip {c} changed under sharding"
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# cfg 4: windows of one long video sharded in contiguous blocks, all per-window outputs in ONE all-gather
+# (l4p_b200.parallel.gather_window_outputs, the function the model calls under enable_window_sharding()).
+# ---------------------------------------------------------------------------------------------------------------
+def _window_result(w: int):
+    g = torch.Generator().manual_seed(2000 + w)
+    return torch.rand(1, 1, 4, 6, 5, generator=g), torch.rand(1, 6, 4, 3, 3, generator=g).double()
+
+
+def _window_worker(rank, world, port, n_windows, out_dir):
+    from l4p_b200.parallel import WindowShard, contiguous_partition, gather_window_outputs
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    shard = WindowShard.for_rank(n_windows)
+    assert (shard.start, shard.count) == contiguous_partition(n_windows, world)[rank]
+    mine = [_window_result(w) for w in range(shard.start, shard.start + shard.count)]
+    depth, rays = gather_window_outputs([[m[0] for m in mine], [m[1] for m in mine]], shard)
+    torch.save((depth, rays), os.path.join(out_dir, f"gathered_{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_window_shard(tmp_path):
+    from l4p_b200.parallel import contiguous_partition, round_robin_partition
+    assert contiguous_partition(5, 2) == [(0, 3), (3, 2)]
+    assert contiguous_partition(3, 4) == [(0, 1), (1, 1), (2, 1), (3, 0)]
+    assert round_robin_partition(5, 2) == [[0, 2, 4], [1, 3]]
+    world, n_windows = 2, 5   # ragged: 3 + 2 windows
+    mp.spawn(_window_worker, args=(world, _free_port(), n_windows, str(tmp_path)), nprocs=world, join=True)
+    for rank in range(world):   # every rank ends up with the outputs of ALL windows, in window order, dtype preserved
+        depth, rays = torch.load(tmp_path / f"gathered_{rank}.pt")
+        assert len(depth) == n_windows and len(rays) == n_windows
+        for w in range(n_windows):
+            d, r = _window_result(w)
+            assert torch.equal(depth[w], d) and depth[w].dtype == torch.float32
+            assert torch.allclose(rays[w], r.float().double()) and rays[w].dtype == torch.float64
