@@ -64,63 +64,63 @@ L4P_DEVICE Axis axis_coord(int o, int in, int out, int align) {
   return a;
 }
 
+// grid (ceil(Wo * C/8 / 256), Ho, B * To): the (b, t, h) coordinates and their source planes are block-uniform, a
+// thread's (wo, channel group) comes from one 32-bit division. All eight corner loads are issued unconditionally
+// (zero-weight corners re-read an in-range neighbour) so that they are in flight together: the kernel is HBM-bound
+// (1 read of x through L1/L2 reuse, 1 write of y), not integer-math- or latency-bound.
 template <bool BF16>
-__global__ void upsample_cl_kernel(const uint16_t* __restrict__ x, uint16_t* __restrict__ y,
+__global__ void __launch_bounds__(256)
+upsample_cl_kernel(const uint16_t* __restrict__ x, uint16_t* __restrict__ y,
                                    uint16_t* __restrict__ y_relu, int B, int Ti, int Hi, int Wi, int To, int Ho, int Wo,
                                    int C, int align, long long total) {
-  const int cg = C / 8;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(idx % cg);
-    long long v = idx / cg;
-    const int wo = (int)(v % Wo); v /= Wo;
-    const int ho = (int)(v % Ho); v /= Ho;
-    const int to = (int)(v % To); v /= To;
-    const long long b = v;
-    const Axis at = axis_coord(to, Ti, To, align);
-    const Axis ah = axis_coord(ho, Hi, Ho, align);
-    const Axis aw = axis_coord(wo, Wi, Wo, align);
-    float acc[8];
+  const int cg = C >> 3;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // (wo, g)
+  if (idx >= Wo * cg) return;
+  const int wo = idx / cg, g = idx - wo * cg;
+  const int ho = blockIdx.y;
+  const int b = blockIdx.z / To, to = blockIdx.z - b * To;
+  const Axis at = axis_coord(to, Ti, To, align);
+  const Axis ah = axis_coord(ho, Hi, Ho, align);
+  const Axis aw = axis_coord(wo, Wi, Wo, align);
+  const long long plane_t0 = ((long long)b * Ti + at.i0) * Hi, plane_t1 = ((long long)b * Ti + at.i1) * Hi;
+  const uint16_t* r00 = x + ((plane_t0 + ah.i0) * Wi) * (long long)C + g * 8;
+  const uint16_t* r01 = x + ((plane_t0 + ah.i1) * Wi) * (long long)C + g * 8;
+  const uint16_t* r10 = x + ((plane_t1 + ah.i0) * Wi) * (long long)C + g * 8;
+  const uint16_t* r11 = x + ((plane_t1 + ah.i1) * Wi) * (long long)C + g * 8;
+  const long long o0 = (long long)aw.i0 * C, o1 = (long long)aw.i1 * C;
+  uint4 raw[8];
+  raw[0] = *reinterpret_cast<const uint4*>(r00 + o0); raw[1] = *reinterpret_cast<const uint4*>(r00 + o1);
+  raw[2] = *reinterpret_cast<const uint4*>(r01 + o0); raw[3] = *reinterpret_cast<const uint4*>(r01 + o1);
+  if (at.w1 != 0.f) {  // block-uniform: the DPT x2 upsampling keeps T
+    raw[4] = *reinterpret_cast<const uint4*>(r10 + o0); raw[5] = *reinterpret_cast<const uint4*>(r10 + o1);
+    raw[6] = *reinterpret_cast<const uint4*>(r11 + o0); raw[7] = *reinterpret_cast<const uint4*>(r11 + o1);
+  } else {
+    raw[4] = raw[5] = raw[6] = raw[7] = make_uint4(0, 0, 0, 0);
+  }
+  const float wt[2] = {1.f - at.w1, at.w1}, wh[2] = {1.f - ah.w1, ah.w1}, ww[2] = {1.f - aw.w1, aw.w1};
+  float acc[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
 #pragma unroll
-    for (int ct = 0; ct < 2; ++ct) {
-      const float wt = ct ? at.w1 : 1.f - at.w1;
-      if (wt == 0.f) continue;
-      const int ti = ct ? at.i1 : at.i0;
+  for (int c = 0; c < 8; ++c) {
+    const float wgt = wt[c >> 2] * wh[(c >> 1) & 1] * ww[c & 1];
+    const uint32_t r[4] = {raw[c].x, raw[c].y, raw[c].z, raw[c].w};
 #pragma unroll
-      for (int ch = 0; ch < 2; ++ch) {
-        const float wh = ch ? ah.w1 : 1.f - ah.w1;
-        if (wh == 0.f) continue;
-        const int hi = ch ? ah.i1 : ah.i0;
-#pragma unroll
-        for (int cw = 0; cw < 2; ++cw) {
-          const float ww = cw ? aw.w1 : 1.f - aw.w1;
-          if (ww == 0.f) continue;
-          const int wi = cw ? aw.i1 : aw.i0;
-          const float wgt = wt * wh * ww;
-          const uint4 raw = *reinterpret_cast<const uint4*>(
-              x + ((((b * Ti + ti) * Hi + hi) * (long long)Wi + wi) * C + g * 8));
-          const uint32_t r[4] = {raw.x, raw.y, raw.z, raw.w};
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float2 f = unpack2<BF16>(r[i]);
-            acc[2 * i] = fmaf(wgt, f.x, acc[2 * i]);
-            acc[2 * i + 1] = fmaf(wgt, f.y, acc[2 * i + 1]);
-          }
-        }
-      }
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = unpack2<BF16>(r[i]);
+      acc[2 * i] = fmaf(wgt, f.x, acc[2 * i]);
+      acc[2 * i + 1] = fmaf(wgt, f.y, acc[2 * i + 1]);
     }
-    const long long o = ((((b * To + to) * Ho + ho) * (long long)Wo + wo) * C + g * 8);
-    if (y != nullptr)
-      *reinterpret_cast<uint4*>(y + o) = make_uint4(pack2<BF16>(acc[0], acc[1]), pack2<BF16>(acc[2], acc[3]),
-                                                    pack2<BF16>(acc[4], acc[5]), pack2<BF16>(acc[6], acc[7]));
-    if (y_relu != nullptr) {
+  }
+  const long long o = ((((long long)b * To + to) * Ho + ho) * (long long)Wo + wo) * C + g * 8;
+  if (y != nullptr)
+    *reinterpret_cast<uint4*>(y + o) = make_uint4(pack2<BF16>(acc[0], acc[1]), pack2<BF16>(acc[2], acc[3]),
+                                                  pack2<BF16>(acc[4], acc[5]), pack2<BF16>(acc[6], acc[7]));
+  if (y_relu != nullptr) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] = fmaxf(acc[i], 0.f);
-      *reinterpret_cast<uint4*>(y_relu + o) = make_uint4(pack2<BF16>(acc[0], acc[1]), pack2<BF16>(acc[2], acc[3]),
-                                                         pack2<BF16>(acc[4], acc[5]), pack2<BF16>(acc[6], acc[7]));
-    }
+    for (int i = 0; i < 8; ++i) acc[i] = fmaxf(acc[i], 0.f);
+    *reinterpret_cast<uint4*>(y_relu + o) = make_uint4(pack2<BF16>(acc[0], acc[1]), pack2<BF16>(acc[2], acc[3]),
+                                                       pack2<BF16>(acc[4], acc[5]), pack2<BF16>(acc[6], acc[7]));
   }
 }
 
@@ -196,7 +196,9 @@ extern "C" int l4p_upsample3d(const void* x16, void* y16, void* y16_relu, int B,
   L4P_REQUIRE(B > 0 && Ti > 0 && Hi > 0 && Wi > 0 && To > 0 && Ho > 0 && Wo > 0 && C > 0 && C % 8 == 0, L4P_ERR_SHAPE,
               "l4p_upsample3d: bad shape (C=%d must be a multiple of 8)", C);
   const long long total = (long long)B * To * Ho * Wo * (C / 8);
-  const unsigned grid = grid_for(total, 256);
+  L4P_REQUIRE((long long)Wo * (C / 8) < (1ll << 31) && Ho <= 65535 && (long long)B * To <= 65535, L4P_ERR_SHAPE,
+              "l4p_upsample3d: grid too large");
+  const dim3 grid((unsigned)(((long long)Wo * (C / 8) + 255) / 256), (unsigned)Ho, (unsigned)(B * To));
   if (bf16)
     upsample_cl_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>((const uint16_t*)x16, (uint16_t*)y16,
                                                                        (uint16_t*)y16_relu, B, Ti, Hi, Wi, To, Ho, Wo, C,

@@ -9,6 +9,7 @@ const GemmKernelSet* gemm_instances_b(int* n) {
       L4P_GEMM_KERNEL_SET(epi_make(L4P_STORE_ROWMAJOR, L4P_ACT_RELU, EPI_OUT16)),
       L4P_GEMM_KERNEL_SET(epi_make(L4P_STORE_ROWMAJOR, L4P_ACT_NONE, EPI_RES32 | EPI_OUT16)),
       L4P_GEMM_KERNEL_SET(epi_make(L4P_STORE_ROWMAJOR, L4P_ACT_NONE, EPI_OUT32)),
+      L4P_GEMM_KERNEL_SET(epi_make(L4P_STORE_ROWMAJOR, L4P_ACT_NONE, EPI_RES16 | EPI_OUT32)),
   };
   *n = (int)(sizeof(sets) / sizeof(sets[0]));
   return sets;
