@@ -259,9 +259,12 @@ token_attention_fast_kernel(const float* __restrict__ q, const uint16_t* __restr
 // run two-wide on the packed f32x2 pipe. blockDim = 32 * H.
 // ------------------------------------------------------------------------------------------------
 template <bool BF16, int D>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 image_attention_kernel(const uint16_t* __restrict__ q16, const float* __restrict__ kf, const float* __restrict__ vf,
                        uint16_t* __restrict__ out16, int Np, int nk, int H, float scale, int rows_per_block) {
+  // Streaming formulation (ncu: the first version held the whole 88-channel q row + output in registers, 211 registers,
+  // one block per SM, latency-bound at 20 % issue utilisation): pass 1 walks the q row in 8-channel chunks and only keeps
+  // the <= 8 score accumulators; pass 2 produces the output chunk by chunk from the probabilities and v. ~50 registers.
   extern __shared__ float sm[];  // k [nk][H*D] (pre-scaled), v [nk][H*D]
   const int ld = H * D;
   const long long row0 = (long long)blockIdx.x * rows_per_block;
@@ -274,41 +277,32 @@ image_attention_kernel(const uint16_t* __restrict__ q16, const float* __restrict
   }
   __syncthreads();
   const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr int NP = D / 2;  // channel pairs
   for (int rr = lane; rr < rows_per_block; rr += 32) {
     const long long row = row0 + rr;
     const uint4* qr = reinterpret_cast<const uint4*>(q16 + row * ld + h * D);
-    uint64_t qv[NP];
+    float sc[kTokMaxQ];
+#pragma unroll
+    for (int j = 0; j < kTokMaxQ; ++j) sc[j] = 0.f;
 #pragma unroll
     for (int c8 = 0; c8 < D / 8; ++c8) {
       const uint4 raw = qr[c8];
-      const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+      const float2 q0 = unpack2<BF16>(raw.x), q1 = unpack2<BF16>(raw.y), q2 = unpack2<BF16>(raw.z), q3 = unpack2<BF16>(raw.w);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float2 f = unpack2<BF16>(w[i]);
-        qv[c8 * 4 + i] = pk2(f.x, f.y);
+      for (int j = 0; j < kTokMaxQ; ++j) {
+        if (j < nk) {
+          const float4* kk = reinterpret_cast<const float4*>(s_k + j * ld + h * D + c8 * 8);
+          const float4 ka = kk[0], kb = kk[1];
+          float a = sc[j];
+          a = fmaf(q0.x, ka.x, a); a = fmaf(q0.y, ka.y, a); a = fmaf(q1.x, ka.z, a); a = fmaf(q1.y, ka.w, a);
+          a = fmaf(q2.x, kb.x, a); a = fmaf(q2.y, kb.y, a); a = fmaf(q3.x, kb.z, a); a = fmaf(q3.y, kb.w, a);
+          sc[j] = a;
+        }
       }
     }
-    float sc[kTokMaxQ];
     float mx = -INFINITY;
 #pragma unroll
-    for (int j = 0; j < kTokMaxQ; ++j) {
-      sc[j] = -INFINITY;
-      if (j < nk) {
-        const float4* kk = reinterpret_cast<const float4*>(s_k + j * ld + h * D);
-        uint64_t a0 = pk2(0.f, 0.f), a1 = pk2(0.f, 0.f);
-#pragma unroll
-        for (int c = 0; c < NP / 2; ++c) {
-          const float4 k4 = kk[c];
-          a0 = fma2(qv[2 * c], pk2(k4.x, k4.y), a0);
-          a1 = fma2(qv[2 * c + 1], pk2(k4.z, k4.w), a1);
-        }
-        float e0, e1;
-        upk2(add2(a0, a1), e0, e1);
-        sc[j] = e0 + e1;
-        mx = fmaxf(mx, sc[j]);
-      }
-    }
+    for (int j = 0; j < kTokMaxQ; ++j)
+      if (j < nk) mx = fmaxf(mx, sc[j]);
     float sum = 0.f;
 #pragma unroll
     for (int j = 0; j < kTokMaxQ; ++j) {
@@ -317,28 +311,24 @@ image_attention_kernel(const uint16_t* __restrict__ q16, const float* __restrict
     }
     const float inv = 1.f / sum;
 #pragma unroll
-    for (int c = 0; c < NP; ++c) qv[c] = pk2(0.f, 0.f);
-#pragma unroll
-    for (int j = 0; j < kTokMaxQ; ++j) {
-      if (j < nk) {
-        const float pj = sc[j] * inv;
-        const uint64_t p2 = pk2(pj, pj);
-        const float4* vv = reinterpret_cast<const float4*>(s_v + j * ld + h * D);
-#pragma unroll
-        for (int c = 0; c < NP / 2; ++c) {
-          const float4 v4 = vv[c];
-          qv[2 * c] = fma2(p2, pk2(v4.x, v4.y), qv[2 * c]);
-          qv[2 * c + 1] = fma2(p2, pk2(v4.z, v4.w), qv[2 * c + 1]);
-        }
-      }
-    }
+    for (int j = 0; j < kTokMaxQ; ++j) sc[j] *= inv;
     uint4* orow = reinterpret_cast<uint4*>(out16 + row * ld + h * D);
 #pragma unroll
     for (int c8 = 0; c8 < D / 8; ++c8) {
-      float f[8];
+      float o[8];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) upk2(qv[c8 * 4 + i], f[2 * i], f[2 * i + 1]);
-      orow[c8] = make_uint4(pack2<BF16>(f[0], f[1]), pack2<BF16>(f[2], f[3]), pack2<BF16>(f[4], f[5]), pack2<BF16>(f[6], f[7]));
+      for (int i = 0; i < 8; ++i) o[i] = 0.f;
+#pragma unroll
+      for (int j = 0; j < kTokMaxQ; ++j) {
+        if (j < nk) {
+          const float4* vv = reinterpret_cast<const float4*>(s_v + j * ld + h * D + c8 * 8);
+          const float4 va = vv[0], vb = vv[1];
+          const float pj = sc[j];
+          o[0] = fmaf(pj, va.x, o[0]); o[1] = fmaf(pj, va.y, o[1]); o[2] = fmaf(pj, va.z, o[2]); o[3] = fmaf(pj, va.w, o[3]);
+          o[4] = fmaf(pj, vb.x, o[4]); o[5] = fmaf(pj, vb.y, o[5]); o[6] = fmaf(pj, vb.z, o[6]); o[7] = fmaf(pj, vb.w, o[7]);
+        }
+      }
+      orow[c8] = make_uint4(pack2<BF16>(o[0], o[1]), pack2<BF16>(o[2], o[3]), pack2<BF16>(o[4], o[5]), pack2<BF16>(o[6], o[7]));
     }
   }
 }
@@ -349,8 +339,8 @@ image_attention_kernel(const uint16_t* __restrict__ q16, const float* __restrict
 // cols multiple of 8, cols <= LPR * 8 * kLn16Iters.
 // ------------------------------------------------------------------------------------------------
 constexpr int kLn16Iters = 8;
-template <bool BF16, int LPR>
-__global__ void __launch_bounds__(256)
+template <bool BF16, int LPR, int ITERS>  // cols <= LPR * 8 * ITERS; fewer iterations = fewer registers = more rows in flight
+__global__ void __launch_bounds__(256, ITERS <= 6 ? 3 : 2)
 layernorm16_kernel(const uint16_t* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                    uint16_t* __restrict__ y, long long rows, int cols, float eps, int gelu) {
   constexpr int RPW = 32 / LPR;  // rows per warp
@@ -360,10 +350,10 @@ layernorm16_kernel(const uint16_t* __restrict__ x, const float* __restrict__ gam
   const bool ok = row < rows;
   const int nch = cols >> 3;
   const uint4* xr = reinterpret_cast<const uint4*>(x + (ok ? row : 0) * cols);
-  float v[kLn16Iters][8];
+  float v[ITERS][8];
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < kLn16Iters; ++i) {
+  for (int i = 0; i < ITERS; ++i) {
     const int j = l + i * LPR;
     if (ok && j < nch) {
       const uint4 raw = xr[j];
@@ -381,7 +371,7 @@ layernorm16_kernel(const uint16_t* __restrict__ x, const float* __restrict__ gam
   const float mean = s / (float)cols;
   float qq = 0.f;
 #pragma unroll
-  for (int i = 0; i < kLn16Iters; ++i) {
+  for (int i = 0; i < ITERS; ++i) {
     const int j = l + i * LPR;
     if (ok && j < nch)
 #pragma unroll
@@ -391,7 +381,7 @@ layernorm16_kernel(const uint16_t* __restrict__ x, const float* __restrict__ gam
   for (int o = LPR / 2; o > 0; o >>= 1) qq += __shfl_xor_sync(0xffffffffu, qq, o);
   const float rstd = rsqrtf(qq / (float)cols + eps);
 #pragma unroll
-  for (int i = 0; i < kLn16Iters; ++i) {
+  for (int i = 0; i < ITERS; ++i) {
     const int j = l + i * LPR;
     if (ok && j < nch) {
       const float4 g0 = reinterpret_cast<const float4*>(gamma)[2 * j], g1 = reinterpret_cast<const float4*>(gamma)[2 * j + 1];
@@ -584,14 +574,18 @@ extern "C" int l4p_layernorm16(const void* x16, const float* gamma, const float*
   cudaStream_t st = (cudaStream_t)stream;
   const uint16_t* x = (const uint16_t*)x16;
   uint16_t* y = (uint16_t*)y16;
-  if (cols <= 8 * 8 * kLn16Iters) {  // short rows: 8 lanes per row, 4 rows per warp
+  if (cols <= 8 * 8 * 6) {  // the mask decoder's 352-channel LayerNorm3d: 6 chunks per lane, 3 blocks per SM
     const unsigned grid = (unsigned)((rows + 31) / 32);
-    if (bf16) layernorm16_kernel<true, 8><<<grid, 256, 0, st>>>(x, gamma, beta, y, rows, cols, eps, gelu);
-    else layernorm16_kernel<false, 8><<<grid, 256, 0, st>>>(x, gamma, beta, y, rows, cols, eps, gelu);
+    if (bf16) layernorm16_kernel<true, 8, 6><<<grid, 256, 0, st>>>(x, gamma, beta, y, rows, cols, eps, gelu);
+    else layernorm16_kernel<false, 8, 6><<<grid, 256, 0, st>>>(x, gamma, beta, y, rows, cols, eps, gelu);
+  } else if (cols <= 8 * 8 * kLn16Iters) {  // short rows: 8 lanes per row, 4 rows per warp
+    const unsigned grid = (unsigned)((rows + 31) / 32);
+    if (bf16) layernorm16_kernel<true, 8, kLn16Iters><<<grid, 256, 0, st>>>(x, gamma, beta, y, rows, cols, eps, gelu);
+    else layernorm16_kernel<false, 8, kLn16Iters><<<grid, 256, 0, st>>>(x, gamma, beta, y, rows, cols, eps, gelu);
   } else {
     const unsigned grid = (unsigned)((rows + 7) / 8);
-    if (bf16) layernorm16_kernel<true, 32><<<grid, 256, 0, st>>>(x, gamma, beta, y, rows, cols, eps, gelu);
-    else layernorm16_kernel<false, 32><<<grid, 256, 0, st>>>(x, gamma, beta, y, rows, cols, eps, gelu);
+    if (bf16) layernorm16_kernel<true, 32, kLn16Iters><<<grid, 256, 0, st>>>(x, gamma, beta, y, rows, cols, eps, gelu);
+    else layernorm16_kernel<false, 32, kLn16Iters><<<grid, 256, 0, st>>>(x, gamma, beta, y, rows, cols, eps, gelu);
   }
   L4P_CHECK_CUDA(cudaGetLastError());
   return L4P_OK;
