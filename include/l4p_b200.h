@@ -117,6 +117,13 @@ int l4p_gemm(const l4p_gemm_desc* desc, void* stream);
  * With l4p_gemm this replaces PatchEmbed.forward (modeling_finetune.py:276-283). */
 int l4p_patchify(const float* rgb, void* out16, int B, int C, int T, int H, int W, int pt, int ph, int pw,
                  int bf16, void* stream);
+
+/* N3 video preprocessing (l4p/data/l4p_dataset_mini.py:543-587, rgb key): temporal mirror padding (:126-190) ->
+ * bilinear spatial resize of the uint8 frames [T0,H0,W0,3] to (Hs,Ws) (F.interpolate 'trilinear' with T unchanged,
+ * align_corners=False, :237-290) -> crop of (To,Hc,Wc) at (t0,i0,j0) (:292-345) -> (x/255 - mean)/std (:576-580),
+ * fused into one gather that writes one clip of rgb_b3thw: out fp32 [3,To,Hc,Wc]. mean3/std3 are HOST pointers. */
+int l4p_preprocess_rgb(const void* frames_u8, float* out, int T0, int H0, int W0, int Hs, int Ws, int t0, int i0, int j0,
+                       int To, int Hc, int Wc, const float* mean3, const float* std3, void* stream);
 /* fp32 -> 16-bit cast, n a multiple of 4. */
 int l4p_cast16(const float* x, void* y16, int64_t n, int bf16, void* stream);
 /* Trilinear resampling of channels-last 16-bit [B,Ti,Hi,Wi,C] -> [B,To,Ho,Wo,C] (y16 and/or its ReLU y16_relu).

@@ -127,6 +127,48 @@ upsample_cl_kernel(const uint16_t* __restrict__ x, uint16_t* __restrict__ y,
 }
 
 // ------------------------------------------------------------------------------------------------
+// N3: video preprocessing fused into one gather (l4p_dataset_mini.py:543-587 for the rgb key):
+//   temporal mirror padding (:126-190: cat[x, flip(x)[1:]] until T >= T_out)  ->  spatial resize to (Hs, Ws)
+//   (F.interpolate trilinear with T unchanged = bilinear, align_corners=False, :237-290)  ->  crop at (t0, i0, j0)
+//   (:292-345)  ->  (x / 255 - mean) / std (:576-580).
+// src: uint8 frames [T0, H0, W0, 3] (decoder layout) ; out: fp32 [3, T_out, Hc, Wc] (one clip of rgb_b3thw).
+// One thread per output pixel (3 channels): the 4 taps x 3 bytes are gathered from L2, the three fp32 planes are
+// written coalesced along x.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+preprocess_rgb_kernel(const uint8_t* __restrict__ src, float* __restrict__ out, int T0, int H0, int W0, int Hs, int Ws,
+                      int t0, int i0, int j0, int To, int Hc, int Wc, float3 mean, float3 istd) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y, t = blockIdx.z;
+  if (x >= Wc) return;
+  // mirror padding: the padded sequence is the period-(2 T0 - 2) reflection of the source
+  int ts = t + t0;
+  if (T0 > 1) {
+    const int period = 2 * T0 - 2;
+    ts %= period;
+    if (ts >= T0) ts = period - ts;
+  } else {
+    ts = 0;
+  }
+  const Axis ay = axis_coord(y + i0, H0, Hs, 0);
+  const Axis ax = axis_coord(x + j0, W0, Ws, 0);
+  const uint8_t* f = src + (long long)ts * H0 * W0 * 3;
+  const uint8_t* p00 = f + ((long long)ay.i0 * W0 + ax.i0) * 3;
+  const uint8_t* p01 = f + ((long long)ay.i0 * W0 + ax.i1) * 3;
+  const uint8_t* p10 = f + ((long long)ay.i1 * W0 + ax.i0) * 3;
+  const uint8_t* p11 = f + ((long long)ay.i1 * W0 + ax.i1) * 3;
+  const float w00 = (1.f - ay.w1) * (1.f - ax.w1), w01 = (1.f - ay.w1) * ax.w1, w10 = ay.w1 * (1.f - ax.w1), w11 = ay.w1 * ax.w1;
+  const long long plane = (long long)To * Hc * Wc;
+  const long long o = ((long long)t * Hc + y) * Wc + x;
+  const float m[3] = {mean.x, mean.y, mean.z}, is[3] = {istd.x, istd.y, istd.z};
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float v = (w00 * (float)p00[c] + w01 * (float)p01[c] + w10 * (float)p10[c] + w11 * (float)p11[c]) * (1.f / 255.f);
+    out[c * plane + o] = (v - m[c]) * is[c];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Strided 3x3x3 gather (pad 1): x [B,T,H,W,C] -> A [B*To*Ho*Wo, 27*C], K ordered (kt,kh,kw,c).
 // Only used for the 1024->1024 stride-2 conv on the 8x16x16 grid (dpt_block.py:265-278): 14 MB.
 // ------------------------------------------------------------------------------------------------
@@ -222,6 +264,22 @@ extern "C" int l4p_im2col3(const void* x16, void* out16, int B, int T, int H, in
   const long long total = (long long)B * To * Ho * Wo * 27 * (C / 8);
   im2col3_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)x16, (uint4*)out16, B, T, H, W, C,
                                                                         sT, sH, sW, To, Ho, Wo, total);
+  L4P_CHECK_CUDA(cudaGetLastError());
+  return L4P_OK;
+}
+
+extern "C" int l4p_preprocess_rgb(const void* frames_u8, float* out, int T0, int H0, int W0, int Hs, int Ws, int t0, int i0,
+                                  int j0, int To, int Hc, int Wc, const float* mean3, const float* std3, void* stream) {
+  L4P_REQUIRE(frames_u8 && out && mean3 && std3, L4P_ERR_ARG, "l4p_preprocess_rgb: null pointer");
+  L4P_REQUIRE(T0 > 0 && H0 > 0 && W0 > 0 && Hs > 0 && Ws > 0 && To > 0 && Hc > 0 && Wc > 0, L4P_ERR_SHAPE,
+              "l4p_preprocess_rgb: empty shape");
+  L4P_REQUIRE(t0 >= 0 && i0 >= 0 && j0 >= 0 && i0 + Hc <= Hs && j0 + Wc <= Ws, L4P_ERR_SHAPE,
+              "l4p_preprocess_rgb: crop (%d,%d)+(%d,%d) outside the resized frame %dx%d", i0, j0, Hc, Wc, Hs, Ws);
+  L4P_REQUIRE(Hc <= 65535 && To <= 65535, L4P_ERR_SHAPE, "l4p_preprocess_rgb: grid too large");
+  const dim3 grid((unsigned)((Wc + 255) / 256), (unsigned)Hc, (unsigned)To);
+  preprocess_rgb_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const uint8_t*)frames_u8, out, T0, H0, W0, Hs, Ws, t0, i0, j0,
+                                                                 To, Hc, Wc, make_float3(mean3[0], mean3[1], mean3[2]),
+                                                                 make_float3(1.f / std3[0], 1.f / std3[1], 1.f / std3[2]));
   L4P_CHECK_CUDA(cudaGetLastError());
   return L4P_OK;
 }

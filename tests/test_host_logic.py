@@ -77,3 +77,25 @@ def test_track_windowed_host_state_machine_matches_oracle_labels():
     assert lab.tolist() == [[2.0, 1.0, 1.0]]
     assert valid_t[0, 0].tolist() == [False] * 4 + [True] * 12   # frames before t=12.5 are never written
     assert valid_t[0, 2].tolist() == [False] * 12 + [True] * 4
+
+
+def test_preprocess_plan_matches_dataset_restatement():
+    """Shapes / crop origin of the fused GPU preprocessing (l4p_b200.data.plan) vs the CPU restatement of the reference's
+    dataset pipeline (oracle/preprocess_oracle.py), including temporal mirror padding and the single-frame case."""
+    import torch
+    from l4p_b200.data import plan
+    from oracle.preprocess_oracle import mirror_and_pad, preprocess
+    x = torch.arange(5.0).view(1, 5, 1, 1)
+    assert mirror_and_pad(x).flatten().tolist() == [0, 1, 2, 3, 4, 3, 2, 1, 0]
+    for (T0, H0, W0, resize, crop) in [(10, 60, 80, (256, 320), None), (1, 50, 70, (240, 300), (16, 224, 224)),
+                                       (40, 224, 224, (224, 224), None), (5, 300, 300, None, (24, 224, 224))]:
+        frames = torch.zeros(T0, H0, W0, 3, dtype=torch.uint8)
+        ref = preprocess(frames, resize, crop)
+        pl = plan(T0, H0, W0, resize, crop)
+        assert tuple(ref.shape) == (1, 3, pl["To"], pl["Hc"], pl["Wc"])
+        assert pl["T_pad"] >= pl["To"] and pl["t0"] == 0
+    try:
+        plan(16, 100, 100, None, (16, 224, 224))
+        assert False, "crop larger than the frame must fail like the reference's assert"
+    except AssertionError:
+        pass
