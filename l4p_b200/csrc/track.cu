@@ -135,11 +135,11 @@ token_attention_kernel(const float* __restrict__ q, const uint16_t* __restrict__
 //   pass 2  half-warps walk the keys, 11 lanes x 16 bytes cover one V row, 48 accumulators per lane
 // ------------------------------------------------------------------------------------------------
 template <bool BF16, int D, int NQ>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 token_attention_fast_kernel(const float* __restrict__ q, const uint16_t* __restrict__ k16, const uint16_t* __restrict__ v16,
                             float* __restrict__ out, int Nk, int ldq, int ldkv, long long kv_group_rows, float scale) {
   constexpr int C8 = D / 8;       // 16-byte chunks per row
-  constexpr int KPT = 8;          // keys per thread in pass 1 (Nk <= 256 * KPT)
+  constexpr int KPT = 4;          // keys per thread per pass-1 sweep (ncu: KPT = 8 needed 184 registers -> 1 block / SM, 12 % occupancy)
   extern __shared__ float sm[];
   float* s_scores = sm;                 // [NQ][Nk]
   float* s_q = s_scores + NQ * Nk;      // [NQ][D]
@@ -152,7 +152,7 @@ token_attention_fast_kernel(const float* __restrict__ q, const uint16_t* __restr
   const uint16_t* vg = v16 + (long long)g * kv_group_rows * ldkv + h * D;
   for (int i = tid; i < NQ * D; i += 256) s_q[i] = qg[(i / D) * ldq + (i % D)] * scale;
   __syncthreads();
-  {
+  for (int kbase = 0; kbase < Nk; kbase += 256 * KPT) {
     float acc[KPT][NQ];
 #pragma unroll
     for (int kk = 0; kk < KPT; ++kk)
@@ -171,7 +171,7 @@ token_attention_fast_kernel(const float* __restrict__ q, const uint16_t* __restr
       uint4 raw[KPT];
 #pragma unroll
       for (int kk = 0; kk < KPT; ++kk) {
-        const int key = tid + kk * 256;
+        const int key = kbase + tid + kk * 256;
         raw[kk] = key < Nk ? *reinterpret_cast<const uint4*>(kg + (long long)key * ldkv + c8 * 8) : make_uint4(0, 0, 0, 0);
       }
 #pragma unroll
@@ -191,7 +191,7 @@ token_attention_fast_kernel(const float* __restrict__ q, const uint16_t* __restr
     }
 #pragma unroll
     for (int kk = 0; kk < KPT; ++kk) {
-      const int key = tid + kk * 256;
+      const int key = kbase + tid + kk * 256;
       if (key < Nk)
 #pragma unroll
         for (int j = 0; j < NQ; ++j) s_scores[j * Nk + key] = acc[kk][j];
