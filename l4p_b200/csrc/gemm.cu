@@ -33,13 +33,35 @@ static GemmKernelFn select_kernel(const l4p_gemm_desc* d, bool pair) {
   return fn;
 }
 
-static int pick_block_n(long long N) {
-  // prefer the widest tile that divides N (UMMA N <= 256, multiple of 16)
+// N-tile width from a measured cost model (tools/ubench/umma_bench.cu, tools/blockn_sweep.py): one UMMA of width bn costs
+// ~43 + bn/2 cycles (the 128 x 16 A operand is fetched before B streams), a tile costs that per k-step, and the kernel
+// needs ceil(tiles / slots) rounds of tiles (slots = CTA pairs when the problem is large enough for the 2-CTA kernel,
+// else SMs). A ragged last N tile (TMA zero fill + column masking) is fine: 704 = 3 x 240 beats 4 x 176 by 8 %,
+// 4224 = 17 x 256 beats 22 x 192 by 18 %.
+static int pick_block_n(long long N, long long tiles_m) {
+  if (N <= 128) return (int)((N + 15) / 16 * 16);
+  const int sms = host_num_sms();
   const int cands[] = {256, 240, 224, 208, 192, 176, 160, 144, 128};
+  int dflt = 256;  // the widest tile that divides N ...
   for (int c : cands)
-    if (N % c == 0) return c;
-  if (N <= 256) return (int)((N + 15) / 16 * 16);
-  return 256;  // ragged tail handled by TMA zero fill + column masking
+    if (N % c == 0) { dflt = c; break; }
+  auto cost = [&](int c) {
+    const long long tn = (N + c - 1) / c;
+    const long long pair_tiles = ((tiles_m + 1) / 2) * tn;
+    const bool pair = pair_tiles >= sms / 2 && tiles_m >= 2;   // same rule as the kernel choice below
+    const long long rounds = pair ? (pair_tiles + sms / 2 - 1) / (sms / 2) : (tiles_m * tn + sms - 1) / sms;
+    return (double)rounds * (43.0 + 0.5 * c);
+  };
+  // ... unless a WIDER (ragged) tiling is predicted >= 3 % cheaper. Narrower alternatives are not considered: 9 x 160 for
+  // N = 1408 is predicted 6 % faster than 8 x 176 and measured 30 % slower.
+  int best = dflt;
+  double best_cost = cost(dflt) * 0.97;
+  for (int c : cands) {
+    if (c <= dflt) break;
+    const double k = cost(c);
+    if (k < best_cost) { best_cost = k; best = c; }
+  }
+  return best;
 }
 
 }  // namespace l4p
@@ -59,13 +81,15 @@ extern "C" int l4p_gemm(const l4p_gemm_desc* d, void* stream_) {
   memset(&p, 0, sizeof(p));
   p.M = (int)d->M;
   p.N = (int)d->N;
-  p.block_n = d->block_n > 0 ? d->block_n : pick_block_n(d->N);
+  const long long tm_all = d->a_mode == L4P_A_CONV3D
+                               ? (long long)d->cB * ((d->cT + d->bT - 1) / d->bT) * ((d->cH + d->bH - 1) / d->bH) * ((d->cW + d->bW - 1) / d->bW)
+                               : (d->M + kBlockM - 1) / kBlockM;
+  p.block_n = d->block_n > 0 ? d->block_n : pick_block_n(d->N, tm_all);
+  if (d->block_n <= 0 && d->store_mode == L4P_STORE_HYPER) p.block_n = d->ctCout;  // one tap per tile
   // split-K decision (needs the tile and k-block counts up front)
   int split_k = 1;
   {
-    const long long tm = d->a_mode == L4P_A_CONV3D
-                             ? (long long)d->cB * ((d->cT + d->bT - 1) / d->bT) * ((d->cH + d->bH - 1) / d->bH) * ((d->cW + d->bW - 1) / d->bW)
-                             : (d->M + kBlockM - 1) / kBlockM;
+    const long long tm = tm_all;
     const long long tiles = tm * ((d->N + p.block_n - 1) / p.block_n);
     const long long nkb = d->a_mode == L4P_A_CONV3D ? (long long)d->kT * d->kH * d->kW * (d->cCin / kBlockK) : (d->K + kBlockK - 1) / kBlockK;
     const bool can = d->store_mode == L4P_STORE_ROWMAJOR && d->splitk_ws != nullptr && d->splitk_ws_bytes >= d->M * d->N * 4 &&
