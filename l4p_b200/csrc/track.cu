@@ -258,34 +258,44 @@ token_attention_fast_kernel(const float* __restrict__ q, const uint16_t* __restr
 // that every shared-memory read of k / v is a warp-wide broadcast (one wavefront) and the 2 * nk * d FMAs per thread
 // run two-wide on the packed f32x2 pipe. blockDim = 32 * H.
 // ------------------------------------------------------------------------------------------------
+// Rows are staged through shared memory: a block of 32 * H threads loads 32 rows (32 x H*D 16-bit values) with fully
+// coalesced 16-byte accesses, every thread then works on its own (row, head) slice out of shared memory (row pitch padded by
+// 16 bytes: conflict-free 128-bit reads for lane = row), overwrites the slice with its output, and the tile is written back
+// coalesced. ncu on the direct version (lane = row reading global memory): every 16-byte access touched 32 different lines,
+// 1.5 TB/s at ideal DRAM traffic.
 template <bool BF16, int D>
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(256, 2)
 image_attention_kernel(const uint16_t* __restrict__ q16, const float* __restrict__ kf, const float* __restrict__ vf,
                        uint16_t* __restrict__ out16, int Np, int nk, int H, float scale, int rows_per_block) {
-  // Streaming formulation (ncu: the first version held the whole 88-channel q row + output in registers, 211 registers,
-  // one block per SM, latency-bound at 20 % issue utilisation): pass 1 walks the q row in 8-channel chunks and only keeps
-  // the <= 8 score accumulators; pass 2 produces the output chunk by chunk from the probabilities and v. ~50 registers.
-  extern __shared__ float sm[];  // k [nk][H*D] (pre-scaled), v [nk][H*D]
+  extern __shared__ float sm[];  // k [nk][H*D] (pre-scaled), v [nk][H*D], then the 16-bit row tile [32][H*D + 8]
   const int ld = H * D;
+  const int pitch = ld + 8;      // 16-bit elements
   const long long row0 = (long long)blockIdx.x * rows_per_block;
   const int g = (int)(row0 / Np);
   float* s_k = sm;
   float* s_v = sm + nk * ld;
+  uint16_t* s_q = reinterpret_cast<uint16_t*>(sm + 2 * nk * ld);
   for (int i = threadIdx.x; i < nk * ld; i += blockDim.x) {
     s_k[i] = kf[(long long)g * nk * ld + i] * scale;
     s_v[i] = vf[(long long)g * nk * ld + i];
   }
-  __syncthreads();
   const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int rr = lane; rr < rows_per_block; rr += 32) {
-    const long long row = row0 + rr;
-    const uint4* qr = reinterpret_cast<const uint4*>(q16 + row * ld + h * D);
+  const int vec_per_row = ld / 8;  // 16-byte vectors per row
+  for (int r0 = 0; r0 < rows_per_block; r0 += 32) {
+    __syncthreads();  // k/v ready (first tile); previous tile fully written back
+    for (int i = threadIdx.x; i < 32 * vec_per_row; i += blockDim.x) {
+      const int rr = i / vec_per_row, cv = i - rr * vec_per_row;
+      *reinterpret_cast<uint4*>(s_q + rr * pitch + cv * 8) =
+          *reinterpret_cast<const uint4*>(q16 + (row0 + r0 + rr) * ld + cv * 8);
+    }
+    __syncthreads();
+    uint16_t* mine = s_q + lane * pitch + h * D;
     float sc[kTokMaxQ];
 #pragma unroll
     for (int j = 0; j < kTokMaxQ; ++j) sc[j] = 0.f;
 #pragma unroll
     for (int c8 = 0; c8 < D / 8; ++c8) {
-      const uint4 raw = qr[c8];
+      const uint4 raw = *reinterpret_cast<const uint4*>(mine + c8 * 8);
       const float2 q0 = unpack2<BF16>(raw.x), q1 = unpack2<BF16>(raw.y), q2 = unpack2<BF16>(raw.z), q3 = unpack2<BF16>(raw.w);
 #pragma unroll
       for (int j = 0; j < kTokMaxQ; ++j) {
@@ -312,7 +322,6 @@ image_attention_kernel(const uint16_t* __restrict__ q16, const float* __restrict
     const float inv = 1.f / sum;
 #pragma unroll
     for (int j = 0; j < kTokMaxQ; ++j) sc[j] *= inv;
-    uint4* orow = reinterpret_cast<uint4*>(out16 + row * ld + h * D);
 #pragma unroll
     for (int c8 = 0; c8 < D / 8; ++c8) {
       float o[8];
@@ -328,7 +337,14 @@ image_attention_kernel(const uint16_t* __restrict__ q16, const float* __restrict
           o[4] = fmaf(pj, vb.x, o[4]); o[5] = fmaf(pj, vb.y, o[5]); o[6] = fmaf(pj, vb.z, o[6]); o[7] = fmaf(pj, vb.w, o[7]);
         }
       }
-      orow[c8] = make_uint4(pack2<BF16>(o[0], o[1]), pack2<BF16>(o[2], o[3]), pack2<BF16>(o[4], o[5]), pack2<BF16>(o[6], o[7]));
+      // the slice is private to this thread and fully consumed by the score pass: overwrite it with the output
+      *reinterpret_cast<uint4*>(mine + c8 * 8) =
+          make_uint4(pack2<BF16>(o[0], o[1]), pack2<BF16>(o[2], o[3]), pack2<BF16>(o[4], o[5]), pack2<BF16>(o[6], o[7]));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 32 * vec_per_row; i += blockDim.x) {
+      const int rr = i / vec_per_row, cv = i - rr * vec_per_row;
+      *reinterpret_cast<uint4*>(out16 + (row0 + r0 + rr) * ld + cv * 8) = *reinterpret_cast<const uint4*>(s_q + rr * pitch + cv * 8);
     }
   }
 }
@@ -556,7 +572,8 @@ extern "C" int l4p_image_attention(const void* q16, const float* k, const float*
   L4P_REQUIRE(G > 0 && nk > 0 && nk <= kTokMaxQ && H > 0 && H <= 8, L4P_ERR_SHAPE, "l4p_image_attention: nk=%d H=%d (<= 8)", nk, H);
   const int rows_per_block = 128;
   L4P_REQUIRE(Np % rows_per_block == 0, L4P_ERR_SHAPE, "l4p_image_attention: Np=%d must be a multiple of %d", Np, rows_per_block);
-  const size_t smem = sizeof(float) * 2 * (size_t)nk * H * d;
+  L4P_REQUIRE(32 * H <= 256 && (H * d) % 8 == 0, L4P_ERR_SHAPE, "l4p_image_attention: H=%d", H);
+  const size_t smem = sizeof(float) * 2 * (size_t)nk * H * d + 32 * (size_t)(H * d + 8) * 2;
   const unsigned grid = (unsigned)(((long long)G * Np) / rows_per_block);
   typedef void (*KFn)(const uint16_t*, const float*, const float*, uint16_t*, int, int, int, float, int);
   KFn kfn = bf16 ? image_attention_kernel<true, 88> : image_attention_kernel<false, 88>;
