@@ -48,7 +48,7 @@ static int pick_block_n(long long N, long long tiles_m) {
   auto cost = [&](int c) {
     const long long tn = (N + c - 1) / c;
     const long long pair_tiles = ((tiles_m + 1) / 2) * tn;
-    const bool pair = pair_tiles >= sms / 2 && tiles_m >= 2;   // same rule as the kernel choice below
+    const bool pair = pair_tiles * 5 >= (sms / 2) * 4 && tiles_m >= 2;   // same rule as the kernel choice below
     const long long rounds = pair ? (pair_tiles + sms / 2 - 1) / (sms / 2) : (tiles_m * tn + sms - 1) / sms;
     return (double)rounds * (43.0 + 0.5 * c);
   };
@@ -270,7 +270,9 @@ extern "C" int l4p_gemm(const l4p_gemm_desc* d, void* stream_) {
   const int pair_tiles = ((p.tiles_m + 1) / 2) * p.tiles_n;
   const int pairs = host_num_sms() / 2;
   int use_pair = d->cta_pair;  // 0 = auto, 1 = force, -1 = never
-  if (use_pair == 0) use_pair = (pair_tiles >= pairs && p.block_n >= 64 && p.tiles_m >= 2) ? 1 : -1;
+  // the pair kernel halves the B traffic per SM: worth it even when it leaves a few pairs idle (M=2048, N=1408: 64 pair
+  // tiles on 74 pairs beat 128 single tiles on 148 SMs by 6 % at K=6144, equal at K=1408)
+  if (use_pair == 0) use_pair = (pair_tiles * 5 >= pairs * 4 && p.block_n >= 64 && p.tiles_m >= 2) ? 1 : -1;
   if (use_pair == 1) {
     L4P_REQUIRE(p.block_n % 32 == 0 || p.block_n % 16 == 0, L4P_ERR_SHAPE, "l4p_gemm(pair): block_n=%d", p.block_n);
     // B tensor map with the half-tile box
