@@ -111,6 +111,11 @@ typedef struct l4p_gemm_desc {
  * and the SAM projections (task_heads/sam/transformer.py:223-245). */
 int l4p_gemm(const l4p_gemm_desc* desc, void* stream);
 
+/* Host-only dry run of l4p_gemm: validates the descriptor and reports the launch decisions without touching the device
+ * (pointers in `desc` are not dereferenced). out6 = {block_n, split_k, cta_pair (0/1), smem ring stages, grid CTAs,
+ * threads per CTA}. Usable without a GPU (the SM count then defaults to 148). */
+int l4p_gemm_plan(const l4p_gemm_desc* desc, int* out6);
+
 /* ---- K1/K7/K9 helpers (HBM-bound) ------------------------------------------------------------- */
 /* Tubelet gather for the patch embedding: rgb fp32 [B,C,T,H,W] -> 16-bit [B*(T/pt)*(H/ph)*(W/pw), C*pt*ph*pw],
  * K ordered (c,dt,dh,dw) = flattened Conv3d weight; token order t'*nh*nw + h'*nw + w'.

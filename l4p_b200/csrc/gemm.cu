@@ -4,6 +4,11 @@
 
 namespace l4p {
 
+// l4p_gemm_plan(): the same host logic as l4p_gemm with the tensor-map encoding and the launch replaced by a report of the
+// decisions taken (N tile, split-K, CTA pairing, stages, grid) - testable without a GPU
+struct GemmPlanOut { int block_n, split_k, cta_pair, stages, grid, threads; };
+static thread_local GemmPlanOut* t_plan = nullptr;
+
 // compiled epilogue instances live in gemm_inst_{a,b,c,d}.cu (split so that they build in parallel)
 static GemmKernelFn find_kernel(int epi, bool bf16, bool pair) {
   typedef const GemmKernelSet* (*Getter)(int*);
@@ -129,7 +134,7 @@ extern "C" int l4p_gemm(const l4p_gemm_desc* d, void* stream_) {
     const uint64_t dims[2] = {(uint64_t)d->K, (uint64_t)d->M};
     const uint64_t strides[1] = {(uint64_t)d->lda * 2};
     const uint32_t box[2] = {kBlockK, kBlockM};
-    rc = host_make_tmap_16b(&tmA, d->a, 2, dims, strides, box, 128);
+    rc = t_plan ? L4P_OK : host_make_tmap_16b(&tmA, d->a, 2, dims, strides, box, 128);
     if (rc != L4P_OK) return rc;
   } else if (d->a_mode == L4P_A_CONV3D) {
     L4P_REQUIRE(d->cCin % kBlockK == 0, L4P_ERR_SHAPE, "l4p_gemm(conv): Cin=%d must be a multiple of 64", d->cCin);
@@ -151,7 +156,7 @@ extern "C" int l4p_gemm(const l4p_gemm_desc* d, void* stream_) {
     const uint64_t dims[5] = {C, (uint64_t)d->cW, (uint64_t)d->cH, (uint64_t)d->cT, (uint64_t)d->cB};
     const uint64_t strides[4] = {C * 2, C * 2 * d->cW, C * 2 * d->cW * d->cH, C * 2 * d->cW * d->cH * d->cT};
     const uint32_t box[5] = {kBlockK, (uint32_t)d->bW, (uint32_t)d->bH, (uint32_t)d->bT, 1};
-    rc = host_make_tmap_16b(&tmA, d->a, 5, dims, strides, box, 128);
+    rc = t_plan ? L4P_OK : host_make_tmap_16b(&tmA, d->a, 5, dims, strides, box, 128);
     if (rc != L4P_OK) return rc;
   } else {
     return host_set_error(L4P_ERR_ARG, "l4p_gemm: a_mode=%d", d->a_mode);
@@ -160,7 +165,7 @@ extern "C" int l4p_gemm(const l4p_gemm_desc* d, void* stream_) {
     const uint64_t dims[2] = {(uint64_t)d->K, (uint64_t)d->N};
     const uint64_t strides[1] = {(uint64_t)d->ldw * 2};
     const uint32_t box[2] = {kBlockK, (uint32_t)p.block_n};
-    rc = host_make_tmap_16b(&tmB, d->w, 2, dims, strides, box, 128);
+    rc = t_plan ? L4P_OK : host_make_tmap_16b(&tmB, d->w, 2, dims, strides, box, 128);
     if (rc != L4P_OK) return rc;
   }
 
@@ -257,6 +262,7 @@ extern "C" int l4p_gemm(const l4p_gemm_desc* d, void* stream_) {
     // K slices accumulate into the fp32 workspace; the finalize kernel applies the epilogue and re-zeroes it
     GemmKernelFn ks = find_kernel(epi_make(kStoreSplitK, L4P_ACT_NONE, 0), d->bf16 != 0, false);
     L4P_REQUIRE(ks != nullptr, L4P_ERR_ARG, "l4p_gemm: split-K kernel instance missing");
+    if (t_plan) { *t_plan = GemmPlanOut{p.block_n, split_k, 0, p.stages, grid, threads}; return L4P_OK; }
     L4P_CHECK_CUDA(cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kRingBudget + 1024 + epi_bytes)));
     L4P_CHECK_CUDA(launch_pdl(ks, dim3(grid), dim3(threads), smem, stream, tmA, tmB, p));
     const long long n4 = (long long)p.M * (p.N / 4);
@@ -279,7 +285,7 @@ extern "C" int l4p_gemm(const l4p_gemm_desc* d, void* stream_) {
     const uint64_t dims[2] = {(uint64_t)d->K, (uint64_t)d->N};
     const uint64_t strides[1] = {(uint64_t)d->ldw * 2};
     const uint32_t box[2] = {kBlockK, (uint32_t)(p.block_n / 2)};
-    rc = host_make_tmap_16b(&tmB, d->w, 2, dims, strides, box, 128);
+    rc = t_plan ? L4P_OK : host_make_tmap_16b(&tmB, d->w, 2, dims, strides, box, 128);
     if (rc != L4P_OK) return rc;
     const uint32_t sb2 = kABytes + (uint32_t)(p.block_n / 2) * 128u;
     int st2 = (int)(kRingBudget / sb2);
@@ -291,6 +297,7 @@ extern "C" int l4p_gemm(const l4p_gemm_desc* d, void* stream_) {
     int g2 = pairs < pair_tiles ? pairs : pair_tiles;
     GemmKernelFn k2 = select_kernel(d, true);
     L4P_REQUIRE(k2 != nullptr, L4P_ERR_ARG, "l4p_gemm: no kernel instance for store_mode=%d", d->store_mode);
+    if (t_plan) { *t_plan = GemmPlanOut{p.block_n, 1, 1, p.stages, 2 * g2, threads}; return L4P_OK; }
     L4P_CHECK_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kRingBudget + 1024 + epi_bytes)));
     L4P_CHECK_CUDA(launch_pdl(k2, dim3(2 * g2), dim3(threads), smem2, stream, tmA, tmB, p));
     return L4P_OK;
@@ -298,7 +305,19 @@ extern "C" int l4p_gemm(const l4p_gemm_desc* d, void* stream_) {
 
   GemmKernelFn kfn = select_kernel(d, false);
   L4P_REQUIRE(kfn != nullptr, L4P_ERR_ARG, "l4p_gemm: no kernel instance for store_mode=%d", d->store_mode);
+  if (t_plan) { *t_plan = GemmPlanOut{p.block_n, 1, 0, p.stages, grid, threads}; return L4P_OK; }
   L4P_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kRingBudget + 1024 + epi_bytes)));
   L4P_CHECK_CUDA(launch_pdl(kfn, dim3(grid), dim3(threads), smem, stream, tmA, tmB, p));
+  return L4P_OK;
+}
+
+extern "C" int l4p_gemm_plan(const l4p_gemm_desc* d, int* out6) {
+  L4P_REQUIRE(d != nullptr && out6 != nullptr, L4P_ERR_ARG, "l4p_gemm_plan: null argument");
+  GemmPlanOut po = {0, 0, 0, 0, 0, 0};
+  t_plan = &po;
+  const int rc = l4p_gemm(d, nullptr);
+  t_plan = nullptr;
+  if (rc != L4P_OK) return rc;
+  out6[0] = po.block_n; out6[1] = po.split_k; out6[2] = po.cta_pair; out6[3] = po.stages; out6[4] = po.grid; out6[5] = po.threads;
   return L4P_OK;
 }

@@ -58,6 +58,7 @@ _SIGNATURES = {
     "l4p_layernorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
                                 C.c_float, C.c_int, C.c_void_p]),
     "l4p_gemm": (C.c_int, [C.POINTER(GemmDesc), C.c_void_p]),
+    "l4p_gemm_plan": (C.c_int, [C.POINTER(GemmDesc), C.POINTER(C.c_int)]),
     "l4p_patchify": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 9 + [C.c_void_p]),
     "l4p_preprocess_rgb": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 11 + [C.c_void_p, C.c_void_p, C.c_void_p]),
     "l4p_cast16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),

@@ -99,3 +99,61 @@ def test_preprocess_plan_matches_dataset_restatement():
         assert False, "crop larger than the frame must fail like the reference's assert"
     except AssertionError:
         pass
+
+
+def _plan(**kw):
+    """l4p_gemm_plan: the host-side launch decisions of l4p_gemm (no device access, fake non-null pointers)."""
+    import ctypes as C
+    from l4p_b200 import lib
+    L = lib.load()
+    d = lib.GemmDesc()
+    fake = 0x10000
+    d.a, d.w = fake, fake
+    d.bf16, d.a_mode, d.store_mode = 0, lib.A_MATRIX, lib.STORE_ROWMAJOR
+    for k, v in kw.items():
+        setattr(d, k, v)
+    if d.lda == 0:
+        d.lda = d.K
+    if d.ldw == 0:
+        d.ldw = d.K
+    if d.store_mode == lib.STORE_ROWMAJOR:
+        if not (d.out_f32 or d.out_16 or d.out_16_relu):
+            d.out_16 = fake
+        d.ld_out = d.ld_out or d.N
+        d.ld_res = d.ld_res or d.N
+    out = (C.c_int * 6)()
+    rc = L.l4p_gemm_plan(C.byref(d), out)
+    assert rc == 0, L.l4p_last_error().decode()
+    return dict(block_n=out[0], split_k=out[1], pair=out[2], stages=out[3], grid=out[4], threads=out[5])
+
+
+def test_gemm_plan_tile_selection():
+    """Host logic of the GEMM launcher: N-tile width from the UMMA cost model, CTA pairing,
+    split-K for few-tile / long-K problems, grid sizing for 148 SMs."""
+    from l4p_b200 import lib
+    # encoder at one clip (M = 2048)
+    fc1 = _plan(M=2048, N=6144, K=1408)
+    assert fc1["block_n"] == 256 and fc1["pair"] == 1 and fc1["grid"] == 148 and fc1["threads"] == 384
+    proj = _plan(M=2048, N=1408, K=1408, out_f32=0x10000, res_f32=0x10000)
+    assert proj["block_n"] == 176 and proj["pair"] == 1 and proj["grid"] == 128     # 64 pair tiles >= 80 % of 74 pairs
+    qkv = _plan(M=2048, N=4224, K=1408, store_mode=lib.STORE_QKV, q=0x10000, k=0x10000, vt=0x10000, heads=16, head_dim=88,
+                head_dim_pad=96, tokens=2048)
+    assert qkv["block_n"] in (240, 256) and qkv["pair"] == 1                        # ragged wide tiles (2 rounds), not 22 x 192 (3 rounds)
+    # track head projections over 128 queries x 2048 video tokens: 3 x 240 instead of 4 x 176
+    kproj = _plan(M=262144, N=704, K=1408)
+    assert kproj["block_n"] == 240 and kproj["pair"] == 1 and kproj["split_k"] == 1
+    # low-resolution DPT level: 256 output voxels, K = 27 * 1024 -> split-K when (and only when) a workspace is given
+    conv = dict(M=256, N=256, K=27 * 1024, a_mode=lib.A_CONV3D, cB=1, cT=4, cH=8, cW=8, cCin=1024, kT=3, kH=3, kW=3, bT=2, bH=8, bW=8,
+                lda=1024, ldw=27 * 1024)
+    no_ws = _plan(**conv)
+    assert no_ws["split_k"] == 1 and no_ws["pair"] == 0
+    ws = _plan(**conv, splitk_ws=0x10000, splitk_ws_bytes=256 * 256 * 4)
+    assert ws["split_k"] > 8 and ws["block_n"] == 256 and ws["grid"] <= 148 and ws["grid"] == 2 * ws["split_k"]
+    # fused-dot modes run four epilogue warpgroups + the helper warp
+    hyper = _plan(M=16384 * 4, N=704, K=352, store_mode=lib.STORE_HYPER, cB=4, cT=16, cH=32, cW=32, sT=1, sH=2, sW=2, ctCout=176,
+                  out_f32=0x10000, w2=0x10000, c2=3, rows_per_group=16384)
+    assert hyper["block_n"] == 176 and hyper["threads"] == 640
+    # invalid descriptors are rejected with an error code, not a crash
+    import ctypes as C
+    d = lib.GemmDesc(); d.a = d.w = 0x10000; d.M, d.N, d.K = 128, 24, 64; d.lda = d.ldw = 64
+    assert lib.load().l4p_gemm_plan(C.byref(d), (C.c_int * 6)()) != 0
