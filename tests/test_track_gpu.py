@@ -96,3 +96,56 @@ def test_track_two_windows_memory_vs_oracle():
     assert (out["track_2d_traj_est_bn2t"].cpu() - ref["track_2d_traj_est_bn2t"]).abs().max() < 0.1      # pixels
     assert (out["track_2d_vis_est_bn1t"].cpu() - ref["track_2d_vis_est_bn1t"]).abs().max() < 1e-2
     assert rel_l2(out["track_2d_depth_est_bn1t"], ref["track_2d_depth_est_bn1t"]) < 3e-3
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# direct kernel checks of the two skinny attentions against plain fp32 torch (sam/transformer.py:223-245)
+# ------------------------------------------------------------------------------------------------------------------
+def _sdpa_ref(q, k, v, heads, scale):
+    """q [G,nq,C], k,v [G,nk,C] fp32 -> [G,nq,C]."""
+    G, nq, C = q.shape
+    d = C // heads
+    qh = q.view(G, nq, heads, d).transpose(1, 2)
+    kh = k.view(G, -1, heads, d).transpose(1, 2)
+    vh = v.view(G, -1, heads, d).transpose(1, 2)
+    a = torch.softmax(qh @ kh.transpose(-1, -2) * scale, dim=-1)
+    return (a @ vh).transpose(1, 2).reshape(G, nq, C)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_image_attention_kernel(dtype):
+    """Many queries x few keys: 2 groups x 256 video tokens x 8 heads of 88 against 6 prompt tokens."""
+    from l4p_b200 import ops
+    G, Np, nk, H, d = 2, 256, 6, 8, 88
+    g = torch.Generator().manual_seed(11)
+    q16 = torch.randn(G * Np, H * d, generator=g).to(dtype).cuda()
+    k = torch.randn(G, nk, H * d, generator=g).cuda()
+    v = torch.randn(G, nk, H * d, generator=g).cuda()
+    out = torch.empty_like(q16)
+    ops.image_attention(q16, k, v, out, G, H, d ** -0.5)
+    torch.cuda.synchronize()
+    ref = _sdpa_ref(q16.float().view(G, Np, -1), k, v, H, d ** -0.5).reshape(G * Np, -1)
+    tol = 2 ** -7 if dtype == torch.bfloat16 else 2 ** -9
+    err = (out.float() - ref).abs().max().item()
+    assert err <= tol * ref.abs().max().item(), f"max abs err {err:.3e}"
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("shared", [False, True])
+def test_token_attention_kernel(dtype, shared):
+    """Few queries x many keys: 6 prompt tokens per query against 2048 video tokens (per-query or shared K/V)."""
+    from l4p_b200 import ops
+    G, nq, Nk, H, d = 3, 6, 2048, 8, 88
+    g = torch.Generator().manual_seed(12)
+    q = torch.randn(G, nq, H * d, generator=g).cuda()
+    rows = Nk if shared else G * Nk
+    k16 = torch.randn(rows, H * d, generator=g).to(dtype).cuda()
+    v16 = torch.randn(rows, H * d, generator=g).to(dtype).cuda()
+    out = torch.empty_like(q)
+    ops.token_attention(q, k16, v16, out, H, shared_kv=shared, scale=d ** -0.5)
+    torch.cuda.synchronize()
+    kf = k16.float().view(1 if shared else G, Nk, -1).expand(G, -1, -1)
+    vf = v16.float().view(1 if shared else G, Nk, -1).expand(G, -1, -1)
+    ref = _sdpa_ref(q, kf, vf, H, d ** -0.5)
+    err = (out - ref).abs().max().item()
+    assert err <= 2e-4 * max(ref.abs().max().item(), 1.0), f"max abs err {err:.3e}"
