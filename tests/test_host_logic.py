@@ -157,3 +157,71 @@ def test_gemm_plan_tile_selection():
     import ctypes as C
     d = lib.GemmDesc(); d.a = d.w = 0x10000; d.M, d.N, d.K = 128, 24, 64; d.lda = d.ldw = 64
     assert lib.load().l4p_gemm_plan(C.byref(d), (C.c_int * 6)()) != 0
+
+
+def test_prepare_model_mirrors_reference_loader(tmp_path):
+    """l4p/models/utils.py:15-60: yaml -> max_queries override -> strict state_dict load -> eval; precision selects the
+    16-bit operand type; CPU / fp32 requests raise instead of falling back."""
+    import pytest
+
+    from l4p_b200.config import DEFAULT_CONFIG
+    from l4p_b200.lib import L4PError
+    from l4p_b200.models.utils import compute_dtype_for, prepare_model
+
+    m = prepare_model(str(DEFAULT_CONFIG), None, max_queries=32, precision="bf16-mixed", device="meta")
+    assert not m.training and m.l4p_model.compute_dtype == torch.bfloat16
+    assert m.l4p_model.task_heads["track_2d"].max_queries == 32
+    assert compute_dtype_for("16-mixed") == torch.float16
+    # Lightning checkpoint layout: {"state_dict": ..., <trainer state>}; meta tensors keep the file small
+    sd = {k: torch.empty(v.shape, dtype=v.dtype, device="meta") for k, v in m.state_dict().items()}
+    ckpt = tmp_path / "model.ckpt"
+    torch.save({"state_dict": sd, "epoch": 3, "global_step": 7}, ckpt)
+    m2 = prepare_model(str(DEFAULT_CONFIG), str(ckpt), device="meta")
+    assert list(m2.state_dict()) == list(sd) and m2.l4p_model.compute_dtype == torch.float16
+    sd.pop("l4p_model.task_heads.depth.task_head.dpt.act_postprocess.3.1.bias")
+    torch.save({"state_dict": sd}, ckpt)
+    with pytest.raises(RuntimeError, match="Missing key"):      # strict_loading: true (configs/model.yaml:11)
+        prepare_model(str(DEFAULT_CONFIG), str(ckpt), device="meta")
+    with pytest.raises(L4PError):
+        prepare_model(str(DEFAULT_CONFIG), None, precision="32-true", device="meta")
+    with pytest.raises(L4PError):
+        prepare_model(str(DEFAULT_CONFIG), None, accelerator="cpu", device="meta")
+
+
+def test_forward_argument_errors_match_reference_asserts():
+    """Shape errors surface as the reference's assertions before any device work (l4p_videomae.py:260, :267-269)."""
+    import pytest
+
+    from l4p_b200.models.l4p_videomae import L4P_VideoMAE
+
+    model = L4P_VideoMAE(torch.nn.ModuleDict(), always_use_windowed_version=True, device="meta")
+    with pytest.raises(AssertionError, match="fixed spatial size"):
+        model.forward(dict(rgb_b3thw=torch.zeros(1, 3, 16, 200, 224, device="meta")), [])
+    with pytest.raises(AssertionError, match="multiple of window stride"):
+        model.forward(dict(rgb_b3thw=torch.zeros(1, 3, 20, 224, 224, device="meta")), [])
+
+
+def test_product_path_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under l4p_b200/ may import it, and bench.py only in its CPU-baseline leg."""
+    import re
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parents[1]
+    pat = re.compile(r"^\s*(from|import)\s+oracle\b|/root/reference", re.M)
+    for f in (root / "l4p_b200").rglob("*.py"):
+        assert not pat.search(f.read_text()), f"{f} references the oracle / the reference tree"
+    bench = (root / "bench.py").read_text()
+    uses = [m.start() for m in re.finditer(r"^\s*(from|import)\s+oracle\b", bench, re.M)]
+    lo, hi = bench.index("def cpu_baseline_sample"), bench.index("def run_reference")
+    assert uses and all(lo < u < hi for u in uses)
+
+
+def test_missing_library_fails_loudly(tmp_path, monkeypatch):
+    from l4p_b200 import lib as L
+
+    monkeypatch.setattr(L, "_lib", None)
+    monkeypatch.setattr(L, "LIB_PATH", tmp_path / "libl4p_b200.so")
+    import pytest
+
+    with pytest.raises(L.L4PError, match="no CPU fallback"):
+        L.load()
