@@ -97,6 +97,11 @@ class FeatureList(list):
         self.taps16 = taps16
 
 
+def _require_device(x: torch.Tensor) -> None:
+    if not x.is_cuda:
+        raise _l.L4PError("VideoMAEEncoder.forward needs a CUDA tensor: the l4p_b200 hot path has no CPU fallback")
+
+
 def _norm_eps(norm_layer) -> float:
     kw = getattr(norm_layer, "keywords", None) or {}
     return float(kw.get("eps", 1e-5))
@@ -204,8 +209,7 @@ class VideoMAEEncoder(nn.Module):
     # ------------------------------------------------------------------ compute
     @torch.no_grad()
     def forward(self, x: torch.Tensor, intrinsics_b44t=None, extrinsics_b44t=None) -> FeatureList:
-        if not x.is_cuda:
-            raise _l.L4PError("VideoMAEEncoder.forward needs a CUDA tensor: the l4p_b200 hot path has no CPU fallback")
+        _require_device(x)
         B, Cin, T, H, W = x.shape
         assert H == self.patch_embed.img_size[0] and W == self.patch_embed.img_size[1], (
             f"Input image size ({H}*{W}) doesn't match model "
