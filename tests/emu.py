@@ -282,10 +282,34 @@ def _affine_apply(self, pred):
     return O.lstsq_affine_apply(self.sol, pred.float(), inverse=bool(self.inverse)).to(pred.dtype)
 
 
+def _solve_sim3(pred, target, frame_step=3, rel_threshold=0.01, iters=8, min_points=10):
+    """sim3.solve_sim3 stand-in: KabaschUmeyama3DAligner.solve (aligner.py:177-237) through the oracle restatement
+    (all sampled-frame points instead of the random 10 % subset, seeded RANSAC)."""
+    import numpy as np
+
+    from oracle import l4p_oracle as O
+
+    _note("sim3_align")
+    d_s, d_t = pred["depth"].float(), target["depth"].float()
+    bs, _, ov, H, W = d_s.shape
+    assert bs == 1
+    thr = float(torch.quantile(d_s.reshape(-1), 0.98)) * rel_threshold
+    pts = []
+    for side, d in ((pred, d_s), (target, d_t)):
+        K = side["camray_intrinsics"].reshape(1, 4, 4, ov).float()[..., ::frame_step]
+        P = side["camray"].reshape(1, 4, 4, ov).float()[..., ::frame_step]
+        pts.append(O.generate_point_map(d[:, :, ::frame_step], K, P)[0].reshape(3, -1).T.double().numpy())
+    T, _ = O.similarity_ransac(pts[0], pts[1], thr, min_samples=min_points)
+    sim = O.similarity_from_T(T)
+    dt = pred["depth"].dtype
+    return {"T": torch.from_numpy(sim["T"])[None].to(dt), "s": torch.from_numpy(np.asarray(sim["s"])).reshape(1).to(dt),
+            "R": torch.from_numpy(sim["R"])[None].to(dt), "t": torch.from_numpy(sim["t"])[None].to(dt)}
+
+
 def install(monkeypatch) -> None:
     """Patch l4p_b200 so that the host mirror runs on CPU tensors through the functions above."""
     from l4p_b200 import ops
-    from l4p_b200.models import aligner, videomae
+    from l4p_b200.models import aligner, sim3, videomae
     from l4p_b200.utils import geometry_utils
 
     CALLS.clear()
@@ -297,4 +321,5 @@ def install(monkeypatch) -> None:
     monkeypatch.setattr(geometry_utils, "_pose_call", _pose_call)
     monkeypatch.setattr(aligner.LstSqAffineAligner, "solve", _affine_solve)
     monkeypatch.setattr(aligner.LstSqAffineAligner, "apply", _affine_apply)
+    monkeypatch.setattr(sim3, "solve_sim3", _solve_sim3)
     monkeypatch.setattr(videomae, "_require_device", lambda x: None)

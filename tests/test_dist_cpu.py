@@ -78,3 +78,58 @@ def test_two_rank_window_shard(tmp_path):
             d, r = _window_result(w)
             assert torch.equal(depth[w], d) and depth[w].dtype == torch.float32
             assert torch.allclose(rays[w], r.float().double()) and rays[w].dtype == torch.float64
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# cfg 4 end to end on CPU: the tiny golden model (tests/test_host_emulated.py) with `enable_window_sharding()` on two
+# gloo ranks -- each rank encodes / decodes only its windows, one all-gather per head, stitching + alignment on every
+# rank -- must return on EVERY rank what the unsharded model returns. Kernel layer = tests/emu.py (test-only).
+# ---------------------------------------------------------------------------------------------------------------
+def _sharded_model_worker(rank, world, port, T, out_dir):
+    import pytest
+
+    from tests import emu
+    from tests import test_host_emulated as H
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    mp_ = pytest.MonkeyPatch()
+    emu.install(mp_)
+    try:
+        tasks = ["depth", "flow_2d_backward"]
+        model = H._tiny_model(tasks)
+        model.enable_window_sharding(True)
+        rgb = H.rnd((1, 3, T, 56, 56), 16)
+        intr = torch.eye(4)[None, :, :, None].repeat(1, 1, 1, T)
+        out = model.forward(dict(rgb_b3thw=rgb, intrinsics_b44t=intr, img_info=H.IMG), tasks)
+        torch.save({"depth": out["depth_est_b1thw"], "flow": out["flow_2d_backward_est_b2thw"],
+                    "local_windows": len(out["enc_features_bpc_2dlist"]), "encoder_passes": emu.CALLS.get("patchify", 0)},
+                   os.path.join(out_dir, f"sharded_{T}_{rank}.pt"))
+        dist.barrier()
+    finally:
+        mp_.undo()
+        dist.destroy_process_group()
+
+
+def test_two_rank_window_sharded_model_matches_unsharded(tmp_path, monkeypatch):
+    from tests import emu
+    from tests import test_host_emulated as H
+    from tests.util import rel_l2
+
+    world = 2
+    for T, local in ((8, [2, 1]), (4, [1, 0])):        # 3 windows -> 2 + 1; 1 window -> 1 + 0 (a rank with nothing to do)
+        mp.spawn(_sharded_model_worker, args=(world, _free_port(), T, str(tmp_path)), nprocs=world, join=True)
+        emu.install(monkeypatch)
+        tasks = ["depth", "flow_2d_backward"]
+        rgb = H.rnd((1, 3, T, 56, 56), 16)
+        intr = torch.eye(4)[None, :, :, None].repeat(1, 1, 1, T)
+        ref = H._tiny_model(tasks).forward(dict(rgb_b3thw=rgb, intrinsics_b44t=intr, img_info=H.IMG), tasks)
+        for rank in range(world):
+            got = torch.load(tmp_path / f"sharded_{T}_{rank}.pt")
+            assert got["local_windows"] == local[rank] and got["encoder_passes"] == (1 if local[rank] else 0)
+            # per-rank batches differ from the single-process batch -> fp32 summation order -> 16-bit rounding flips
+            assert got["depth"].shape == ref["depth_est_b1thw"].shape
+            assert rel_l2(got["depth"], ref["depth_est_b1thw"]) < 1e-3
+            assert rel_l2(got["flow"], ref["flow_2d_backward_est_b2thw"]) < 1e-3
+        a, b = (torch.load(tmp_path / f"sharded_{T}_{r}.pt") for r in range(world))
+        assert torch.equal(a["depth"], b["depth"]) and torch.equal(a["flow"], b["flow"])   # identical on every rank

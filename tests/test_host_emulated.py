@@ -322,3 +322,52 @@ def test_joint_depth_pose_alignment_chain(cpu_kernels, monkeypatch):
     pose[:, :3, :3] /= 2.0
     assert torch.allclose(out["camray_est_b16t"][:, :, 2:], pose.reshape(1, 16, 4), atol=1e-6)
     assert torch.equal(out["camray_intrinsics_est_b16t"], intr.reshape(1, 16, T))
+
+
+def test_orchestrator_joint_alignment_path_vs_oracle_chain(cpu_kernels):
+    """joint_alignment=True with depth + camray routes both through `joint_windowed_estimation` (l4p_videomae.py:299-311);
+    its result must equal the oracle's chain (point maps of every 3rd overlap frame -> similarity -> apply, aligner.py
+    :177-265) run on the per-window outputs of the same heads."""
+    import numpy as np
+
+    from l4p_b200.models.l4p_videomae import L4P_VideoMAE
+    from l4p_b200.models.task_heads import dense_heads as D
+    from oracle import l4p_oracle as O
+
+    depth, flow, _ = _heads()
+    cam = D.VideoMAETraj3DDPTHead("camray", depth=3, embed_dim=64, hooks_idx=HOOKS, output_size=(4, 4, 4),
+                                  use_intrinsics=True, fixed_intrinsics=False)
+    weights.fill_module_(cam, seed=15)
+    heads = torch.nn.ModuleDict(dict(depth=depth, camray=cam, flow_2d_backward=flow))
+    model = L4P_VideoMAE(heads, window_size=IMG, window_stride_T=2, always_use_windowed_version=True, joint_alignment=True,
+                         device="meta")
+    model.video_encoder = _encoder()
+    T, starts = 6, [0, 2]
+    rgb = rnd((1, 3, T, 56, 56), 5)
+    k = torch.eye(4)
+    k[0, 0] = k[1, 1] = 56.0
+    k[0, 2] = k[1, 2] = 28.0
+    intr = k[None, :, :, None].repeat(1, 1, 1, T)
+    tasks = ["depth", "camray", "flow_2d_backward"]
+    out = model.forward(dict(rgb_b3thw=rgb, intrinsics_b44t=intr, img_info=IMG), tasks)
+    assert cpu_kernels.CALLS["sim3_align"] == 1 and cpu_kernels.CALLS.get("affine_align_solve", 0) == 0
+    assert set(["depth_est_b1thw", "camray_est_b16t", "camray_intrinsics_est_b16t", "flow_2d_backward_est_b2thw"]) <= set(out)
+    # the chain by hand from single-window outputs
+    per = []
+    for w, s in enumerate(starts):
+        f = model.video_encoder(rgb[:, :, s:s + 4])
+        d = depth.forward(f, img_info=IMG)["depth_est_b1thw"]
+        p = cam.forward(f, img_info=IMG, intrinsics_b44t=intr[..., s:s + 4], win_id=w)["camray_est_b16t"]
+        per.append((d, p))
+    (d0, p0), (d1, p1) = per
+    Kov = intr[..., 2:4]
+    src = O.generate_point_map(d1[:, :, 0:2:3], Kov[..., ::3], p1.reshape(1, 4, 4, 4)[..., 0:2:3])[0].reshape(3, -1).T.double().numpy()
+    dst = O.generate_point_map(d0[:, :, 2:4:3], Kov[..., ::3], p0.reshape(1, 4, 4, 4)[..., 2:4:3])[0].reshape(3, -1).T.double().numpy()
+    thr = float(torch.quantile(d1[:, :, :2].reshape(-1), 0.98)) * 0.01
+    Tm, _ = O.similarity_ransac(src, dst, thr, min_samples=10)
+    d1a, p1a = O.sim3_apply(Tm, d1, p1)
+    assert rel_l2(out["depth_est_b1thw"][:, :, :2], d0[:, :, :2]) < 1e-3
+    assert rel_l2(out["depth_est_b1thw"][:, :, 2:], d1a) < 2e-3
+    assert rel_l2(out["camray_est_b16t"][:, :, :2], p0[:, :, :2]) < 1e-3
+    assert rel_l2(out["camray_est_b16t"][:, :, 2:], p1a) < 5e-3
+    assert np.isfinite(Tm).all()
