@@ -75,7 +75,7 @@ class ClockSampler:
 
 
 def synth_batch(clips: int):
-    from tests.util import grid_queries, synth_intrinsics, synth_rgb
+    from tests.util import synth_intrinsics, synth_rgb
 
     rgb = synth_rgb(clips, 16, seed=0)
     intr = synth_intrinsics(clips, 16)

@@ -9,7 +9,6 @@ import torch
 
 from .. import lib as _l
 from .. import ops as _ops
-from .. import ops as _ops
 from ..ops import _dev_init, _stream
 
 

@@ -3,7 +3,7 @@
 (SURVEY.md §5 "checkpoint / resume"). They hold weights only: their forward is never the compute path."""
 from __future__ import annotations
 
-from typing import Sequence, Tuple
+from typing import Sequence
 
 import torch
 from torch import nn

@@ -19,7 +19,6 @@ from ... import ops
 from ...utils.misc import apply_fn
 from ...utils import geometry_utils as G
 from ..aligner import KabaschUmeyama3DAligner, LinearAligner, LstSqAffineAligner, WindowOverlapAligner
-from ..videomae import FeatureList
 from .dpt import PixelwiseTaskWithDPT
 
 

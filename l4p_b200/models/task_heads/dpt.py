@@ -15,7 +15,7 @@ Compute (all activations channels-last [B,T,H,W,C] 16-bit, fp32 accumulation, on
 """
 from __future__ import annotations
 
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import Dict, Optional, Sequence, Tuple
 
 import torch
 from torch import nn

@@ -18,7 +18,7 @@ Compute layout (B == 1, G = number of queries in the chunk, P = 2048 video token
 from __future__ import annotations
 
 import math
-from typing import Dict, List, Literal, Optional, Tuple
+from typing import List, Literal, Optional, Tuple
 
 import torch
 from torch import nn

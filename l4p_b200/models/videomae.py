@@ -16,7 +16,7 @@ The residual stream and all LayerNorm/softmax statistics are fp32; GEMM operands
 """
 from __future__ import annotations
 
-from typing import Dict, Iterable, List, Optional, Sequence
+from typing import Dict, Iterable, List, Optional
 
 import numpy as np
 import torch

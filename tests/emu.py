@@ -12,9 +12,6 @@ The product path is unaffected: without `install`, CPU tensors still raise L4PEr
 """
 from __future__ import annotations
 
-import math
-from typing import Optional, Tuple
-
 import torch
 import torch.nn.functional as F
 

@@ -275,7 +275,6 @@ def test_joint_depth_pose_alignment_chain(cpu_kernels, monkeypatch):
     """`joint_windowed_estimation` (dense_heads.py:360-492) on two windows with a known similarity between them: the
     chain must hand the aligner the overlap slices (depth, pose, intrinsics of both sides), apply the returned
     scale / transform to the new window (aligner.py:239-265) and write later windows over the buffer."""
-    from l4p_b200.models import aligner as A
     from l4p_b200.models.task_heads import dense_heads as D
 
     depth, _, _ = _heads()
