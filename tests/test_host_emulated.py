@@ -370,3 +370,51 @@ def test_orchestrator_joint_alignment_path_vs_oracle_chain(cpu_kernels):
     assert rel_l2(out["camray_est_b16t"][:, :, :2], p0[:, :, :2]) < 1e-3
     assert rel_l2(out["camray_est_b16t"][:, :, 2:], p1a) < 5e-3
     assert np.isfinite(Tm).all()
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_tracker_state_machine_random_queries_vs_oracle(cpu_kernels, seed):
+    """Random query times / positions (some starting in later windows, some after the clip's last frame -> never valid)
+    over 4 windows: written-frame masks, label state machine and argmax re-query must follow the oracle's restatement of
+    sparse_heads.py:213-495 exactly; values to 16-bit operand noise."""
+    from oracle import l4p_oracle as O
+
+    gen = torch.Generator().manual_seed(100 + seed)
+    T, starts = 10, [0, 2, 4, 6]
+    enc = _encoder()
+    rgb = rnd((1, 3, T, 56, 56), 200 + seed)
+    f2d = _windows(enc, rgb, starts)
+    n = 7
+    q = torch.cat([torch.randint(0, 12, (1, n, 1), generator=gen).float() + 0.5,
+                   torch.rand(1, n, 2, generator=gen) * 50 + 3], dim=-1)
+    lab = torch.ones(1, n)
+    trk = _tracker()
+    sd = {k: v.clone() for k, v in trk.state_dict().items()}
+    got = trk.forward_windowed(f2d, q, lab, time_strides=torch.tensor(starts))
+    ref = O.track_windowed(sd, "", [f[-1] for f in f2d], q, lab, starts, image_size=IMG)
+    for k in ("track_2d_traj_est_bn2t", "track_2d_vis_est_bn1t", "track_2d_depth_est_bn1t"):
+        a, b = got[k], ref[k]
+        assert a.shape == b.shape == (1, n, b.shape[2], T)
+        assert torch.equal(a == 0, b == 0) and torch.equal(a == -10, b == -10), f"{k}: written-frame mask differs"
+    late = q[0, :, 0] > T                                             # queried after the last frame: never written
+    assert (got["track_2d_vis_est_bn1t"][0, late] == -10).all()
+    assert (got["track_2d_traj_est_bn2t"] - ref["track_2d_traj_est_bn2t"]).abs().max() < 0.02
+    assert (got["track_2d_vis_est_bn1t"] - ref["track_2d_vis_est_bn1t"]).abs().max() < 3e-3
+    assert rel_l2(got["track_2d_depth_est_bn1t"], ref["track_2d_depth_est_bn1t"]) < 2e-3
+
+
+def test_bf16_operands_through_the_same_path(g, cpu_kernels):
+    """`set_compute_dtype(torch.bfloat16)` (prepare_model precision 'bf16-mixed') switches every operand buffer of the
+    encoder and heads; results stay within bf16 operand noise of the reference goldens."""
+    model = _tiny_model(["depth", "flow_2d_backward"])
+    model.set_compute_dtype(torch.bfloat16)
+    T = 8
+    rgb = rnd((1, 3, T, 56, 56), 16)
+    out = model.forward(dict(rgb_b3thw=rgb, intrinsics_b44t=torch.eye(4)[None, :, :, None].repeat(1, 1, 1, T), img_info=IMG),
+                        ["depth", "flow_2d_backward"])
+    feats = out["enc_features_bpc_2dlist"][0]
+    assert all(t.dtype == torch.bfloat16 for t in model.video_encoder._ws[next(iter(model.video_encoder._ws))].values()
+               if t.dtype != torch.float32)
+    assert feats[-1].dtype == torch.float32
+    assert rel_l2(out["depth_est_b1thw"], g["depth_windowed"]) < 5e-3
+    assert rel_l2(out["flow_2d_backward_est_b2thw"], g["flow_windowed"]) < 1.5e-2
