@@ -1,0 +1,186 @@
+"""Host mirror vs the UNMODIFIED reference run live (build container only: /root/reference through oracle/ref_loader.py;
+skipped where the tree is absent, e.g. on the GPU box). Fresh seeds, i.e. not the committed fixtures: both sides get the
+same key-addressed synthetic weights (`l4p_b200.weights`), the mirror runs on tests/emu.py's per-op torch definitions.
+
+Covers what the fixtures do not: the dynamic-mask head, the camera-ray head's three intrinsics modes including the
+reference's first-window quirk (dense_heads.py:327-334), prompt-feature / label inputs of the single-window track head."""
+from functools import partial
+
+import pytest
+import torch
+
+from l4p_b200 import weights
+from oracle import ref_loader
+from tests import emu
+from tests.util import rel_l2
+
+pytestmark = pytest.mark.skipif(not ref_loader.available(), reason="reference tree not present")
+
+HOOKS = [1, 2, 3, 3]
+IMG = (4, 56, 56)
+
+
+@pytest.fixture()
+def cpu_kernels(monkeypatch):
+    emu.install(monkeypatch)
+    return emu
+
+
+@pytest.fixture(scope="module")
+def ref():
+    ref_loader.load()
+    import l4p.models.l4p_videomae as RV
+    import l4p.models.task_heads.dense_heads as RD
+    import l4p.models.task_heads.sparse_heads as RS
+    import l4p.utils.geometry_utils as RG
+
+    return dict(V=RV, D=RD, S=RS, G=RG)
+
+
+def rnd(shape, seed, scale=1.0):
+    return torch.randn(shape, generator=torch.Generator().manual_seed(seed)) * scale
+
+
+ENC_KW = dict(img_size=56, patch_size=14, embed_dim=64, depth=3, num_heads=4, mlp_ratio=4, qkv_bias=True,
+              norm_layer=partial(torch.nn.LayerNorm, eps=1e-6), init_values=0.0, tubelet_size=2, all_frames=4)
+
+
+def _pair(ref_cls, our_cls, seed, *args, **kw):
+    r, o = ref_cls(*args, **kw).eval(), our_cls(*args, **kw)
+    weights.fill_module_(r, seed=seed)
+    weights.fill_module_(o, seed=seed)
+    assert list(r.state_dict().keys()) == list(o.state_dict().keys())
+    return r, o
+
+
+@torch.no_grad()
+def test_dense_heads_windowed_fresh_seed(ref, cpu_kernels):
+    from l4p_b200.models.task_heads import dense_heads as D
+    from l4p_b200.models.videomae import VideoMAEEncoder
+
+    renc, oenc = _pair(ref["V"].VideoMAEEncoder, VideoMAEEncoder, 41, **ENC_KW)
+    oenc.keep_features = "all"
+    T, starts = 10, torch.arange(0, 10 - 4 + 1, 2)
+    rgb = rnd((1, 3, T, 56, 56), 42)
+    intr = torch.eye(4)[None, :, :, None].repeat(1, 1, 1, T)
+    rf2d = [renc(rgb[:, :, s:s + 4]) for s in starts]
+    of2d = [oenc(rgb[:, :, s:s + 4]) for s in starts]
+    for i in range(4):
+        assert rel_l2(of2d[1][i], rf2d[1][i]) < 1e-3
+    cases = [
+        ("depth", ref["D"].VideoMAEDepthDPTHead, D.VideoMAEDepthDPTHead,
+         dict(depth=3, embed_dim=64, depth_fn="exp", hooks_idx=HOOKS, align_window_overlap_fn="inverse"), "depth_est_b1thw"),
+        ("flow_2d_backward", ref["D"].VideoMAEFlowDPTHead, D.VideoMAEFlowDPTHead,
+         dict(out_nchan=2, depth=3, embed_dim=64, hooks_idx=HOOKS), "flow_2d_backward_est_b2thw"),
+        ("dyn_mask", ref["D"].VideoMAEDynMaskDPTHead, D.VideoMAEDynMaskDPTHead,
+         dict(out_nchan=1, depth=3, embed_dim=64, apply_fn="sigmoid", hooks_idx=HOOKS), "dyn_mask_est_b1thw"),
+    ]
+    for seed, (name, rc, oc, kw, key) in enumerate(cases, start=43):
+        rh, oh = _pair(rc, oc, seed, name, **kw)
+        want = rh.forward_windowed(rf2d, img_info=IMG, time_strides=starts, intrinsics_b44t=intr)[key]
+        got = oh.forward_windowed(of2d, img_info=IMG, time_strides=starts, intrinsics_b44t=intr)[key]
+        assert got.shape == want.shape == (1, want.shape[1], T, 56, 56)
+        assert rel_l2(got, want) < 1.5e-3, (name, rel_l2(got, want))
+
+
+class _Rays(torch.nn.Module):
+    """Stands in for the reference head's DPT (`task_head`): returns prepared ray maps in call order."""
+
+    def __init__(self, rays):
+        super().__init__()
+        self.rays, self.i = list(rays), 0
+
+    def forward(self, feats, img_info):
+        r = self.rays[self.i % len(self.rays)]
+        self.i += 1
+        return r
+
+
+def _camera_windows(G, starts, Tw, T):
+    """Valid Plücker ray maps of a synthetic moving camera, one per window (each window in its own first-camera frame,
+    as the head would predict them: get_rays_plucker, geometry_utils.py:165-241)."""
+    gen = torch.Generator().manual_seed(7)
+    K = torch.eye(4)[None, :, :, None].repeat(1, 1, 1, T)
+    K[:, 0, 0], K[:, 1, 1], K[:, 0, 2], K[:, 1, 2] = 0.9, 1.1, 0.5, 0.5          # normalised
+    ext = torch.zeros(1, 4, 4, T)
+    for t in range(T):
+        qm, _ = torch.linalg.qr(torch.eye(3) + 0.2 * torch.randn(3, 3, generator=gen))
+        if torch.linalg.det(qm) < 0:
+            qm[:, 0] = -qm[:, 0]
+        ext[0, :3, :3, t] = qm
+        ext[0, :3, 3, t] = torch.randn(3, generator=gen) * 0.3
+        ext[0, 3, 3, t] = 1
+    rays = [G.get_rays_plucker(K[..., s:s + Tw], ext[..., s:s + Tw], (4, 4))[0] for s in starts]
+    return rays, G.denormalize_intrinsics(K, 56, 56)
+
+
+@torch.no_grad()
+@pytest.mark.parametrize("use_intrinsics,fixed", [(True, False), (False, True)])
+def test_camray_head_modes_and_first_window_quirk(ref, cpu_kernels, use_intrinsics, fixed):
+    """Both heads are fed the SAME valid ray maps (the DPT is pinned elsewhere), so this isolates the pose logic: mode
+    dispatch, `win_id` / first-window intrinsics state, later windows solved with the INPUT intrinsics while reporting
+    the first-window estimate, window writes into the [B,16,T] buffer."""
+    from l4p_b200.models.task_heads import dense_heads as D
+
+    kw = dict(depth=3, embed_dim=64, hooks_idx=HOOKS, output_size=(4, 4, 4), use_intrinsics=use_intrinsics,
+              fixed_intrinsics=fixed)
+    rh, oh = _pair(ref["D"].VideoMAETraj3DDPTHead, D.VideoMAETraj3DDPTHead, 51, "camray", **kw)
+    T, starts = 8, torch.arange(0, 8 - 4 + 1, 2)
+    rays, intr = _camera_windows(ref["G"], [int(s) for s in starts], 4, T)
+    it_o = iter(rays)
+    rh.task_head = _Rays(rays)
+    oh.rays = lambda feats, img_info=IMG: next(it_o)
+    dummy = [[torch.zeros(1)]] * len(starts)      # the reference reads dtype / device off the first feature
+    want = rh.forward_windowed(dummy, img_info=IMG, time_strides=starts, intrinsics_b44t=intr)["camray_est_b16t"]
+    got = oh.forward_windowed(dummy, img_info=IMG, time_strides=starts, intrinsics_b44t=intr)["camray_est_b16t"]
+    assert got.shape == want.shape == (1, 16, T)
+    assert (got - want).abs().max() < 2e-3, (got - want).abs().max()
+    # single-window call: the intrinsics estimate is reported only in the fixed-intrinsics mode
+    rh.task_head = _Rays(rays[:1])
+    oh.rays = lambda feats, img_info=IMG: rays[0]
+    w1 = rh.forward([None], img_info=IMG, intrinsics_b44t=intr[..., :4], win_id=0)
+    g1 = oh.forward([None], img_info=IMG, intrinsics_b44t=intr[..., :4], win_id=0)
+    assert set(w1) == set(g1)
+    for k in w1:
+        assert (g1[k] - w1[k]).abs().max() < 2e-3 * max(1.0, float(w1[k].abs().max())), k
+    if fixed:
+        # window 1 after window 0: pose from the INPUT intrinsics, reported intrinsics = window 0's estimate
+        rh.task_head = _Rays(rays[1:2])
+        oh.rays = lambda feats, img_info=IMG: rays[1]
+        w2 = rh.forward([None], img_info=IMG, intrinsics_b44t=intr[..., 2:6], win_id=1)
+        g2 = oh.forward([None], img_info=IMG, intrinsics_b44t=intr[..., 2:6], win_id=1)
+        assert torch.equal(g2["camray_intrinsics_est_b16t"], g1["camray_intrinsics_est_b16t"])
+        assert (g2["camray_intrinsics_est_b16t"] - w2["camray_intrinsics_est_b16t"]).abs().max() < 2e-3 * 56
+        assert (g2["camray_est_b16t"] - w2["camray_est_b16t"]).abs().max() < 2e-3
+
+
+@torch.no_grad()
+def test_track_head_prompt_features_and_labels(ref, cpu_kernels):
+    """Single-window track head with explicit prompt features / feature labels and mixed point labels {0,1,2}
+    (the inputs the windowed driver feeds from the second window on, sparse_heads.py:497-591)."""
+    from l4p_b200.models.task_heads.sparse_heads import VideoMAETrack2DSamHead
+    from l4p_b200.models.videomae import VideoMAEEncoder
+
+    renc, oenc = _pair(ref["V"].VideoMAEEncoder, VideoMAEEncoder, 61, **ENC_KW)
+    kw = dict(task_name="track_2d", prompt_embed_dim=64, image_size=IMG, estimate_vis=True, estimate_depth=True,
+              sam_head_depth=2, num_point_embeddings=2, modify_pointlabels_for_windowing=True, prompt_using_features=True,
+              attend_to_past=True, estimation_directions=[1], depth_fn="exp", vis_fn="linear")
+    rt, ot = _pair(ref["S"].VideoMAETrack2DSamHead, VideoMAETrack2DSamHead, 62, **kw)
+    rgb = rnd((1, 3, 4, 56, 56), 63)
+    rf, of = renc(rgb), oenc(rgb)
+    q = torch.tensor([[[0.5, 10.5, 12.5], [1.5, 40.5, 30.5], [2.5, 28.0, 28.0], [3.5, 5.5, 50.5], [0.5, 33.3, 8.1]]])
+    lab = torch.tensor([[1.0, 2.0, 0.0, 1.0, 2.0]])
+    pf = rnd((1, 5, 64), 64, 0.5)
+    pl = torch.tensor([[1.0, 0.0, 1.0, 0.0, 1.0]])
+    # per-query history tokens (as from the second window on): [B, N, P, C]
+    hist = rnd((1, 5, 32, 64), 65, 0.3)
+    for enc_r, enc_o in ((rf[-1], of[-1]), (rf[-1].unsqueeze(1) + hist, of[-1].unsqueeze(1) + hist)):
+        want = rt.forward([enc_r], q, lab, pf, pl)
+        got = ot.forward([enc_o], q, lab, pf, pl)
+        assert set(want) == set(got)
+        assert (got["track_2d_traj_est_bn2t"] - want["track_2d_traj_est_bn2t"]).abs().max() < 0.02
+        assert (got["track_2d_vis_est_bn1t"] - want["track_2d_vis_est_bn1t"]).abs().max() < 3e-3
+        assert rel_l2(got["track_2d_depth_est_bn1t"], want["track_2d_depth_est_bn1t"]) < 2e-3
+        assert rel_l2(got["track_2d_prompt_features_bnc"], want["track_2d_prompt_features_bnc"]) < 5e-3
+        assert rel_l2(got["track_2d_enc_features_with_track_history_bnpc"],
+                      want["track_2d_enc_features_with_track_history_bnpc"]) < 5e-3
