@@ -183,6 +183,12 @@ def main():
 
         dist.init_process_group("nccl", device_id=dev)
 
+    from l4p_b200 import build as _build
+
+    if local == 0:
+        _build.build()  # no-op when the in-tree library is current; the harness never runs without the CUDA library
+    if world > 1:
+        dist.barrier()
     from l4p_b200 import ops, weights
     from l4p_b200.config import load_model
     from l4p_b200.parallel import gather_clip_outputs

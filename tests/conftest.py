@@ -12,6 +12,22 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+@pytest.fixture(scope="session", autouse=True)
+def _cuda_library_is_current():
+    """On a GPU box make sure the in-tree CUDA library matches the sources (a no-op when it travelled with the snapshot).
+    CPU-only runs never build here: tests/test_abi.py asserts the library `__graft_entry__.build()` produced."""
+    try:
+        import torch
+
+        if torch.cuda.is_available():
+            from l4p_b200 import build
+
+            build.build()
+    except ImportError:
+        pass
+    yield
+
+
 def pytest_collection_modifyitems(config, items):
     try:
         import torch
