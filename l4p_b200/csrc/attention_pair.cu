@@ -1,58 +1,62 @@
-// K4: fused spatio-temporal multi-head attention, softmax(Q K^T * scale) V, for sm_100a.
+// K4 (experimental CTA-pair variant, opt-in with L4P_ATT_PAIR=1; NOT yet run on hardware - written at the end of round 1
+// when the GPU budget was spent): the fused attention kernel of attention.cu with
+// tcgen05.mma.cta_group::2. A cluster of two CTAs owns 512 query rows of one (batch, head): each CTA keeps two 128-row
+// query tiles (as attention.cu), but every key / value block is staged HALF per CTA - 64 of the 128 keys of K_j, 48 of the
+// 96 rows of V^T_j - and the leader CTA issues M=256 UMMAs that read both CTAs' shared memory and write each CTA's own TMEM.
+// Per SM and key block that is 24 KiB instead of 48 KiB of TMA writes and 128 KiB instead of 176 KiB of UMMA operand reads
+// through the 128 B/clk shared-memory port (the measured limiter of attention.cu), and half the single-thread UMMA issue
+// work per SM. The softmax warpgroups are attention.cu's, unchanged except that their "S consumed" / "P ready" arrivals go
+// to the leader CTA's barriers (2 x 128 arrivals each).
 //
-// Flash-style, never materialises the [N,N] score matrix (the reference does: modeling_finetune.py:180-186).
-// One CTA owns two 128-row query tiles of one (batch, head) and streams the keys/values in blocks of 128:
+//   barrier            lives in     arrivals
+//   bar_q              leader       1 (leader's expect_tx) + bytes of both CTAs' Q tiles
+//   bar_kfull/vfull[s] leader       1 (leader's expect_tx) + bytes of both halves
+//   bar_kempty/vempty  each CTA     multicast tcgen05.commit
+//   bar_sfull[t]       each CTA     multicast tcgen05.commit (S_t complete in both TMEMs)
+//   bar_sfree[t]       leader       256 (every softmax thread of tile t in both CTAs holds S_t in registers)
+//   bar_pfull[t]       leader       256 (P_t of both CTAs written, O_t rescaled)
+//   bar_pvdone[t]      each CTA     multicast tcgen05.commit
 //
-//   warp 0       TMA producer: Q tiles once, then K blocks ([128 keys x 96] as three 64-byte-swizzled
-//                32-element chunks) and V^T blocks ([96 x 128 keys], two 128-byte-swizzled chunks) in rings
-//   warp 1       UMMA issuer (one thread): S_t = Q_t K_j^T (M128 N128 K96) into TMEM, O_t += P_t V_j
-//                (M128 N96 K128) into TMEM; S_t(j+1) is issued before P_t(j) V_j so the tensor pipe
-//                works while the softmax warps run
-//   warp 2       TMEM allocator (512 columns: S0 | S1 | O0 | O1 | P0)
-//   warps 4..7   softmax warpgroup for tile 0, one query row per thread
-//   warps 8..11  softmax warpgroup for tile 1
-//
-// Softmax: fp32 scores from TMEM, running max with lazy rescale (O is only rescaled in TMEM when the row max
-// grew by more than 2^8), exp2 with the scale folded into one FFMA, fp32 row sums, P rounded to the operand
-// type; tile 0's P goes back to TMEM (64 spare columns) as the A operand of a TS-mode PV UMMA, tile 1's P to
-// 128B-swizzled smem (SS mode).
-//
-// Layouts (produced by the QKV GEMM epilogue, see gemm.cu L4P_STORE_QKV):
-//   Q, K : [B, H, N, dpad]   (dpad = 96, columns >= head_dim are zero)
-//   Vt   : [B, H, dpad, N]
-//   out  : [B*N, H*head_dim] row-major 16-bit (operand of the output projection GEMM)
+// Every wait is the bounded mbar_wait of common.cuh: a protocol bug traps instead of hanging the GPU.
 #include <cstdlib>
 
 #include "common.cuh"
 
 namespace l4p {
+namespace attpair {
 
 constexpr int kAttThreads = 384;
 constexpr int kDPad = 96;
-constexpr int kTileM = 128;   // query rows per tile
+constexpr int kTileM = 128;   // query rows per tile and CTA
 constexpr int kTileN = 128;   // keys per block
-constexpr int kQTileBytes = kTileM * kDPad * 2;  // 24576: 3 chunks x (128 rows x 64 B)
-constexpr int kKBytes = kTileN * kDPad * 2;      // 24576
-constexpr int kVBytes = kDPad * kTileN * 2;      // 24576: 2 chunks x (96 rows x 128 B)
-constexpr int kPBytes = kTileM * kTileN * 2;     // 32768: 2 chunks x (128 rows x 128 B)
-constexpr int kKS = 2, kVS = 2;
-constexpr int kAttSmem = 2 * kQTileBytes + kKS * kKBytes + kVS * kVBytes + 2 * kPBytes + 1024;
-constexpr uint32_t kColS0 = 0, kColS1 = 128, kColO0 = 256, kColO1 = 352, kColP0 = 448;  // P0: tile 0's probabilities (64 columns)
+constexpr int kQTileBytes = kTileM * kDPad * 2;        // 24576: 3 chunks x (128 rows x 64 B)
+constexpr int kKHalfBytes = (kTileN / 2) * kDPad * 2;  // 12288: 3 chunks x (64 keys x 64 B)
+constexpr int kVHalfBytes = (kDPad / 2) * kTileN * 2;  // 12288: 2 chunks x (48 rows x 128 B)
+constexpr int kKChunk = (kTileN / 2) * 64;             // 4096 B between the 32-element chunks of a K half
+constexpr int kVChunk = (kDPad / 2) * 128;             // 6144 B between the 64-key chunks of a V^T half
+constexpr int kPBytes = kTileM * kTileN * 2;           // 32768: tile 1's P, 2 chunks x (128 rows x 128 B)
+constexpr int kKS = 4, kVS = 4;
+constexpr int kAttSmem = 2 * kQTileBytes + kKS * kKHalfBytes + kVS * kVHalfBytes + kPBytes + 1024;
+constexpr uint32_t kColS0 = 0, kColS1 = 128, kColO0 = 256, kColO1 = 352, kColP0 = 448;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
-#ifndef L4P_ATT_P_TMEM
-#define L4P_ATT_P_TMEM 1
-#endif
-constexpr bool kPTmem = L4P_ATT_P_TMEM != 0;  // tile 0's P through the 64 spare TMEM columns (TS-mode UMMA)
 
 struct AttParams {
   uint16_t* out;
   int B, H, N, head_dim;
   float scale_log2;  // scale * log2(e)
-  long long* prof;   // optional [3 roles][64 iters][8] clock64 stamps of CTA 0 (debug; NULL in production)
 };
 
-#define ATT_STAMP(role, it, slot) \
-  do { if (p.prof != nullptr && blockIdx.x == 0 && lane == 0 && (it) < 64) p.prof[((role) * 64 + (it)) * 8 + (slot)] = clock64(); } while (0)
+// D[tmem, both CTAs] (+)= A[tmem, each CTA's own 128 lanes] * B[smem, N/2 rows per CTA]
+L4P_DEVICE void umma2_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}\n"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 
 // 2^x for a pair on the FMA/ALU pipes (no MUFU): round-to-nearest split x = n + f, f in [-0.5, 0.5], cubic minimax for
 // 2^f (max rel err 7.6e-5, well below the 16-bit rounding of P), exponent patched in with an integer add.
@@ -79,9 +83,9 @@ L4P_DEVICE uint64_t exp2_poly2(uint64_t t2) {
 }
 
 template <bool BF16, int POLY>
-__global__ void __launch_bounds__(kAttThreads, 1)
-attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                 const __grid_constant__ CUtensorMap tmV, const AttParams p) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kAttThreads, 1)
+attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                      const __grid_constant__ CUtensorMap tmV, const AttParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_q;
   __shared__ __align__(8) uint64_t bar_kfull[kKS], bar_kempty[kKS];
@@ -91,23 +95,18 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  if (p.prof != nullptr && threadIdx.x == 0) {  // per-CTA wall/cycle stamps after the [3][64][8] timeline
-    long long gt;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
-    uint32_t smid;
-    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-    long long* c = p.prof + 1536 + 5 * (long long)blockIdx.x;
-    c[0] = gt; c[2] = clock64(); c[4] = smid;
-  }
+  const uint32_t rank = cluster_ctarank();
+  const bool is_leader = rank == 0;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = smem_base;
   const uint32_t sK = sQ + 2 * kQTileBytes;
-  const uint32_t sV = sK + kKS * kKBytes;
-  const uint32_t sP = sV + kVS * kVBytes;
+  const uint32_t sV = sK + kKS * kKHalfBytes;
+  const uint32_t sP = sV + kVS * kVHalfBytes;
 
-  const int pairs_per_head = p.N / (2 * kTileM);
-  const int pair = blockIdx.x % pairs_per_head;
-  const int bh = blockIdx.x / pairs_per_head;  // b * H + h
+  const int clusters_per_head = p.N / (4 * kTileM);
+  const int cluster = blockIdx.x >> 1;
+  const int cl = cluster % clusters_per_head;
+  const int bh = cluster / clusters_per_head;  // b * H + h
   const int nblk = p.N / kTileN;
 
   if (threadIdx.x == 0) {
@@ -119,15 +118,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     for (int s = 0; s < kVS; ++s) { mbar_init(smem_u32(&bar_vfull[s]), 1); mbar_init(smem_u32(&bar_vempty[s]), 1); }
     for (int t = 0; t < 2; ++t) {
       mbar_init(smem_u32(&bar_sfull[t]), 1);
-      mbar_init(smem_u32(&bar_sfree[t]), 128);
-      mbar_init(smem_u32(&bar_pfull[t]), 128);
+      mbar_init(smem_u32(&bar_sfree[t]), 256);
+      mbar_init(smem_u32(&bar_pfull[t]), 256);
       mbar_init(smem_u32(&bar_pvdone[t]), 1);
     }
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc(smem_u32(&tmem_base_slot), 512);
+  if (warp == 2) tmem_alloc2(smem_u32(&tmem_base_slot), 512);
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();  // both CTAs' barriers are initialised before any remote arrive / multicast commit / peer TMA signal
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
   pdl_launch_dependents();
@@ -136,70 +135,63 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     if (warp == 0 && lane == 0) {
-      // ---------------------------------------------------------------- TMA producer
-      const int q_row0 = bh * p.N + pair * 2 * kTileM;  // row in the [B*H*N, 96] view
-      const uint32_t qb = smem_u32(&bar_q);
-      mbar_expect_tx(qb, 2 * kQTileBytes);
+      // ---------------------------------------------------------------- TMA producer (both CTAs: own Q tiles, own halves)
+      const int q_row0 = bh * p.N + cl * 4 * kTileM;  // row in the [B*H*N, 96] view
+      const uint32_t qb = mapa_shared(smem_u32(&bar_q), 0);
+      if (is_leader) mbar_expect_tx(smem_u32(&bar_q), 4 * kQTileBytes);
       for (int t = 0; t < 2; ++t)
         for (int c = 0; c < 3; ++c)
-          tma_load_2d(sQ + t * kQTileBytes + c * (kTileM * 64), &tmQ, qb, c * 32, q_row0 + t * kTileM);
+          tma2_load_2d(sQ + t * kQTileBytes + c * (kTileM * 64), &tmQ, qb, c * 32, q_row0 + (t * 2 + (int)rank) * kTileM);
       for (int j = 0; j < nblk; ++j) {
         {
           const int s = j % kKS;
           mbar_wait(smem_u32(&bar_kempty[s]), (((uint32_t)(j / kKS)) & 1u) ^ 1u);
-          const uint32_t fb = smem_u32(&bar_kfull[s]);
-          mbar_expect_tx(fb, kKBytes);
+          const uint32_t fb = mapa_shared(smem_u32(&bar_kfull[s]), 0);
+          if (is_leader) mbar_expect_tx(smem_u32(&bar_kfull[s]), 2 * kKHalfBytes);
           for (int c = 0; c < 3; ++c)
-            tma_load_2d(sK + s * kKBytes + c * (kTileN * 64), &tmK, fb, c * 32, bh * p.N + j * kTileN);
+            tma2_load_2d(sK + s * kKHalfBytes + c * kKChunk, &tmK, fb, c * 32, bh * p.N + j * kTileN + (int)rank * (kTileN / 2));
         }
         {
           const int s = j % kVS;
           mbar_wait(smem_u32(&bar_vempty[s]), (((uint32_t)(j / kVS)) & 1u) ^ 1u);
-          const uint32_t fb = smem_u32(&bar_vfull[s]);
-          mbar_expect_tx(fb, kVBytes);
+          const uint32_t fb = mapa_shared(smem_u32(&bar_vfull[s]), 0);
+          if (is_leader) mbar_expect_tx(smem_u32(&bar_vfull[s]), 2 * kVHalfBytes);
           for (int c = 0; c < 2; ++c)
-            tma_load_2d(sV + s * kVBytes + c * (kDPad * 128), &tmV, fb, j * kTileN + c * 64, bh * kDPad);
+            tma2_load_2d(sV + s * kVHalfBytes + c * kVChunk, &tmV, fb, j * kTileN + c * 64, bh * kDPad + (int)rank * (kDPad / 2));
         }
       }
-    } else if (warp == 1) {
-      // ---------------------------------------------------------------- UMMA issuer
-      // The whole warp walks the pipeline (warp-uniform control flow keeps descriptors in uniform registers);
-      // one elected lane issues. Descriptor words are precomputed: per UMMA only an add remains.
-      // Measured (tools/ubench/umma_bench.cu): an SS-mode UMMA costs ~43 + N/2 cycles (the 128 x 16 A operand is
-      // fetched from shared memory before B streams), a TS-mode one ~10 + N/2, and one thread issues at most one per
-      // ~93 cycles. The 12 + 16 UMMAs of a key block therefore occupy the tensor pipe for ~2700 cycles against 1536
-      // cycles of arithmetic - that, not the softmax, bounds this kernel. A second issuer warp (one per query tile)
-      // was tried: the pipe speeds up ~10 % but both softmax warpgroups then run their exp phases in lockstep and the
-      // kernel gets slower.
+    } else if (warp == 1 && is_leader) {
+      // ---------------------------------------------------------------- UMMA issuer (leader CTA only, M = 256)
       const bool leader = elect_one();
-      const uint32_t idesc_s = umma_idesc_f16(BF16, kTileM, kTileN);
-      const uint32_t idesc_o = umma_idesc_f16(BF16, kTileM, kDPad);
+      const uint32_t idesc_s = umma_idesc_f16(BF16, 2 * kTileM, kTileN);
+      const uint32_t idesc_o = umma_idesc_f16(BF16, 2 * kTileM, kDPad);
       constexpr uint32_t hi64 = umma_desc_hi(64, 4), hi128 = umma_desc_hi(128, 2);
       const uint32_t q_lo = umma_desc_lo(sQ), k_lo = umma_desc_lo(sK), p_lo = umma_desc_lo(sP), v_lo = umma_desc_lo(sV);
       auto issue_s = [&](const int t, const int s) {
         const uint32_t d = tmem_base + (t == 0 ? kColS0 : kColS1);
-        const uint32_t qa = q_lo + (uint32_t)t * (kQTileBytes >> 4), ka = k_lo + (uint32_t)s * (kKBytes >> 4);
+        const uint32_t qa = q_lo + (uint32_t)t * (kQTileBytes >> 4), ka = k_lo + (uint32_t)s * (kKHalfBytes >> 4);
 #pragma unroll
         for (int kk = 0; kk < kDPad / 16; ++kk) {
-          const uint32_t off = ((uint32_t)(kk >> 1) * (kTileM * 64) + (uint32_t)(kk & 1) * 32) >> 4;
-          umma_ss(d, umma_desc_make(qa + off, hi64), umma_desc_make(ka + off, hi64), idesc_s, kk != 0 ? 1u : 0u);
+          const uint32_t qoff = ((uint32_t)(kk >> 1) * (kTileM * 64) + (uint32_t)(kk & 1) * 32) >> 4;
+          const uint32_t koff = ((uint32_t)(kk >> 1) * kKChunk + (uint32_t)(kk & 1) * 32) >> 4;
+          umma2_ss(d, umma_desc_make(qa + qoff, hi64), umma_desc_make(ka + koff, hi64), idesc_s, kk != 0 ? 1u : 0u);
         }
-        umma_commit(smem_u32(&bar_sfull[t]));
+        umma2_commit_mc(smem_u32(&bar_sfull[t]), 3);
       };
       auto issue_pv = [&](const int t, const int s, const uint32_t acc) {
         const uint32_t d = tmem_base + (t == 0 ? kColO0 : kColO1);
-        const uint32_t pa = p_lo + (uint32_t)t * (kPBytes >> 4), va = v_lo + (uint32_t)s * (kVBytes >> 4);
+        const uint32_t va = v_lo + (uint32_t)s * (kVHalfBytes >> 4);
 #pragma unroll
         for (int kk = 0; kk < kTileN / 16; ++kk) {
           const uint32_t o = ((uint32_t)(kk & 3) * 32) >> 4;
-          const uint64_t vdesc = umma_desc_make(va + (uint32_t)(kk >> 2) * ((kDPad * 128) >> 4) + o, hi128);
-          if (kPTmem && t == 0)  // P_0 is the TMEM A operand: 8 columns per K = 16 step, no shared-memory traffic for P
-            umma_ts(d, tmem_base + kColP0 + (uint32_t)kk * 8u, vdesc, idesc_o, kk != 0 ? 1u : acc);
+          const uint64_t vdesc = umma_desc_make(va + (uint32_t)(kk >> 2) * (kVChunk >> 4) + o, hi128);
+          if (t == 0)  // P_0 is each CTA's TMEM A operand: 8 columns per K = 16 step
+            umma2_ts(d, tmem_base + kColP0 + (uint32_t)kk * 8u, vdesc, idesc_o, kk != 0 ? 1u : acc);
           else
-            umma_ss(d, umma_desc_make(pa + (uint32_t)(kk >> 2) * ((kTileM * 128) >> 4) + o, hi128), vdesc, idesc_o,
-                    kk != 0 ? 1u : acc);
+            umma2_ss(d, umma_desc_make(p_lo + (uint32_t)(kk >> 2) * ((kTileM * 128) >> 4) + o, hi128), vdesc, idesc_o,
+                     kk != 0 ? 1u : acc);
         }
-        umma_commit(smem_u32(&bar_pvdone[t]));
+        umma2_commit_mc(smem_u32(&bar_pvdone[t]), 3);
       };
 
       mbar_wait(smem_u32(&bar_q), 0);
@@ -208,7 +200,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       if (leader) {
         issue_s(0, 0);
         issue_s(1, 0);
-        umma_commit(smem_u32(&bar_kempty[0]));
+        umma2_commit_mc(smem_u32(&bar_kempty[0]), 3);
       }
       __syncwarp();
       for (int j = 0; j < nblk; ++j) {
@@ -218,25 +210,22 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         for (int t = 0; t < 2; ++t) {
           if (jn < nblk) {
             if (t == 0) mbar_wait(smem_u32(&bar_kfull[sk]), ((uint32_t)(jn / kKS)) & 1u);
-            mbar_wait(smem_u32(&bar_sfree[t]), (uint32_t)j & 1u);  // softmax t holds S_t(j) in registers
+            mbar_wait(smem_u32(&bar_sfree[t]), (uint32_t)j & 1u);  // both CTAs' softmax t hold S_t(j) in registers
             tc_fence_after();
             if (leader) {
               issue_s(t, sk);
-              if (t == 1) umma_commit(smem_u32(&bar_kempty[sk]));
+              if (t == 1) umma2_commit_mc(smem_u32(&bar_kempty[sk]), 3);
             }
             __syncwarp();
           }
-          ATT_STAMP(2, j, t * 4 + 0);
-          mbar_wait(smem_u32(&bar_pfull[t]), (uint32_t)j & 1u);  // P_t(j) ready (and O_t rescaled)
-          ATT_STAMP(2, j, t * 4 + 1);
+          mbar_wait(smem_u32(&bar_pfull[t]), (uint32_t)j & 1u);  // P_t(j) ready in both CTAs (and O_t rescaled)
           if (t == 0) mbar_wait(smem_u32(&bar_vfull[sv]), ((uint32_t)(j / kVS)) & 1u);
           tc_fence_after();
           if (leader) {
             issue_pv(t, sv, j != 0 ? 1u : 0u);
-            if (t == 1) umma_commit(smem_u32(&bar_vempty[sv]));
+            if (t == 1) umma2_commit_mc(smem_u32(&bar_vempty[sv]), 3);
           }
           __syncwarp();
-          ATT_STAMP(2, j, t * 4 + 2);
         }
       }
     }
@@ -249,27 +238,26 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
     const uint32_t tS = tmem_base + lane_addr + (t == 0 ? kColS0 : kColS1);
     const uint32_t tO = tmem_base + lane_addr + (t == 0 ? kColO0 : kColO1);
-    const uint32_t pRow = sP + t * kPBytes + (uint32_t)r * 128u;
+    const uint32_t pRow = sP + (uint32_t)r * 128u;  // only tile 1 stages P in shared memory
     const uint32_t swz = (uint32_t)(r & 7);
     const float c = p.scale_log2;
+    const uint32_t sfree_leader = mapa_shared(smem_u32(&bar_sfree[t]), 0);
+    const uint32_t pfull_leader = mapa_shared(smem_u32(&bar_pfull[t]), 0);
 
     float m_used = -INFINITY;
     float l = 0.f;
 
     for (int j = 0; j < nblk; ++j) {
-      ATT_STAMP(t, j, 0);
       mbar_wait(smem_u32(&bar_sfull[t]), (uint32_t)j & 1u);
       tc_fence_after();
-      ATT_STAMP(t, j, 1);
       uint32_t s[128];
       tmem_ld32(tS + 0, s + 0);
       tmem_ld32(tS + 32, s + 32);
       tmem_ld32(tS + 64, s + 64);
       tmem_ld32(tS + 96, s + 96);
       tmem_ld_wait();
-      ATT_STAMP(t, j, 2);
       tc_fence_before();
-      mbar_arrive(smem_u32(&bar_sfree[t]));
+      mbar_arrive_cluster(sfree_leader);
 
       float mx0 = __uint_as_float(s[0]), mx1 = __uint_as_float(s[1]), mx2 = __uint_as_float(s[2]),
             mx3 = __uint_as_float(s[3]);
@@ -308,8 +296,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           m_used = m_new;
         }
       }
-
-      ATT_STAMP(t, j, 3);
       // p = exp2(s*c - m_used), row sum in fp32, pack pairs in place
       // scale/subtract and the row sum run as packed f32x2; of every 16 scores, 6 take the polynomial exp2 on the
       // FMA pipe and 10 the MUFU, which balances the two pipes (MUFU alone is the measured bound of this kernel)
@@ -339,11 +325,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         upk2(lsum1, b0, b1);
         l += (a0 + a1) + (b0 + b1);
       }
-      ATT_STAMP(t, j, 4);
 
       if (j > 0) mbar_wait(smem_u32(&bar_pvdone[t]), (uint32_t)(j - 1) & 1u);  // P_t smem is free again
-      ATT_STAMP(t, j, 5);
-      if (kPTmem && t == 0) {
+      if (t == 0) {
         // tile 0: P goes straight back to TMEM (row = lane, two probabilities per 32-bit column) as the A operand of PV
         const uint32_t tP = tmem_base + lane_addr + kColP0;
         tmem_st16(tP + 0, s + 0);
@@ -363,8 +347,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
         fence_proxy_async();
       }
-      mbar_arrive(smem_u32(&bar_pfull[t]));
-      ATT_STAMP(t, j, 6);
+      mbar_arrive_cluster(pfull_leader);
     }
 
     // ---- epilogue: O_t / l -> global
@@ -372,7 +355,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     tc_fence_after();
     const float inv_l = 1.0f / l;
     const int b = bh / p.H, h = bh - b * p.H;
-    const long long row = (long long)b * p.N + (long long)pair * 2 * kTileM + t * kTileM + r;
+    const long long row = (long long)b * p.N + (long long)cl * 4 * kTileM + (t * 2 + (int)rank) * kTileM + r;
     uint16_t* dst = p.out + row * ((long long)p.H * p.head_dim) + (long long)h * p.head_dim;
 #pragma unroll
     for (int cc = 0; cc < kDPad; cc += 32) {
@@ -394,50 +377,39 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     tc_fence_before();
   }
 
-  __syncthreads();
-  if (p.prof != nullptr && threadIdx.x == 0) {
-    long long gt;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
-    long long* c = p.prof + 1536 + 5 * (long long)blockIdx.x;
-    c[1] = gt; c[3] = clock64();
-  }
+
+  tc_fence_before();
+  cluster_sync_all();  // nobody exits (or frees TMEM) while the peer's UMMAs may still read this CTA's smem / TMEM
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc2(tmem_base, 512);
   }
 }
 
-// csrc/attention_pair.cu: experimental cta_group::2 variant (opt-in, L4P_ATT_PAIR=1)
+}  // namespace attpair
+
+using namespace attpair;
+
+// Host launcher, called by l4p_attention() when L4P_ATT_PAIR=1 and N is a multiple of 512.
 int attention_pair_launch(const void* q, const void* k, const void* vt, void* out, int B, int H, int N, int head_dim,
-                          float scale, int bf16, int poly, void* stream);
-
-}  // namespace l4p
-
-using namespace l4p;
-
-extern "C" int l4p_attention(const void* q, const void* k, const void* vt, void* out, int B, int H, int N,
-                             int head_dim, int head_dim_pad, float scale, int bf16, void* stream, void* prof) {
-  L4P_REQUIRE(q && k && vt && out, L4P_ERR_ARG, "l4p_attention: null pointer");
-  L4P_REQUIRE(B > 0 && H > 0, L4P_ERR_SHAPE, "l4p_attention: B=%d H=%d", B, H);
-  L4P_REQUIRE(head_dim_pad == kDPad && head_dim % 8 == 0 && head_dim > 0 && head_dim <= kDPad, L4P_ERR_SHAPE,
-              "l4p_attention: head_dim=%d pad=%d (this build: pad 96, head_dim multiple of 8 <= 96)", head_dim,
-              head_dim_pad);
-  L4P_REQUIRE(N >= 2 * kTileM && N % (2 * kTileM) == 0, L4P_ERR_SHAPE, "l4p_attention: N=%d must be a multiple of 256", N);
+                          float scale, int bf16, int poly, void* stream) {
+  L4P_REQUIRE(N >= 4 * kTileM && N % (4 * kTileM) == 0, L4P_ERR_SHAPE, "attention (CTA pair): N=%d must be a multiple of 512", N);
   CUtensorMap tmQ, tmK, tmV;
   int rc;
   {
     const uint64_t dims[2] = {(uint64_t)kDPad, (uint64_t)B * H * N};
     const uint64_t strides[1] = {(uint64_t)kDPad * 2};
-    const uint32_t box[2] = {32, (uint32_t)kTileM};
-    rc = host_make_tmap_16b(&tmQ, q, 2, dims, strides, box, 64);
+    const uint32_t boxq[2] = {32, (uint32_t)kTileM};
+    const uint32_t boxk[2] = {32, (uint32_t)kTileN / 2};
+    rc = host_make_tmap_16b(&tmQ, q, 2, dims, strides, boxq, 64);
     if (rc != L4P_OK) return rc;
-    rc = host_make_tmap_16b(&tmK, k, 2, dims, strides, box, 64);
+    rc = host_make_tmap_16b(&tmK, k, 2, dims, strides, boxk, 64);
     if (rc != L4P_OK) return rc;
   }
   {
     const uint64_t dims[2] = {(uint64_t)N, (uint64_t)B * H * kDPad};
     const uint64_t strides[1] = {(uint64_t)N * 2};
-    const uint32_t box[2] = {64, (uint32_t)kDPad};
+    const uint32_t box[2] = {64, (uint32_t)kDPad / 2};
     rc = host_make_tmap_16b(&tmV, vt, 2, dims, strides, box, 128);
     if (rc != L4P_OK) return rc;
   }
@@ -445,32 +417,19 @@ extern "C" int l4p_attention(const void* q, const void* k, const void* vt, void*
   p.out = (uint16_t*)out;
   p.B = B; p.H = H; p.N = N; p.head_dim = head_dim;
   p.scale_log2 = scale * 1.4426950408889634f;
-  p.prof = (long long*)prof;
-  // POLY = number of score pairs (of every 8) whose exp2 runs as an FMA-pipe polynomial instead of MUFU
-  static int poly = -1;
-  if (poly < 0) {
-    const char* e = getenv("L4P_ATT_POLY");
-    poly = e ? atoi(e) : 2;
-    if (poly < 0 || poly > 3) poly = 0;
-  }
-  static int pair_mode = -1;
-  if (pair_mode < 0) {
-    const char* e = getenv("L4P_ATT_PAIR");
-    pair_mode = (e && atoi(e) == 1) ? 1 : 0;
-  }
-  if (pair_mode == 1 && prof == nullptr && N % (4 * kTileM) == 0)
-    return attention_pair_launch(q, k, vt, out, B, H, N, head_dim, scale, bf16, poly, stream);
   typedef void (*KFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const AttParams);
-  static const KFn table[2][4] = {
-      {attention_kernel<false, 0>, attention_kernel<false, 1>, attention_kernel<false, 2>, attention_kernel<false, 3>},
-      {attention_kernel<true, 0>, attention_kernel<true, 1>, attention_kernel<true, 2>, attention_kernel<true, 3>}};
-  KFn kfn = table[bf16 ? 1 : 0][poly];
-  static bool attr_set[2][4] = {};
-  if (!attr_set[bf16 ? 1 : 0][poly]) {
+  static const KFn table[2][2] = {{attention_pair_kernel<false, 0>, attention_pair_kernel<false, 2>},
+                                  {attention_pair_kernel<true, 0>, attention_pair_kernel<true, 2>}};
+  const int pi = poly == 0 ? 0 : 1;
+  KFn kfn = table[bf16 ? 1 : 0][pi];
+  static bool attr_set[2][2] = {};
+  if (!attr_set[bf16 ? 1 : 0][pi]) {
     L4P_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmem));
-    attr_set[bf16 ? 1 : 0][poly] = true;
+    attr_set[bf16 ? 1 : 0][pi] = true;
   }
-  const int grid = B * H * (N / (2 * kTileM));
+  const int grid = B * H * (N / (4 * kTileM)) * 2;
   L4P_CHECK_CUDA(launch_pdl(kfn, dim3(grid), dim3(kAttThreads), (size_t)kAttSmem, (cudaStream_t)stream, tmQ, tmK, tmV, p));
   return L4P_OK;
 }
+
+}  // namespace l4p
