@@ -42,6 +42,9 @@ constexpr float kRescaleThreshold = 8.0f;  // log2 units
 #ifndef L4P_ATT_P_TMEM
 #define L4P_ATT_P_TMEM 1
 #endif
+#ifndef L4P_ATT_S_FIRST
+#define L4P_ATT_S_FIRST 0
+#endif
 constexpr bool kPTmem = L4P_ATT_P_TMEM != 0;  // tile 0's P through the 64 spare TMEM columns (TS-mode UMMA)
 
 struct AttParams {
@@ -214,6 +217,34 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       for (int j = 0; j < nblk; ++j) {
         const int jn = j + 1;
         const int sk = jn % kKS, sv = j % kVS;
+#if L4P_ATT_S_FIRST
+        // experiment (build with L4P_NVCC_EXTRA=-DL4P_ATT_S_FIRST=1): both tiles' S(j+1) before the first PV(j), so that
+        // S_1(j+1) does not queue behind P_0(j)
+        if (jn < nblk) {
+          mbar_wait(smem_u32(&bar_kfull[sk]), ((uint32_t)(jn / kKS)) & 1u);
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            mbar_wait(smem_u32(&bar_sfree[t]), (uint32_t)j & 1u);
+            tc_fence_after();
+            if (leader) {
+              issue_s(t, sk);
+              if (t == 1) umma_commit(smem_u32(&bar_kempty[sk]));
+            }
+            __syncwarp();
+          }
+        }
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          mbar_wait(smem_u32(&bar_pfull[t]), (uint32_t)j & 1u);
+          if (t == 0) mbar_wait(smem_u32(&bar_vfull[sv]), ((uint32_t)(j / kVS)) & 1u);
+          tc_fence_after();
+          if (leader) {
+            issue_pv(t, sv, j != 0 ? 1u : 0u);
+            if (t == 1) umma_commit(smem_u32(&bar_vempty[sv]));
+          }
+          __syncwarp();
+        }
+#else
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
           if (jn < nblk) {
@@ -238,6 +269,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           __syncwarp();
           ATT_STAMP(2, j, t * 4 + 2);
         }
+#endif
       }
     }
   } else {
