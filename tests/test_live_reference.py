@@ -184,3 +184,94 @@ def test_track_head_prompt_features_and_labels(ref, cpu_kernels):
         assert rel_l2(got["track_2d_prompt_features_bnc"], want["track_2d_prompt_features_bnc"]) < 5e-3
         assert rel_l2(got["track_2d_enc_features_with_track_history_bnpc"],
                       want["track_2d_enc_features_with_track_history_bnpc"]) < 5e-3
+
+
+@torch.no_grad()
+def test_full_size_dpt_heads_reference_oracle_mirror(ref, cpu_kernels):
+    """At the model's real size (1408-channel taps of a 16x224x224 window, hooks 14/21/28/36 of a 41-entry list) the
+    unmodified reference, the oracle restatement and the host mirror (per-op torch definitions) agree: pins the oracle the
+    GPU tests compare against at the size they use it, not only at the tiny golden size."""
+    from l4p_b200.models.task_heads import dense_heads as D
+    from oracle import l4p_oracle as O
+
+    hooks = [14, 21, 28, 36]
+    feats = [None] * 41
+    for n, i in enumerate(hooks):
+        feats[i] = rnd((1, 2048, 1408), 70 + n)
+    # depth head: full 224x224 output
+    rh, oh = _pair(ref["D"].VideoMAEDepthDPTHead, D.VideoMAEDepthDPTHead, 81, "depth", depth_fn="exp", hooks_idx=hooks,
+                   align_window_overlap_fn="inverse")
+    want = rh.forward(feats, img_info=(16, 224, 224))["depth_est_b1thw"]
+    sd = {k: v.clone() for k, v in rh.state_dict().items()}
+    orc = torch.exp(O.dpt_forward(sd, "task_head.dpt.", feats, hooks, img_info=(16, 224, 224)))
+    got = oh.forward(feats, img_info=(16, 224, 224))["depth_est_b1thw"]
+    assert want.shape == orc.shape == got.shape == (1, 1, 16, 224, 224)
+    assert rel_l2(orc, want) < 2e-5, rel_l2(orc, want)
+    assert rel_l2(got, want) < 1e-3 and rel_l2(torch.log(got), torch.log(want)) < 2e-3, rel_l2(got, want)
+    # camera-ray head: other reassemble / fusion scale factors, fixed 16x16x16 output
+    rc, oc = _pair(ref["D"].VideoMAETraj3DDPTHead, D.VideoMAETraj3DDPTHead, 82, "traj3d", hooks_idx=hooks,
+                   use_intrinsics=False, fixed_intrinsics=True)
+    want = rc.task_head(feats, (16, 224, 224))
+    sd = {k: v.clone() for k, v in rc.state_dict().items()}
+    orc = O.dpt_forward(sd, "task_head.dpt.", feats, hooks, img_info=(16, 224, 224), actpost=O.CAMRAY_ACTPOST,
+                        fusion=O.CAMRAY_FUSION, output_size=(16, 16, 16))
+    got = oc.rays(feats, (16, 224, 224))
+    assert want.shape == orc.shape == got.shape == (1, 6, 16, 16, 16)
+    assert rel_l2(orc, want) < 2e-5
+    assert rel_l2(got, want) < 1.5e-3, rel_l2(got, want)
+
+
+@torch.no_grad()
+def test_full_size_track_head_reference_oracle_mirror(ref, cpu_kernels):
+    """Track head at its real size (2048 x 1408 tokens, 8 heads of 88 / 176, 16x64x64 mask logits -> 224x224 read-out) for
+    two queries, first-window form (shared tokens) and with per-query history: reference == oracle == host mirror."""
+    from l4p_b200.models.task_heads.sparse_heads import VideoMAETrack2DSamHead
+    from oracle import l4p_oracle as O
+
+    kw = dict(task_name="track_2d", estimate_vis=True, estimate_depth=True, sam_head_depth=2, num_point_embeddings=2,
+              modify_pointlabels_for_windowing=True, prompt_using_features=True, attend_to_past=True,
+              estimation_directions=[1], depth_fn="exp", vis_fn="linear")
+    rt, ot = _pair(ref["S"].VideoMAETrack2DSamHead, VideoMAETrack2DSamHead, 91, **kw)
+    sd = {k: v.clone() for k, v in rt.state_dict().items()}
+    feat = rnd((1, 2048, 1408), 92)
+    q = torch.tensor([[[0.5, 50.5, 60.5], [6.5, 150.5, 100.5]]])
+    lab = torch.tensor([[1.0, 2.0]])
+    pf = rnd((1, 2, 1408), 93, 0.5)
+    pl = torch.tensor([[0.0, 1.0]])
+    hist = rnd((1, 2, 2048, 1408), 94, 0.3)
+    for enc in (feat, feat.unsqueeze(1) + hist):
+        want = rt.forward([enc], q, lab, pf, pl)
+        orc = O.track_head_window(sd, "", enc, q, lab, pf, pl)
+        got = ot.forward([enc], q, lab, pf, pl)
+        for k in ("track_2d_traj_est_bn2t", "track_2d_vis_est_bn1t", "track_2d_depth_est_bn1t",
+                  "track_2d_prompt_features_bnc", "track_2d_enc_features_with_track_history_bnpc"):
+            assert want[k].shape == orc[k].shape == got[k].shape, k
+            assert rel_l2(orc[k], want[k]) < 5e-5, (k, rel_l2(orc[k], want[k]))
+        assert (got["track_2d_traj_est_bn2t"] - want["track_2d_traj_est_bn2t"]).abs().max() < 0.05      # pixels of 224
+        assert (got["track_2d_vis_est_bn1t"] - want["track_2d_vis_est_bn1t"]).abs().max() < 5e-3
+        assert rel_l2(got["track_2d_depth_est_bn1t"], want["track_2d_depth_est_bn1t"]) < 2e-3
+        assert rel_l2(got["track_2d_prompt_features_bnc"], want["track_2d_prompt_features_bnc"]) < 5e-3
+        assert rel_l2(got["track_2d_enc_features_with_track_history_bnpc"],
+                      want["track_2d_enc_features_with_track_history_bnpc"]) < 5e-3
+
+
+@torch.no_grad()
+def test_full_width_encoder_reference_oracle_mirror(ref, cpu_kernels):
+    """Two ViT-giant blocks at full width on one 16x224x224 window (what `__graft_entry__.smoke()` runs on the GPU against
+    the oracle): tubelet patch embed + position table, 16 heads of 88 (padded to 96 in the kernel layout), MLP 6144, final
+    norm on the last entry - reference == oracle == host mirror."""
+    from l4p_b200.models.videomae import VideoMAEEncoder
+    from oracle import l4p_oracle as O
+    from tests.util import synth_rgb
+
+    kw = dict(img_size=224, patch_size=14, embed_dim=1408, depth=2, num_heads=16, mlp_ratio=48 / 11, qkv_bias=True,
+              norm_layer=partial(torch.nn.LayerNorm, eps=1e-6), init_values=0.0, tubelet_size=2, all_frames=16)
+    renc, oenc = _pair(ref["V"].VideoMAEEncoder, VideoMAEEncoder, 0, **kw)
+    rgb = synth_rgb(1, 16)
+    want = renc(rgb)
+    orc = O.encoder_forward({k: v.clone() for k, v in renc.state_dict().items()}, "", rgb, depth=2)
+    got = oenc(rgb)
+    assert len(want) == len(orc) == len(got) == 3
+    for i in range(3):
+        assert rel_l2(orc[i], want[i]) < 2e-5, (i, rel_l2(orc[i], want[i]))
+        assert rel_l2(got[i], want[i]) < 1.5e-3, (i, rel_l2(got[i], want[i]))      # smoke()'s bound on the GPU
