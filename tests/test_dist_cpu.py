@@ -132,4 +132,6 @@ def test_two_rank_window_sharded_model_matches_unsharded(tmp_path, monkeypatch):
             assert rel_l2(got["depth"], ref["depth_est_b1thw"]) < 1e-3
             assert rel_l2(got["flow"], ref["flow_2d_backward_est_b2thw"]) < 1e-3
         a, b = (torch.load(tmp_path / f"sharded_{T}_{r}.pt") for r in range(world))
-        assert torch.equal(a["depth"], b["depth"]) and torch.equal(a["flow"], b["flow"])   # identical on every rank
+        # every rank ends with the same result: flow is pure data movement after the gather (bit-equal); depth goes through
+        # the overlap least-squares solve, whose multi-threaded CPU reductions are not bit-reproducible across processes
+        assert torch.equal(a["flow"], b["flow"]) and rel_l2(a["depth"], b["depth"]) < 1e-6
