@@ -275,3 +275,73 @@ def test_full_width_encoder_reference_oracle_mirror(ref, cpu_kernels):
     for i in range(3):
         assert rel_l2(orc[i], want[i]) < 2e-5, (i, rel_l2(orc[i], want[i]))
         assert rel_l2(got[i], want[i]) < 1.5e-3, (i, rel_l2(got[i], want[i]))      # smoke()'s bound on the GPU
+
+
+@torch.no_grad()
+def test_whole_model_orchestrator_vs_reference(ref, cpu_kernels, monkeypatch):
+    """`L4P_VideoMAE.forward` of the unmodified reference (its hard-wired ViT-giant constructor call answered with the tiny
+    encoder) against the drop-in on a 10-frame clip = 4 sliding windows, all task heads, per-task alignment
+    (l4p_videomae.py:256-330): same output keys, shapes, dtypes; values to 16-bit operand noise; tracker state exact."""
+    from l4p_b200.models import l4p_videomae as OV
+    from l4p_b200.models.task_heads import dense_heads as D
+    from l4p_b200.models.task_heads.sparse_heads import VideoMAETrack2DSamHead
+    from l4p_b200.models.videomae import VideoMAEEncoder
+
+    RV, RD, RS = ref["V"], ref["D"], ref["S"]
+    renc, oenc = _pair(RV.VideoMAEEncoder, VideoMAEEncoder, 101, **ENC_KW)
+    specs = {
+        "depth": (RD.VideoMAEDepthDPTHead, D.VideoMAEDepthDPTHead, ("depth",),
+                  dict(depth=3, embed_dim=64, depth_fn="exp", hooks_idx=HOOKS, align_window_overlap_fn="inverse")),
+        "flow_2d_backward": (RD.VideoMAEFlowDPTHead, D.VideoMAEFlowDPTHead, ("flow_2d_backward",),
+                             dict(out_nchan=2, depth=3, embed_dim=64, hooks_idx=HOOKS)),
+        "dyn_mask": (RD.VideoMAEDynMaskDPTHead, D.VideoMAEDynMaskDPTHead, ("dyn_mask",),
+                     dict(out_nchan=1, depth=3, embed_dim=64, apply_fn="linear", hooks_idx=HOOKS)),
+        "track_2d": (RS.VideoMAETrack2DSamHead, VideoMAETrack2DSamHead, (),
+                     dict(task_name="track_2d", prompt_embed_dim=64, image_size=IMG, estimate_vis=True, estimate_depth=True,
+                          sam_head_depth=2, num_point_embeddings=2, modify_pointlabels_for_windowing=True,
+                          prompt_using_features=True, attend_to_past=True, estimation_directions=[1], depth_fn="exp",
+                          vis_fn="linear")),
+    }
+    rheads, oheads = {}, {}
+    for seed, (task, (rc, oc, args, kw)) in enumerate(specs.items(), start=102):
+        rheads[task], oheads[task] = _pair(rc, oc, seed, *args, **kw)
+    monkeypatch.setattr(RV, "VideoMAEEncoder", lambda **kw: renc)        # the reference constructs ViT-giant unconditionally
+    common = dict(window_size=IMG, window_stride_T=2, always_use_windowed_version=True, joint_alignment=True)
+    rmodel = RV.L4P_VideoMAE(torch.nn.ModuleDict(rheads), **common).eval()
+    omodel = OV.L4P_VideoMAE(torch.nn.ModuleDict(oheads), device="meta", **common)
+    omodel.video_encoder = oenc
+    T = 10
+    tasks = list(specs)
+    q = torch.tensor([[[0.5, 10.5, 12.5], [3.5, 40.5, 30.5], [8.5, 28.0, 28.0], [5.5, 20.5, 44.5], [11.5, 9.0, 9.0]]])
+    data = dict(rgb_b3thw=rnd((1, 3, T, 56, 56), 110), intrinsics_b44t=torch.eye(4)[None, :, :, None].repeat(1, 1, 1, T),
+                track_2d_pointquerries_bn3=q, track_2d_pointlabels_bn=torch.ones(1, 5), img_info=IMG, seq_name=["clip"])
+    want = rmodel.forward(dict(data), tasks)     # joint_alignment=True but no camray task -> per-task path (:318-328)
+    got = omodel.forward(dict(data), tasks)
+    assert set(want) == set(got)
+    assert len(got["enc_features_bpc_2dlist"]) == len(want["enc_features_bpc_2dlist"]) == 4
+    for k, w in want.items():
+        if k == "enc_features_bpc_2dlist":
+            continue
+        g = got[k]
+        assert g.shape == w.shape and g.dtype == w.dtype, k
+        if k.startswith("track_2d"):
+            assert torch.equal(g == 0, w == 0) and torch.equal(g == -10, w == -10), f"{k}: written-frame mask differs"
+    assert rel_l2(got["depth_est_b1thw"], want["depth_est_b1thw"]) < 1e-3
+    assert rel_l2(got["flow_2d_backward_est_b2thw"], want["flow_2d_backward_est_b2thw"]) < 1.5e-3
+    assert rel_l2(got["dyn_mask_est_b1thw"], want["dyn_mask_est_b1thw"]) < 1.5e-3
+    assert (got["track_2d_traj_est_bn2t"] - want["track_2d_traj_est_bn2t"]).abs().max() < 0.02
+    assert (got["track_2d_vis_est_bn1t"] - want["track_2d_vis_est_bn1t"]).abs().max() < 3e-3
+    assert rel_l2(got["track_2d_depth_est_bn1t"], want["track_2d_depth_est_bn1t"]) < 2e-3
+    # single-window dispatch (T == window length, always_use_windowed_version=False -> forward_single_window, :262-263):
+    # heads are called as head(enc_features_bpc_list=..., **data), outputs carry `enc_features_bpc_list`
+    rmodel.always_use_windowed_version = omodel.always_use_windowed_version = False
+    one = dict(data, rgb_b3thw=data["rgb_b3thw"][:, :, :4].contiguous(), intrinsics_b44t=data["intrinsics_b44t"][..., :4],
+               track_2d_pointquerries_bn3=q[:, :2], track_2d_pointlabels_bn=torch.ones(1, 2))
+    want1, got1 = rmodel.forward(dict(one), tasks), omodel.forward(dict(one), tasks)
+    assert set(want1) == set(got1) and "enc_features_bpc_list" in got1
+    for k, w in want1.items():
+        if k == "enc_features_bpc_list":
+            continue
+        assert got1[k].shape == w.shape, k
+        tol = 0.02 if "traj" in k else 5e-3
+        assert (got1[k] - w).abs().max() < tol * max(1.0, float(w.abs().max())), (k, (got1[k] - w).abs().max())
