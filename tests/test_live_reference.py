@@ -345,3 +345,98 @@ def test_whole_model_orchestrator_vs_reference(ref, cpu_kernels, monkeypatch):
         assert got1[k].shape == w.shape, k
         tol = 0.02 if "traj" in k else 5e-3
         assert (got1[k] - w).abs().max() < tol * max(1.0, float(w.abs().max())), (k, (got1[k] - w).abs().max())
+
+
+class _StubHead(torch.nn.Module):
+    """A task head that returns prepared per-window outputs: lets the REFERENCE's joint_windowed_estimation and
+    KabaschUmeyama3DAligner run live on a geometrically consistent synthetic scene."""
+
+    def __init__(self, task_name, task_suffix, outputs):
+        super().__init__()
+        self.task_name, self.task_suffix, self.outputs, self.calls = task_name, task_suffix, outputs, []
+
+    def _out(self, win_id):
+        return {f"{self.task_name}_est_{self.task_suffix}": self.outputs[win_id].clone()}
+
+    def forward(self, feats, img_info=IMG, intrinsics_b44t=None, win_id=None, **kw):
+        w = int(feats[0].item()) if win_id is None else win_id       # the mirror's depth call carries no win_id
+        self.calls.append(w)
+        return self._out(w)
+
+    # the drop-in asks the camera head for rays and poses separately (pose solves are stateful per window)
+    def rays(self, feats, img_info=IMG):
+        return feats[0]
+
+    def pose_from_rays(self, rays, img_info, intrinsics_b44t=None, win_id=None, **kw):
+        return self._out(win_id)
+
+
+@torch.no_grad()
+def test_joint_alignment_chain_live_reference_on_consistent_scene(ref, cpu_kernels, monkeypatch):
+    """Two overlapping windows whose depth maps and camera poses describe ONE scene in two similarity frames
+    (x = s R x' + t). The reference's own chain (dense_heads.py:360-492, aligner.py:158-265; scikit-image is absent, so its
+    `ransac` / `SimilarityTransform` are answered by the oracle's restatement) and the drop-in's chain must both bring
+    window 1 into window 0's frame: depth * s, pose -> [R R' | s R t' + t], later windows written over the buffer."""
+    import numpy as np
+
+    import l4p.models.aligner as RA
+    from l4p_b200.models.task_heads import dense_heads as D
+    from oracle import l4p_oracle as O
+
+    class SimT:
+        def __init__(self, params):
+            self.params = params
+            self.rotation, self.translation = params[:3, :3], params[:3, 3]
+            self.scale = float(np.cbrt(np.linalg.det(params[:3, :3])))
+
+    def ransac(data, model_class, min_samples, residual_threshold, stop_probability, max_trials):
+        Tm, inl = O.similarity_ransac(data[0].astype(np.float64), data[1].astype(np.float64), float(residual_threshold),
+                                      min_samples=min_samples, max_trials=max_trials, stop_probability=stop_probability)
+        return SimT(Tm), inl
+
+    monkeypatch.setattr(RA, "ransac", ransac)
+    monkeypatch.setattr(RA, "SimilarityTransform", SimT)
+    gen = torch.Generator().manual_seed(3)
+    T, Tw, starts = 6, 4, torch.tensor([0, 2])
+    H = W = 56
+    K = torch.eye(4)
+    K[0, 0] = K[1, 1] = 50.0
+    K[0, 2] = K[1, 2] = 28.0
+    intr = K[None, :, :, None].repeat(1, 1, 1, T)
+    yy, xx = torch.meshgrid(torch.arange(H, dtype=torch.float32), torch.arange(W, dtype=torch.float32), indexing="ij")
+    depth = torch.stack([2.0 + 0.3 * torch.sin(xx / 9 + t) + 0.2 * torch.cos(yy / 7 - t) for t in range(T)])[None, None]
+    pose = torch.zeros(1, 4, 4, T)
+    for t in range(T):
+        qm, _ = torch.linalg.qr(torch.eye(3) + 0.1 * torch.randn(3, 3, generator=gen))
+        if torch.linalg.det(qm) < 0:
+            qm[:, 0] = -qm[:, 0]
+        pose[0, :3, :3, t], pose[0, :3, 3, t], pose[0, 3, 3, t] = qm, torch.randn(3, generator=gen) * 0.2, 1.0
+    s_true = 1.6
+    Rm, _ = torch.linalg.qr(torch.eye(3) + 0.3 * torch.randn(3, 3, generator=gen))
+    if torch.linalg.det(Rm) < 0:
+        Rm[:, 0] = -Rm[:, 0]
+    t_true = torch.tensor([0.4, -0.3, 0.2])
+    # window 1 lives in the primed frame: x' = R^T (x - t) / s
+    pose1 = pose[..., 2:6].clone()
+    pose1[0, :3, :3] = torch.einsum("ji,jkt->ikt", Rm, pose[0, :3, :3, 2:6])
+    pose1[0, :3, 3] = torch.einsum("ji,jt->it", Rm, pose[0, :3, 3, 2:6] - t_true[:, None]) / s_true
+    d_w = [depth[:, :, 0:4], depth[:, :, 2:6] / s_true]
+    p_w = [pose[..., 0:4].reshape(1, 16, Tw), pose1.reshape(1, 16, Tw)]
+    feats = [[torch.tensor([0.0])], [torch.tensor([1.0])]]
+
+    def heads():
+        return torch.nn.ModuleDict(dict(depth=_StubHead("depth", "b1thw", d_w), camray=_StubHead("traj3d", "b16t", p_w)))
+
+    np.random.seed(0)
+    want = ref["D"].joint_windowed_estimation(["depth", "camray"], heads(), enc_features_bpc_2dlist=feats, time_strides=starts,
+                                              intrinsics_b44t=intr, img_info=IMG)
+    got = D.joint_windowed_estimation(["depth", "camray"], heads(), feats, time_strides=starts, intrinsics_b44t=intr,
+                                      img_info=IMG)
+    assert set(want) == set(got) == {"depth_est_b1thw", "traj3d_est_b16t", "traj3d_intrinsics_est_b16t"}
+    for out in (want, got):      # both recover the one consistent scene
+        assert rel_l2(out["depth_est_b1thw"], depth) < 1e-4
+        assert (out["traj3d_est_b16t"] - pose.reshape(1, 16, T)).abs().max() < 1e-3
+        assert torch.equal(out["traj3d_intrinsics_est_b16t"], intr.reshape(1, 16, T))
+    for k in want:
+        assert got[k].shape == want[k].shape and got[k].dtype == want[k].dtype
+        assert (got[k] - want[k]).abs().max() < 1e-3, k
