@@ -1,8 +1,9 @@
 """TEST INFRASTRUCTURE ONLY (see oracle/l4p_oracle.py): CPU restatement of the rgb branch of the reference's dataset
 pipeline, `l4p/data/l4p_dataset_mini.py`, with the same torch calls the reference makes.
 
-Parity unpinned: the reference's data module cannot be imported here (kornia / mediapy / lightning are not installed),
-so this file follows its source line by line instead of being checked against a run of it."""
+Pinned: bit-exact against the UNMODIFIED reference `L4PDataset.__getitem__` (imported through oracle/ref_loader.py with a
+kornia stub; the rgb key never touches it) on seeded uint8 clips - committed fixture tests/golden/golden_preprocess.pt
+(tests/golden/make_golden_preprocess.py) and a live run when /root/reference is present (tests/test_oracle_golden.py)."""
 from __future__ import annotations
 
 from math import ceil

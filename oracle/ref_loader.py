@@ -1,6 +1,6 @@
 """TEST INFRASTRUCTURE ONLY. Imports the UNMODIFIED reference from /root/reference (build container only;
 the path does not exist on the GPU box) behind `sys.modules` shims for the third-party packages that are not
-installed here: timm.models.layers/registry, skimage.measure/transform, lightning.
+installed here: timm.models.layers/registry, skimage.measure/transform, kornia.morphology, lightning.
 
 Used by tests/golden/make_golden.py to generate fixtures and by the CPU tests that pin `oracle/l4p_oracle.py`
 against the real reference.
@@ -59,6 +59,16 @@ def _install_shims() -> None:
         transform.SimilarityTransform = _absent
         sk.measure, sk.transform = measure, transform
         sys.modules.update({"skimage": sk, "skimage.measure": measure, "skimage.transform": transform})
+    if "kornia" not in sys.modules:   # l4p/data/l4p_dataset_mini.py:13 (used for segmentation masks only, not the rgb key)
+        kornia = types.ModuleType("kornia")
+        morphology = types.ModuleType("kornia.morphology")
+
+        def erosion(*a, **k):
+            raise RuntimeError("kornia is not installed; mask erosion cannot run through the reference here")
+
+        morphology.erosion = erosion
+        kornia.morphology = morphology
+        sys.modules.update({"kornia": kornia, "kornia.morphology": morphology})
     if "lightning" not in sys.modules:
         L = types.ModuleType("lightning")
 

@@ -204,3 +204,29 @@ def test_oracle_vs_live_reference_tiny():
         ref = enc(rgb)
         got = O.encoder_forward({k: v for k, v in enc.state_dict().items()}, "", rgb, depth=3, num_heads=4)
     close(torch.stack(got), torch.stack(ref))
+
+
+def test_preprocess_oracle_vs_reference_dataset_golden():
+    """N3: oracle/preprocess_oracle.py against the fixture made by running the unmodified reference dataset pipeline
+    (mirror pad / single-frame repeat, trilinear resize, centre crop, normalise): bit-exact on the stored sub-samples."""
+    from oracle.preprocess_oracle import preprocess
+    from tests.golden.make_golden_preprocess import CASES, frames_for
+
+    gp = torch.load(GOLD / "golden_preprocess.pt")
+    for i, case in enumerate(CASES):
+        x = preprocess(frames_for(case), case[3], case[4])[0]
+        assert list(x.shape) == gp[f"{i}/shape"].tolist()
+        assert torch.equal(x[:, ::5, ::37, ::41], gp[f"{i}/sub"]), f"case {i}"
+        assert abs(float(x.double().sum()) - float(gp[f"{i}/sum"])) <= 1e-9 * abs(float(gp[f"{i}/sum"])) + 1e-6
+
+
+@pytest.mark.skipif(not __import__("oracle.ref_loader", fromlist=["x"]).available(), reason="reference tree not present")
+def test_preprocess_oracle_vs_live_reference_dataset():
+    from oracle.preprocess_oracle import preprocess
+    from tests.golden.make_golden_preprocess import CASES, frames_for, reference_item
+
+    for case in CASES[:4]:
+        frames = frames_for(case)
+        item = reference_item(frames, case[3], case[4])
+        assert torch.equal(preprocess(frames, case[3], case[4])[0], item["rgb_b3thw"])
+        assert item["ori_video_len"] == case[0]
