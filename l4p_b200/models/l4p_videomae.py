@@ -76,6 +76,11 @@ class L4P_VideoMAE(torch.nn.Module):
         self.shard_windows = bool(enabled)
         self.window_shard_group = group
 
+    def enable_query_sharding(self, enabled: bool = True, group: Any = None) -> None:
+        """Shard the track queries across the ranks of `group`: every rank encodes the clip, tracks its slice of the queries
+        and one all-gather returns all tracks everywhere (the demo's 625-query grids are 5 chunks of 128)."""
+        self.task_heads["track_2d"].enable_query_sharding(enabled, group)
+
     def encode_features(self, data: Dict[str, Any]):
         """Generates video encoder features for a single window (l4p_videomae.py:222-232)."""
         return self.video_encoder(data["rgb_b3thw"])

@@ -201,11 +201,18 @@ class VideoMAETrack2DSamHead(nn.Module):
         self.processed_video_mask_token = P.Embedding(1, prompt_embed_dim, device)
         self.processed_video_features_proj = P.Linear(prompt_embed_dim, prompt_embed_dim, device=device)
         self.task_suffix = "_track_2d"
+        # multi-GPU: shard the (independent) queries across the ranks of a process group (enable_query_sharding)
+        self.shard_queries, self.query_shard_group = False, None
         self._packed = None
         self.register_load_state_dict_post_hook(lambda m, k: m.invalidate())
 
     def invalidate(self) -> None:
         self._packed = None
+
+    def enable_query_sharding(self, enabled: bool = True, group=None) -> None:
+        """Track only this rank's contiguous slice of the queries in `forward_windowed` and all-gather the tracks
+        (every rank still needs the encoder features of all windows: combine with clip sharding, not window sharding)."""
+        self.shard_queries, self.query_shard_group = bool(enabled), group
 
     # ------------------------------------------------------------------ weight packing
     def prepare(self, device, dt):
@@ -464,6 +471,25 @@ class VideoMAETrack2DSamHead(nn.Module):
         """Query chunking by max_queries (sparse_heads.py:162-211)."""
         kwargs.pop("_batched_windows", None)
         N = track_2d_pointquerries_bn3.shape[1]
+        if self.shard_queries:
+            # multi-GPU (SURVEY.md §8e): queries are independent -> this rank tracks its contiguous slice (chunked by
+            # max_queries as usual), ONE all-gather returns the tracks of all queries on every rank
+            import torch.distributed as dist
+            from ...parallel import contiguous_partition, gather_query_outputs
+            assert dist.is_initialized(), "query sharding needs an initialised torch.distributed process group"
+            grp = self.query_shard_group
+            start, count = contiguous_partition(N, dist.get_world_size(grp))[dist.get_rank(grp)]
+            keys = [f"{self.task_name}_traj_est_bn2t", f"{self.task_name}_vis_est_bn1t", f"{self.task_name}_depth_est_bn1t"]
+            local = [None] * len(keys)
+            if count > 0:
+                self.shard_queries = False
+                try:
+                    mine = self.forward_windowed(enc_features_bpc_2dlist, track_2d_pointquerries_bn3[:, start:start + count],
+                                                 track_2d_pointlabels_bn[:, start:start + count], time_strides, **kwargs)
+                finally:
+                    self.shard_queries = True
+                local = [mine[k] for k in keys]
+            return dict(zip(keys, gather_query_outputs(local, N, grp)))
         if N < self.max_queries:
             return self.forward_windowed_core(enc_features_bpc_2dlist, track_2d_pointquerries_bn3,
                                               track_2d_pointlabels_bn, time_strides, **kwargs)

@@ -88,6 +88,38 @@ def gather_window_outputs(local: Sequence[Sequence[torch.Tensor]], shard: Window
     return out
 
 
+def gather_query_outputs(local: Sequence[Optional[torch.Tensor]], n_queries: int, group=None) -> List[torch.Tensor]:
+    """Track queries are independent (sparse_heads.py:181-211): rank r tracks the contiguous slice
+    `contiguous_partition(n_queries, world)[r]` of the queries. local[k]: this rank's output k, shape [1, n_r, ...] (None
+    when the rank has no query). Returns every output for ALL queries ([1, n_queries, ...], query order preserved),
+    identical on every rank; all outputs travel in ONE all_gather_into_tensor."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    parts = contiguous_partition(n_queries, world)
+    per = -(-n_queries // world)
+    count = parts[rank][1]
+    meta = [(tuple(t.shape[2:]), t.dtype) for t in local] if count > 0 else None
+    metas: List[Any] = [None] * world
+    dist.all_gather_object(metas, meta, group=group)
+    meta0 = next(m for m in metas if m is not None)
+    sizes = [int(torch.tensor(s).prod()) if len(s) else 1 for s, _ in meta0]
+    unit = sum(sizes)
+    if count > 0:
+        dev = local[0].device
+    else:
+        dev = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
+    packed = torch.zeros(per, unit, device=dev, dtype=torch.float32)
+    if count > 0:
+        packed[:count] = torch.cat([t[0].reshape(count, -1).float() for t in local], dim=1)
+    gathered = torch.empty(world * per, unit, device=dev, dtype=torch.float32)
+    dist.all_gather_into_tensor(gathered, packed, group=group)
+    rows = torch.cat([gathered[r * per:r * per + cnt] for r, (_, cnt) in enumerate(parts)], dim=0)   # [n_queries, unit]
+    out, off = [], 0
+    for n, (shape, dtype) in zip(sizes, meta0):
+        out.append(rows[:, off:off + n].reshape(1, n_queries, *shape).to(dtype))
+        off += n
+    return out
+
+
 def gather_clip_outputs(packed: torch.Tensor, group=None) -> torch.Tensor:
     """cfg 3: every rank contributes the packed head outputs of its clips ([clips_per_rank, unit]); returns
     [world, clips_per_rank, unit] on every rank (clip i sits at [i % world, i // world])."""

@@ -135,3 +135,58 @@ def test_two_rank_window_sharded_model_matches_unsharded(tmp_path, monkeypatch):
         # every rank ends with the same result: flow is pure data movement after the gather (bit-equal); depth goes through
         # the overlap least-squares solve, whose multi-threaded CPU reductions are not bit-reproducible across processes
         assert torch.equal(a["flow"], b["flow"]) and rel_l2(a["depth"], b["depth"]) < 1e-6
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Track queries sharded across ranks (queries are independent): `enable_query_sharding()` on the tiny
+# golden tracker, two gloo ranks, 3 windows with the sliding-window memory -> every rank returns all tracks.
+# ---------------------------------------------------------------------------------------------------------------
+def _sharded_tracker_worker(rank, world, port, n_queries, out_dir):
+    import pytest
+
+    from tests import emu
+    from tests import test_host_emulated as H
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    mp_ = pytest.MonkeyPatch()
+    emu.install(mp_)
+    try:
+        enc = H._encoder()
+        starts = torch.arange(0, 8 - 4 + 1, 2)
+        f2d = H._windows(enc, H.rnd((1, 3, 8, 56, 56), 16), starts)
+        trk = H._tracker(max_queries=2)
+        trk.enable_query_sharding(True)
+        q = _queries(n_queries)
+        out = trk.forward_windowed(f2d, q, torch.ones(1, n_queries), time_strides=starts)
+        torch.save({k: v for k, v in out.items()}, os.path.join(out_dir, f"tracks_{n_queries}_{rank}.pt"))
+        dist.barrier()
+    finally:
+        mp_.undo()
+        dist.destroy_process_group()
+
+
+def _queries(n):
+    g = torch.Generator().manual_seed(77)
+    return torch.cat([torch.randint(0, 7, (1, n, 1), generator=g).float() + 0.5, torch.rand(1, n, 2, generator=g) * 50 + 3], -1)
+
+
+def test_two_rank_query_sharded_tracker_matches_unsharded(tmp_path, monkeypatch):
+    from tests import emu
+    from tests import test_host_emulated as H
+
+    world = 2
+    emu.install(monkeypatch)
+    enc = H._encoder()
+    starts = torch.arange(0, 8 - 4 + 1, 2)
+    f2d = H._windows(enc, H.rnd((1, 3, 8, 56, 56), 16), starts)
+    for n in (5, 1):                                  # 3 + 2 queries; 1 + 0 (a rank without work)
+        mp.spawn(_sharded_tracker_worker, args=(world, _free_port(), n, str(tmp_path)), nprocs=world, join=True)
+        ref = H._tracker().forward_windowed(f2d, _queries(n), torch.ones(1, n), time_strides=starts)
+        outs = [torch.load(tmp_path / f"tracks_{n}_{r}.pt") for r in range(world)]
+        for k, v in ref.items():
+            for o in outs:
+                assert o[k].shape == v.shape and o[k].dtype == v.dtype, k
+                assert torch.equal(o[k] == 0, v == 0) and torch.equal(o[k] == -10, v == -10), f"{k}: written-frame mask"
+                assert (o[k] - v).abs().max() < 2e-3, (k, (o[k] - v).abs().max())
+            assert torch.equal(outs[0][k], outs[1][k])          # gathered result is identical on every rank
