@@ -418,3 +418,18 @@ def test_bf16_operands_through_the_same_path(g, cpu_kernels):
     assert feats[-1].dtype == torch.float32
     assert rel_l2(out["depth_est_b1thw"], g["depth_windowed"]) < 5e-3
     assert rel_l2(out["flow_2d_backward_est_b2thw"], g["flow_windowed"]) < 1.5e-2
+
+
+def test_track_head_16bit_token_stream_experiment(g, cpu_kernels):
+    """Opt-in `L4P_TRACK_RES16=1` (VideoMAETrack2DSamHead.residual16): the per-query video-token stream between the two
+    two-way layers kept 16-bit (existing RES32|OUT16 / RES16|OUT16 GEMM epilogues + layernorm16). Same tracks as the
+    reference goldens within the same bounds as the default path; at full size vs the live reference: 0.005-0.007 px."""
+    enc = _encoder()
+    rgb = rnd((1, 3, 8, 56, 56), 16)
+    starts = torch.arange(0, 8 - 4 + 1, 2)
+    f2d = _windows(enc, rgb, starts)
+    trk = _tracker()
+    trk.residual16 = True
+    o = trk.forward_windowed(f2d, Q, torch.ones(1, 4), time_strides=starts)
+    _check_tracks(o, g)
+    assert cpu_kernels.CALLS["layernorm16"] > 3      # LayerNorm3d of the mask decoder + the two token-stream norms per call
