@@ -13,6 +13,9 @@ T=600 run bench_n1 python bench.py --steps 10 --warmup 3
 T=300 run att_pair_ab python tools/att_pair_ab.py
 # 2. if the pair kernel is parity-green: whole-step effect
 T=600 run bench_pair env L4P_ATT_PAIR=1 python bench.py --steps 10 --warmup 3 --no-cpu-baseline
+# 2a. ncu --set full of both attention arms (source-level stalls: --import-source on; the build has -lineinfo)
+T=600 run ncu_att_default ncu --set full --clock-control none --import-source on --profile-from-start off -o "$OUT/att_default" -f python tools/att_ncu.py
+T=600 run ncu_att_pair env L4P_ATT_PAIR=1 ncu --set full --clock-control none --import-source on --profile-from-start off -o "$OUT/att_pair" -f python tools/att_ncu.py
 # 2b. track head with a 16-bit per-query token stream (numerically equivalent on CPU vs the live reference: DESIGN.md §7.4)
 T=600 run track_res16_tests env L4P_TRACK_RES16=1 python -m pytest tests/test_track_gpu.py tests/test_windowed_gpu.py -x -q
 T=600 run bench_res16 env L4P_TRACK_RES16=1 python bench.py --steps 10 --warmup 3 --no-cpu-baseline
