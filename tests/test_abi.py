@@ -85,3 +85,33 @@ def test_ops_refuse_cpu_tensors():
     enc = VideoMAEEncoder(img_size=28, patch_size=14, embed_dim=16, depth=1, num_heads=2, all_frames=2, device="meta")
     with pytest.raises(L.L4PError):
         enc(torch.zeros(1, 3, 2, 28, 28))
+
+
+def test_shape_validation_precedes_device_work(lib):
+    """Every entry point checks its arguments before touching the device: bad shapes return L4P_ERR_SHAPE (-2) with a message
+    naming the entry, null pointers L4P_ERR_ARG (-1). Dummy non-null pointers are never dereferenced on these paths."""
+    P = ctypes.c_void_p(4096)
+    f = ctypes.c_float
+    cases = [
+        # fused attention: N must be a multiple of 256, head_dim a multiple of 8 <= 96, pad 96
+        (lambda: lib.l4p_attention(P, P, P, P, 1, 16, 2000, 88, 96, f(0.1), 0, None, None), -2, b"l4p_attention"),
+        (lambda: lib.l4p_attention(P, P, P, P, 1, 16, 2048, 90, 96, f(0.1), 0, None, None), -2, b"head_dim"),
+        (lambda: lib.l4p_attention(P, P, P, P, 1, 16, 2048, 88, 128, f(0.1), 0, None, None), -2, b"pad"),
+        (lambda: lib.l4p_attention(None, P, P, P, 1, 16, 2048, 88, 96, f(0.1), 0, None, None), -1, b"null"),
+        # LayerNorm kernels
+        (lambda: lib.l4p_layernorm(P, P, P, P, None, 4, 1407, f(1e-6), 0, None), -2, b"l4p_layernorm"),
+        (lambda: lib.l4p_layernorm16(P, P, P, P, 4, 4096, f(1e-6), 0, 0, None), -2, b"l4p_layernorm16"),
+        # gathers
+        (lambda: lib.l4p_patchify(P, P, 1, 3, 16, 224, 225, 2, 14, 14, 0, None), -2, b"l4p_patchify"),
+        (lambda: lib.l4p_cast16(P, P, 6, 0, None), -2, b"multiple of 4"),
+        (lambda: lib.l4p_upsample3d(P, P, None, 1, 4, 4, 4, 8, 8, 8, 12, 1, 0, None), -2, b"l4p_upsample3d"),
+        # track-head attentions and read-out
+        (lambda: lib.l4p_image_attention(P, P, P, P, 2, 256, 6, 8, 64, f(0.1), 0, None), -2, b"head_dim"),
+        (lambda: lib.l4p_token_attention(P, P, P, P, 2, 6, 2048, 8, 90, 2048, f(0.1), 0, None), -2, b"l4p_token_attention"),
+        (lambda: lib.l4p_track_readout(P, P, None, None, 2, 3, 16, 64, 64, 224, 224, None), -1, b"missing output"),
+    ]
+    for call, code, needle in cases:
+        rc = call()
+        msg = lib.l4p_last_error()
+        assert rc == code, (rc, code, msg)
+        assert needle in msg, (needle, msg)
