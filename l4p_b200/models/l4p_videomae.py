@@ -14,7 +14,6 @@ from typing import Any, Dict, List, Optional, Tuple
 
 import torch
 
-from ..utils.geometry_utils import normalize_intrinsics
 from .task_heads.dense_heads import joint_windowed_estimation
 from .videomae import FeatureList, VideoMAEEncoder
 

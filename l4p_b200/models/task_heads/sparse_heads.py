@@ -321,7 +321,6 @@ class VideoMAETrack2DSamHead(nn.Module):
             keys32 = (feat32.unsqueeze(0) + hist32).reshape(G * Pn, C).contiguous()
             keys16 = torch.empty(G * Pn, C, device=dev, dtype=dt)
             ops.cast16(keys32, keys16)
-        rows = keys16.shape[0]
 
         def img_proj(x16, l, table):
             y = torch.empty(x16.shape[0], l["w"].shape[0], device=dev, dtype=dt)
