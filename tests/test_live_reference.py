@@ -440,3 +440,29 @@ def test_joint_alignment_chain_live_reference_on_consistent_scene(ref, cpu_kerne
     for k in want:
         assert got[k].shape == want[k].shape and got[k].dtype == want[k].dtype
         assert (got[k] - want[k]).abs().max() < 1e-3, k
+
+
+@torch.no_grad()
+@pytest.mark.skipif(__import__("os").environ.get("L4P_SLOW_TESTS", "0") != "1", reason="~2 min, 15 GB: set L4P_SLOW_TESTS=1")
+def test_cfg1_full_model_depth_reference_vs_mirror(ref, cpu_kernels):
+    """BASELINE.json configs[0] as a parity case: one 16x224x224 clip, depth head only, the reference's full ViT-giant
+    (40 blocks) + depth DPT head in PyTorch eager on CPU against the drop-in on the per-op torch definitions."""
+    from l4p_b200.models.task_heads import dense_heads as D
+    from l4p_b200.models.videomae import VideoMAEEncoder
+    from tests.util import synth_rgb
+
+    kw = dict(img_size=224, patch_size=14, embed_dim=1408, depth=40, num_heads=16, mlp_ratio=48 / 11, qkv_bias=True,
+              norm_layer=partial(torch.nn.LayerNorm, eps=1e-6), init_values=0.0, tubelet_size=2, all_frames=16)
+    renc, oenc = _pair(ref["V"].VideoMAEEncoder, VideoMAEEncoder, 0, **kw)
+    rh, oh = _pair(ref["D"].VideoMAEDepthDPTHead, D.VideoMAEDepthDPTHead, 1, "depth", depth_fn="exp", hooks_idx=[14, 21, 28, 36],
+                   align_window_overlap_fn="inverse")
+    rgb = synth_rgb(1, 16)
+    rf = renc(rgb)
+    want = rh.forward(rf, img_info=(16, 224, 224))["depth_est_b1thw"]
+    of = oenc(rgb)
+    got = oh.forward(of, img_info=(16, 224, 224))["depth_est_b1thw"]
+    taps = {i: rel_l2(of[i], rf[i]) for i in (14, 21, 28, 36, 40)}
+    print("cfg1: encoder taps rel-L2", {k: f"{v:.2e}" for k, v in taps.items()}, "depth rel-L2 %.2e" % rel_l2(got, want),
+          "log-depth rel-L2 %.2e" % rel_l2(torch.log(got), torch.log(want)))
+    assert max(taps.values()) < 1.5e-3
+    assert rel_l2(got, want) < 1e-3 and rel_l2(torch.log(got), torch.log(want)) < 2e-3
