@@ -45,6 +45,13 @@ constexpr float kRescaleThreshold = 8.0f;  // log2 units
 #ifndef L4P_ATT_S_FIRST
 #define L4P_ATT_S_FIRST 0
 #endif
+#ifndef L4P_ATT_P_ALIAS
+#define L4P_ATT_P_ALIAS 0
+#endif
+// experiment (build with L4P_NVCC_EXTRA=-DL4P_ATT_P_ALIAS=1): FA4-style, BOTH tiles' P overwrite the first 64 columns of
+// their own S tile in TMEM (TS-mode PV for both, no P staging in shared memory); S_t(j+1) is then issued right after
+// PV_t(j) - the tensor pipe executes one thread's UMMAs in order, so PV_t(j) has read P_t(j) before S_t(j+1) overwrites it
+constexpr bool kPAlias = L4P_ATT_P_ALIAS != 0;
 constexpr bool kPTmem = L4P_ATT_P_TMEM != 0;  // tile 0's P through the 64 spare TMEM columns (TS-mode UMMA)
 
 struct AttParams {
@@ -196,7 +203,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         for (int kk = 0; kk < kTileN / 16; ++kk) {
           const uint32_t o = ((uint32_t)(kk & 3) * 32) >> 4;
           const uint64_t vdesc = umma_desc_make(va + (uint32_t)(kk >> 2) * ((kDPad * 128) >> 4) + o, hi128);
-          if (kPTmem && t == 0)  // P_0 is the TMEM A operand: 8 columns per K = 16 step, no shared-memory traffic for P
+          if (kPAlias)
+            umma_ts(d, tmem_base + (t == 0 ? kColS0 : kColS1) + (uint32_t)kk * 8u, vdesc, idesc_o, kk != 0 ? 1u : acc);
+          else if (kPTmem && t == 0)  // P_0 is the TMEM A operand: 8 columns per K = 16 step, no shared-memory traffic for P
             umma_ts(d, tmem_base + kColP0 + (uint32_t)kk * 8u, vdesc, idesc_o, kk != 0 ? 1u : acc);
           else
             umma_ss(d, umma_desc_make(pa + (uint32_t)(kk >> 2) * ((kTileM * 128) >> 4) + o, hi128), vdesc, idesc_o,
@@ -217,7 +226,24 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       for (int j = 0; j < nblk; ++j) {
         const int jn = j + 1;
         const int sk = jn % kKS, sv = j % kVS;
-#if L4P_ATT_S_FIRST
+#if L4P_ATT_P_ALIAS
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          mbar_wait(smem_u32(&bar_pfull[t]), (uint32_t)j & 1u);  // P_t(j) sits in S_t's columns, O_t rescaled
+          if (t == 0) mbar_wait(smem_u32(&bar_vfull[sv]), ((uint32_t)(j / kVS)) & 1u);
+          if (jn < nblk && t == 0) mbar_wait(smem_u32(&bar_kfull[sk]), ((uint32_t)(jn / kKS)) & 1u);
+          tc_fence_after();
+          if (leader) {
+            issue_pv(t, sv, j != 0 ? 1u : 0u);
+            if (t == 1) umma_commit(smem_u32(&bar_vempty[sv]));
+            if (jn < nblk) {
+              issue_s(t, sk);  // overwrites S_t / P_t(j) after PV_t(j) in pipe order
+              if (t == 1) umma_commit(smem_u32(&bar_kempty[sk]));
+            }
+          }
+          __syncwarp();
+        }
+#elif L4P_ATT_S_FIRST
         // experiment (build with L4P_NVCC_EXTRA=-DL4P_ATT_S_FIRST=1): both tiles' S(j+1) before the first PV(j), so that
         // S_1(j+1) does not queue behind P_0(j)
         if (jn < nblk) {
@@ -375,9 +401,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 
       if (j > 0) mbar_wait(smem_u32(&bar_pvdone[t]), (uint32_t)(j - 1) & 1u);  // P_t smem is free again
       ATT_STAMP(t, j, 5);
-      if (kPTmem && t == 0) {
+      if (kPAlias || (kPTmem && t == 0)) {
         // tile 0: P goes straight back to TMEM (row = lane, two probabilities per 32-bit column) as the A operand of PV
-        const uint32_t tP = tmem_base + lane_addr + kColP0;
+        const uint32_t tP = kPAlias ? tS : tmem_base + lane_addr + kColP0;
         tmem_st16(tP + 0, s + 0);
         tmem_st16(tP + 16, s + 16);
         tmem_st16(tP + 32, s + 32);

@@ -24,4 +24,8 @@ T=300 run att_timeline python tools/att_prof.py
 # 4. S-first issue order (build-time variant), then restore the default build
 T=600 run build_sfirst env L4P_NVCC_EXTRA=-DL4P_ATT_S_FIRST=1 python -m l4p_b200.build
 T=300 run att_sfirst env L4P_NVCC_EXTRA=-DL4P_ATT_S_FIRST=1 python tools/att_prof.py
+# 5. FA4-style P-aliases-S variant (both tiles TS-mode, no P staging in smem): parity of the attention tests, then timing
+T=600 run build_palias env L4P_NVCC_EXTRA=-DL4P_ATT_P_ALIAS=1 python -m l4p_b200.build
+T=300 run att_palias_parity env L4P_NVCC_EXTRA=-DL4P_ATT_P_ALIAS=1 python -m pytest tests/test_gemm_gpu.py -q -k attention
+T=300 run att_palias env L4P_NVCC_EXTRA=-DL4P_ATT_P_ALIAS=1 python tools/att_prof.py
 T=600 run build_default python -m l4p_b200.build
