@@ -39,6 +39,10 @@ constexpr int kKS = 4, kVS = 4;
 constexpr int kAttSmem = 2 * kQTileBytes + kKS * kKHalfBytes + kVS * kVHalfBytes + kPBytes + 1024;
 constexpr uint32_t kColS0 = 0, kColS1 = 128, kColO0 = 256, kColO1 = 352, kColP0 = 448;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
+#ifndef L4P_ATT_P_ALIAS
+#define L4P_ATT_P_ALIAS 0
+#endif
+constexpr bool kPAlias = L4P_ATT_P_ALIAS != 0;  // as in attention.cu: both tiles' P overwrite S_t[0,64) in TMEM, PV always TS-mode
 
 struct AttParams {
   uint16_t* out;
@@ -185,7 +189,9 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         for (int kk = 0; kk < kTileN / 16; ++kk) {
           const uint32_t o = ((uint32_t)(kk & 3) * 32) >> 4;
           const uint64_t vdesc = umma_desc_make(va + (uint32_t)(kk >> 2) * (kVChunk >> 4) + o, hi128);
-          if (t == 0)  // P_0 is each CTA's TMEM A operand: 8 columns per K = 16 step
+          if (kPAlias)
+            umma2_ts(d, tmem_base + (t == 0 ? kColS0 : kColS1) + (uint32_t)kk * 8u, vdesc, idesc_o, kk != 0 ? 1u : acc);
+          else if (t == 0)  // P_0 is each CTA's TMEM A operand: 8 columns per K = 16 step
             umma2_ts(d, tmem_base + kColP0 + (uint32_t)kk * 8u, vdesc, idesc_o, kk != 0 ? 1u : acc);
           else
             umma2_ss(d, umma_desc_make(p_lo + (uint32_t)(kk >> 2) * ((kTileM * 128) >> 4) + o, hi128), vdesc, idesc_o,
@@ -206,6 +212,25 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       for (int j = 0; j < nblk; ++j) {
         const int jn = j + 1;
         const int sk = jn % kKS, sv = j % kVS;
+#if L4P_ATT_P_ALIAS
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          mbar_wait(smem_u32(&bar_pfull[t]), (uint32_t)j & 1u);  // P_t(j) sits in S_t's columns in both CTAs, O_t rescaled
+          if (t == 0) mbar_wait(smem_u32(&bar_vfull[sv]), ((uint32_t)(j / kVS)) & 1u);
+          if (jn < nblk && t == 0) mbar_wait(smem_u32(&bar_kfull[sk]), ((uint32_t)(jn / kKS)) & 1u);
+          tc_fence_after();
+          if (leader) {
+            issue_pv(t, sv, j != 0 ? 1u : 0u);
+            if (t == 1) umma2_commit_mc(smem_u32(&bar_vempty[sv]), 3);
+            if (jn < nblk) {
+              issue_s(t, sk);  // overwrites S_t / P_t(j) after PV_t(j) in pipe order
+              if (t == 1) umma2_commit_mc(smem_u32(&bar_kempty[sk]), 3);
+            }
+          }
+          __syncwarp();
+        }
+        continue;
+#endif
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
           if (jn < nblk) {
@@ -327,9 +352,9 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       }
 
       if (j > 0) mbar_wait(smem_u32(&bar_pvdone[t]), (uint32_t)(j - 1) & 1u);  // P_t smem is free again
-      if (t == 0) {
+      if (kPAlias || t == 0) {
         // tile 0: P goes straight back to TMEM (row = lane, two probabilities per 32-bit column) as the A operand of PV
-        const uint32_t tP = tmem_base + lane_addr + kColP0;
+        const uint32_t tP = kPAlias ? tS : tmem_base + lane_addr + kColP0;
         tmem_st16(tP + 0, s + 0);
         tmem_st16(tP + 16, s + 16);
         tmem_st16(tP + 32, s + 32);

@@ -28,4 +28,5 @@ T=300 run att_sfirst env L4P_NVCC_EXTRA=-DL4P_ATT_S_FIRST=1 python tools/att_pro
 T=600 run build_palias env L4P_NVCC_EXTRA=-DL4P_ATT_P_ALIAS=1 python -m l4p_b200.build
 T=300 run att_palias_parity env L4P_NVCC_EXTRA=-DL4P_ATT_P_ALIAS=1 python -m pytest tests/test_gemm_gpu.py -q -k attention
 T=300 run att_palias env L4P_NVCC_EXTRA=-DL4P_ATT_P_ALIAS=1 python tools/att_prof.py
+T=300 run att_palias_pair_ab env L4P_NVCC_EXTRA=-DL4P_ATT_P_ALIAS=1 python tools/att_pair_ab.py   # both arms built with P alias
 T=600 run build_default python -m l4p_b200.build
