@@ -52,6 +52,13 @@ constexpr float kRescaleThreshold = 8.0f;  // log2 units
 // their own S tile in TMEM (TS-mode PV for both, no P staging in shared memory); S_t(j+1) is then issued right after
 // PV_t(j) - the tensor pipe executes one thread's UMMAs in order, so PV_t(j) has read P_t(j) before S_t(j+1) overwrites it
 constexpr bool kPAlias = L4P_ATT_P_ALIAS != 0;
+#ifndef L4P_ATT_LSUM_MMA
+#define L4P_ATT_LSUM_MMA 0
+#endif
+// experiment (build with L4P_NVCC_EXTRA=-DL4P_ATT_LSUM_MMA=1 AND run with L4P_ATT_LSUM_MMA=1 so that l4p_b200.ops fills row
+// `head_dim` of V^T with ones): the softmax denominator is column `head_dim` of O (= sum of the ROUNDED P, accumulated by the
+// PV UMMA for free since N = 96 costs the same as 128) instead of 64 FADD2 per key block and thread; needs head_dim < 96
+constexpr bool kLsumMma = L4P_ATT_LSUM_MMA != 0;
 constexpr bool kPTmem = L4P_ATT_P_TMEM != 0;  // tile 0's P through the 64 spare TMEM columns (TS-mode UMMA)
 
 struct AttParams {
@@ -386,7 +393,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           upk2(t2, a, b);
           p2 = pk2(ex2(a), ex2(b));
         }
-        if (i & 2) lsum1 = add2(lsum1, p2); else lsum0 = add2(lsum0, p2);
+        if (!kLsumMma) { if (i & 2) lsum1 = add2(lsum1, p2); else lsum0 = add2(lsum0, p2); }
         float p0, p1;
         upk2(p2, p0, p1);
         s[i >> 1] = pack2<BF16>(p0, p1);
@@ -428,6 +435,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     // ---- epilogue: O_t / l -> global
     mbar_wait(smem_u32(&bar_pvdone[t]), (uint32_t)(nblk - 1) & 1u);
     tc_fence_after();
+    if (kLsumMma) {  // l = O[:, head_dim] (head_dim is a multiple of 8 < 96: column head_dim is index 0 of a 16-column load)
+      uint32_t lo[16];
+      tmem_ld16(tO + (uint32_t)p.head_dim, lo);
+      tmem_ld_wait();
+      l = __uint_as_float(lo[0]);
+    }
     const float inv_l = 1.0f / l;
     const int b = bh / p.H, h = bh - b * p.H;
     const long long row = (long long)b * p.N + (long long)pair * 2 * kTileM + t * kTileM + r;

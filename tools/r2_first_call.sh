@@ -29,4 +29,8 @@ T=600 run build_palias env L4P_NVCC_EXTRA=-DL4P_ATT_P_ALIAS=1 python -m l4p_b200
 T=300 run att_palias_parity env L4P_NVCC_EXTRA=-DL4P_ATT_P_ALIAS=1 python -m pytest tests/test_gemm_gpu.py -q -k attention
 T=300 run att_palias env L4P_NVCC_EXTRA=-DL4P_ATT_P_ALIAS=1 python tools/att_prof.py
 T=300 run att_palias_pair_ab env L4P_NVCC_EXTRA=-DL4P_ATT_P_ALIAS=1 python tools/att_pair_ab.py   # both arms built with P alias
+# 6. softmax denominator from the PV UMMA (ones row in the V^T pad): needs the build macro AND the run-time env
+T=600 run build_lsum env L4P_NVCC_EXTRA=-DL4P_ATT_LSUM_MMA=1 python -m l4p_b200.build
+T=300 run att_lsum_parity env L4P_NVCC_EXTRA=-DL4P_ATT_LSUM_MMA=1 L4P_ATT_LSUM_MMA=1 python -m pytest tests/test_gemm_gpu.py -q -k attention
+T=300 run att_lsum env L4P_NVCC_EXTRA=-DL4P_ATT_LSUM_MMA=1 L4P_ATT_LSUM_MMA=1 python tools/att_prof.py
 T=600 run build_default python -m l4p_b200.build
