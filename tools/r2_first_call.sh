@@ -1,5 +1,5 @@
 #!/usr/bin/env bash
-# First GPU call of round 2 (one `gpurun --timeout 1500 -- bash tools/r2_first_call.sh`): regression + the experiments that
+# First GPU call of round 2 (one `gpurun --timeout 2400 -- bash tools/r2_first_call.sh`): regression + the experiments that
 # were prepared on CPU at the end of round 1. Everything lands in gpurun_out/r2_first/. Each step has its own timeout; all
 # device-side waits are bounded (mbar_wait traps), so a protocol bug in an experimental kernel ends as a CUDA error.
 set -u
