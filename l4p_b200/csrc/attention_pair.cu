@@ -253,6 +253,9 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           __syncwarp();
         }
       }
+      // the last commit (release of the last V slot, multicast) has no other waiter: wait for its local arrival so that no
+      // multicast arrive is in flight towards the peer's shared memory when the cluster exits (tools/att_protocol_sim.py)
+      mbar_wait(smem_u32(&bar_vempty[(nblk - 1) % kVS]), ((uint32_t)((nblk - 1) / kVS)) & 1u);
     }
   } else {
     // ------------------------------------------------------------------ softmax warpgroups

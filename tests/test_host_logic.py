@@ -225,3 +225,19 @@ def test_missing_library_fails_loudly(tmp_path, monkeypatch):
 
     with pytest.raises(L.L4PError, match="no CPU fallback"):
         L.load()
+
+
+def test_attention_synchronisation_protocol_model():
+    """tools/att_protocol_sim.py: discrete-event model of the attention kernels' mbarrier / TMA / tcgen05.commit protocol
+    (production kernel, S-first and P-alias build variants, the CTA-pair kernel and its P-alias variant). Random
+    interleavings must terminate with every buffer consumed at the right version and no parity aliasing; deliberately
+    broken protocols must be rejected."""
+    import importlib.util
+    from pathlib import Path
+
+    spec = importlib.util.spec_from_file_location("att_protocol_sim", Path(__file__).resolve().parents[1] / "tools" / "att_protocol_sim.py")
+    sim = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(sim)
+    caught = sim.self_test(seeds=20)
+    assert all(v > 0 for v in caught.values()), caught
+    sim.check_all(seeds=25, verbose=False)
