@@ -3,8 +3,19 @@
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-One step = one pass of the all-heads hot path (encoder + flow/depth/dyn-mask/camray DPT heads + 128-query track head)
-over `clips_per_gpu` synthetic 16x224x224 clips per GPU. Metric: frames/s = 16 * clips / step time (BASELINE.json).
+Headline (BASELINE.json configs[1]): one step = one pass of the all-heads hot path (encoder + flow / depth / dyn-mask /
+camray DPT heads + 128-query track head, the shipped config: windowed path + joint alignment) over ONE synthetic 16x224x224
+clip per GPU through `L4PLitModule.predict_step`. Metric: frames/s = 16 * clips / step time. N > 1: one clip per GPU
+(weak scaling) + ONE all-gather of the packed head outputs over NVLink.
+
+The same process then times (block `configs` of the same JSON line, skipped with --skip-configs):
+  cfg3  BASELINE.json configs[2]: 4 clips per GPU as ONE batch (encoder + DPT heads batched over the clips, tracker per clip)
+  cfg4  BASELINE.json configs[3]: one long video (T=264 -> 32 windows, T=512 -> 63 windows), depth + camray with joint
+        Sim(3) window alignment on the GPU; N > 1 shards the windows across ranks (`enable_window_sharding`), and a
+        4-window clip is run sharded AND unsharded to report their difference.
+
+`--impl reference` times the UNMODIFIED reference (baseline/_ref, see oracle/ref_arm.py) on the same full workload: fp32
+eager on the host cores (the comparator), plus its eager fp16-autocast path on the B200 (informational).
 """
 from __future__ import annotations
 
@@ -25,6 +36,9 @@ sys.path.insert(0, str(ROOT))
 TASKS = ["flow_2d_backward", "track_2d", "depth", "dyn_mask", "camray"]
 NQ = 128
 ATT_FLOPS_PER_BLOCK_WINDOW = 4 * 2048 * 2048 * 88 * 16  # 23 622 320 128 (unpadded d=88)
+WORKLOAD = ("single 16x224x224 clip per GPU, all heads (flow, depth, dyn-mask, camray pose, 128-query 2D/3D tracks), "
+            "shipped config (windowed + joint alignment), BASELINE.json configs[1]")
+REF_ARM_FILES = [Path("/tmp/l4p_reference_arm.json"), ROOT / "gpurun_out" / "reference_arm_last.json"]
 
 
 def peaks():
@@ -74,50 +88,38 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(self.rows)}
 
 
-def synth_batch(clips: int):
+def synth_batch(clips: int, T: int = 16, queries: bool = True):
     from tests.util import synth_intrinsics, synth_rgb
 
-    rgb = synth_rgb(clips, 16, seed=0)
-    intr = synth_intrinsics(clips, 16)
-    xs = torch.linspace(7, 217, 16)
-    ys = torch.linspace(14, 210, 8)
-    gy, gx = torch.meshgrid(ys, xs, indexing="ij")
-    q = torch.stack([torch.full_like(gx, 0.5), gx + 0.5, gy + 0.5], dim=-1).reshape(1, NQ, 3).repeat(clips, 1, 1)
-    return dict(rgb_b3thw=rgb, intrinsics_b44t=intr, track_2d_pointquerries_bn3=q,
-                track_2d_pointlabels_bn=torch.ones(clips, NQ))
+    batch = dict(rgb_b3thw=synth_rgb(clips, T, seed=0), intrinsics_b44t=synth_intrinsics(clips, T))
+    if queries:
+        xs = torch.linspace(7, 217, 16)
+        ys = torch.linspace(14, 210, 8)
+        gy, gx = torch.meshgrid(ys, xs, indexing="ij")
+        q = torch.stack([torch.full_like(gx, 0.5), gx + 0.5, gy + 0.5], dim=-1).reshape(1, NQ, 3).repeat(clips, 1, 1)
+        batch.update(track_2d_pointquerries_bn3=q, track_2d_pointlabels_bn=torch.ones(clips, NQ))
+    return batch
 
 
 OUT_KEYS = ["depth_est_b1thw", "flow_2d_backward_est_b2thw", "dyn_mask_est_b1thw", "traj3d_est_b16t",
             "traj3d_intrinsics_est_b16t", "track_2d_traj_est_bn2t", "track_2d_vis_est_bn1t", "track_2d_depth_est_bn1t"]
 
 
-def run_clip(model, batch, c):
-    one = {k: v[c:c + 1] for k, v in batch.items()}
-    out = model.forward(one, TASKS)
-    return torch.cat([out[k].reshape(-1).float() for k in OUT_KEYS])
+def pack_outputs(out, keys, clips):
+    """[clips, unit] fp32: every head output of every clip, the buffer that is exchanged / copied to the host."""
+    return torch.cat([out[k].reshape(clips, -1).float() for k in keys], dim=1)
 
 
-_CPU_SDS = None
-
-
-def cpu_baseline_sample():
-    """One bounded sample of the all-heads window on the host cores through the oracle port (oracle/cpu_bench.py)."""
-    global _CPU_SDS
-    from oracle import cpu_bench
-
-    torch.set_num_threads(os.cpu_count() or 1)
-    if _CPU_SDS is None:
-        _CPU_SDS = _cpu_state_dicts()
-    sds = _CPU_SDS
-    return cpu_bench.sample(sds["block"], sds["depth"], sds["cam"], sds["track"], NQ), cpu_bench.SAMPLE_DESC
-
-
-def _cpu_state_dicts():
+# ------------------------------------------------------------------------------------------------ reference arm
+def _port_sample():
+    """Fallback comparator when the reference sources did not travel (no baseline/_ref): the oracle port on a bounded sample."""
     from l4p_b200 import weights
     from l4p_b200.models.task_heads.dense_heads import VideoMAEDepthDPTHead, VideoMAETraj3DDPTHead
     from l4p_b200.models.task_heads.sparse_heads import VideoMAETrack2DSamHead
     from l4p_b200.models.videomae import Block
+    from oracle import cpu_bench
 
+    torch.set_num_threads(os.cpu_count() or 1)
     hooks = [0, 1, 2, 3]
     mods = dict(
         block=Block(1408, 16, 48 / 11, True, None, 1e-6, 0.0, device="meta"),
@@ -126,37 +128,72 @@ def _cpu_state_dicts():
         track=VideoMAETrack2DSamHead(estimate_vis=True, estimate_depth=True, prompt_using_features=True, attend_to_past=True,
                                      modify_pointlabels_for_windowing=True, estimation_directions=[1], depth_fn="exp",
                                      device="meta"))
-    return {n: weights.synth_state_dict([(k, tuple(v.shape)) for k, v in m.state_dict().items()], seed=0) for n, m in mods.items()}
+    sds = {n: weights.synth_state_dict([(k, tuple(v.shape)) for k, v in m.state_dict().items()], seed=0) for n, m in mods.items()}
+    s = cpu_bench.sample(sds["block"], sds["depth"], sds["cam"], sds["track"], NQ)
+    return s, cpu_bench.SAMPLE_DESC
+
+
+def reference_cpu(steps: int, warmup: int, budget_s: float, with_cuda: bool):
+    """(cpu_baseline dict, extra dict). Real reference when its sources are on the box, else the port sample."""
+    from oracle import ref_arm
+
+    cores = os.cpu_count() or 1
+    if ref_arm.root() is None:
+        s, desc = _port_sample()
+        return ({"value": s["frames_per_s"], "unit": "frames/s", "cores": cores, "kind": "port", "sample": desc,
+                 "same_config": False}, {"window_ms": 1e3 * s["window_s"], "steps_timed": 1})
+    t0 = time.perf_counter()
+    model = ref_arm.build_model(NQ)
+    build_s = time.perf_counter() - t0
+    batch = synth_batch(1)
+    r = ref_arm.time_cpu(model, batch, TASKS, steps, warmup, budget_s)
+    cb = {"value": 16.0 / r["mean_s"], "unit": "frames/s", "cores": r["threads"], "kind": "reference", "same_config": True,
+          "sample": f"UNMODIFIED reference (baseline/_ref: l4p.l4p.L4PLitModule from its own configs/model.yaml, fp32 eager, "
+                    f"{r['threads']} host threads): the full all-heads window, {r['steps_timed']} timed pass(es) after "
+                    f"{min(warmup, 1)} warm-up, no sampling, no extrapolation"}
+    extra = {"window_ms": 1e3 * r["mean_s"], "steps_timed": r["steps_timed"], "model_build_s": round(build_s, 1),
+             "step_s": [round(x, 2) for x in r["step_s"]], "out_keys": r["out_keys"]}
+    if with_cuda and torch.cuda.is_available():
+        try:
+            g = ref_arm.time_cuda_eager(model, batch, TASKS)
+            extra["reference_eager_cuda"] = {
+                "value": g["frames_per_s"], "unit": "frames/s", "ms_per_step": g["ms_per_step"], "autocast": g["autocast"],
+                "peak_mem_gb": round(g["peak_mem_gb"], 2), "steps": g["steps"],
+                "what": "the same unmodified reference modules on this B200: eager ATen/cuBLAS/cuDNN kernels under "
+                        "torch.autocast(fp16) (= Lightning 16-mixed, demo/demo.py:22), inputs resident on the device"}
+        except Exception as e:  # noqa: BLE001 - informational leg only
+            extra["reference_eager_cuda"] = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
+    del model
+    return cb, extra
 
 
 def run_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    if int(os.environ.get("RANK", "0")) != 0:
         return
-    cores = os.cpu_count() or 1
-    for _ in range(max(args.warmup, 0) and 1):
-        cpu_baseline_sample()
-    vals, wins = [], []
     t_all = time.perf_counter()
-    for _ in range(args.steps):
-        s, desc = cpu_baseline_sample()
-        vals.append(s["frames_per_s"])
-        wins.append(s["window_s"])
-    v = sum(vals) / len(vals)
+    cb, extra = reference_cpu(args.steps, args.warmup, budget_s=float(os.environ.get("L4P_REF_BUDGET_S", "150")), with_cuda=True)
+    v = cb["value"]
     line = {"impl": "reference", "metric": "frames/sec (16x224x224, all heads)", "value": v, "unit": "frames/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            # one step = one bounded sample (wall time below); `value` = 16 frames / the window time extrapolated from it
-            "ms_per_step": 1e3 * (time.perf_counter() - t_all) / args.steps,
-            "window_ms_extrapolated": 1e3 * sum(wins) / len(wins), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "single 16x224x224 clip, all heads, 128 track queries (BASELINE.json configs[1])"},
-            "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": "port", "sample": desc},
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": extra["window_ms"],
+            "steps_timed": extra["steps_timed"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "clips_per_gpu": 1, "track_queries": NQ},
+            "cpu_baseline": cb,
             "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "note": "the reference is pure Python and cannot travel to the GPU box (/root/reference absent there); this "
-                    "arm times the oracle port (oracle/l4p_oracle.py, pinned against the reference by tests/golden)"}
+            "wall_s": None}
+    line.update({k: x for k, x in extra.items() if k not in ("window_ms", "steps_timed")})
+    line["wall_s"] = round(time.perf_counter() - t_all, 1)
+    line["note"] = ("each step is one full un-sampled window; the run stops early once the time budget is spent "
+                    "(steps_timed < steps), value = 16 frames / mean step time")
+    for p in REF_ARM_FILES:
+        try:
+            p.parent.mkdir(parents=True, exist_ok=True)
+            p.write_text(json.dumps(line))
+        except OSError:
+            pass
     print(json.dumps(line))
 
 
+# ------------------------------------------------------------------------------------------------ our arm
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -166,6 +203,7 @@ def main():
     ap.add_argument("--clips-per-gpu", type=int, default=1)
     ap.add_argument("--dtype", default="fp16", choices=["fp16", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-configs", action="store_true", help="headline only (no cfg3 / cfg4 legs)")
     ap.add_argument("--ncu-range", action="store_true", help="bracket the timed region with cudaProfilerStart/Stop "
                     "(run under `ncu --profile-from-start off`)")
     args = ap.parse_args()
@@ -194,100 +232,195 @@ def main():
     from l4p_b200.parallel import gather_clip_outputs
 
     dt = torch.float16 if args.dtype == "fp16" else torch.bfloat16
-    lit = load_model(device=dev, max_queries=NQ + 1, compute_dtype=dt)
+    lit = load_model(device=dev, max_queries=NQ + 1, compute_dtype=dt)   # configs/model.yaml: all five tasks, joint alignment
     model = lit.l4p_model
     weights.fill_module_fast_(model, seed=rank)
-    clips = args.clips_per_gpu
-    host = {k: v.pin_memory() for k, v in synth_batch(clips).items()}
-    batch = {k: v.to(dev) for k, v in host.items()}
-    h2d = sum(v.numel() * v.element_size() for v in host.values())
-
-    def step(b):
-        outs = [run_clip(model, b, c) for c in range(clips)]
-        packed = torch.stack(outs)                                  # [clips_per_gpu, unit]
-        if world > 1:
-            return gather_clip_outputs(packed).view(-1)             # the single exchange step: head outputs over NVLink
-        return packed.view(-1)
+    copy_stream = torch.cuda.Stream(device=dev)
 
     def sync_all():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    with torch.no_grad():
-        for _ in range(args.warmup):
-            res = step(batch)
-        d2h = res.numel() * 4 if world == 1 else res.numel() * 4
-        host_out = torch.empty(res.shape, dtype=torch.float32).pin_memory()
-        # ---------------- device-resident timed region
+    def measure(make_step, host, steps, warmup, instrument=False):
+        """Device-resident and end-to-end timing of `make_step(batch) -> packed [units, n] fp32` (this rank's outputs; the
+        step itself contains the exchange collective when world > 1). Returns ms, ms_e2e (max over ranks), byte counts."""
+        batch = {k: v.to(dev) for k, v in host.items()}
+        res = None
+        for _ in range(warmup):
+            res = make_step(batch)
+        pinned = [torch.empty(res.shape, dtype=torch.float32).pin_memory() for _ in range(2)]
+        h2d = sum(v.numel() * v.element_size() for v in host.values())
+        d2h = res.numel() * 4
         sync_all()
-        launches0 = ops.LAUNCHES
+        l0 = ops.LAUNCHES
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with ClockSampler(local) as cs:
-            if args.ncu_range:
+            if args.ncu_range and instrument:
                 torch.cuda.profiler.start()
             e0.record()
-            for _ in range(args.steps):
-                step(batch)
+            for _ in range(steps):
+                make_step(batch)
             e1.record()
             sync_all()
-            if args.ncu_range:
+            if args.ncu_range and instrument:
                 torch.cuda.profiler.stop()
-        ms = e0.elapsed_time(e1) / args.steps
-        launches = (ops.LAUNCHES - launches0) // args.steps
+        ms = e0.elapsed_time(e1) / steps
+        launches = (ops.LAUNCHES - l0) // steps
+        # end to end: the user-facing call on PINNED HOST inputs (predict_step moves them to the device: H2D inside the timed
+        # region), D2H of this rank's packed head outputs into double-buffered pinned memory on a copy stream, so that the copy
+        # of step i overlaps the compute of step i+1; everything is complete before the closing event.
+        sync_all()
+        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        main_stream = torch.cuda.current_stream()
+        e2.record()
+        for i in range(steps):
+            r = make_step(dict(host))
+            done = torch.cuda.Event()
+            done.record(main_stream)
+            copy_stream.wait_event(done)
+            with torch.cuda.stream(copy_stream):
+                pinned[i % 2].copy_(r, non_blocking=True)
+                r.record_stream(copy_stream)
+        main_stream.wait_stream(copy_stream)
+        e3.record()
+        sync_all()
+        ms_e2e = e2.elapsed_time(e3) / steps
+        t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = t.tolist()
+        return dict(ms=ms, ms_e2e=ms_e2e, h2d=h2d, d2h=d2h, launches=int(launches), clocks=cs.summary(), batch=batch)
+
+    # ---------------------------------------------------------------- headline: cfg 2, one clip per GPU
+    clips = args.clips_per_gpu
+
+    def step_clips(n_clips):
+        def step(b):
+            out = lit.predict_step(b, 0)                       # the reference-facing call (l4p/l4p.py:107-109)
+            packed = pack_outputs(out, OUT_KEYS, n_clips)      # [clips, unit]
+            if world > 1:
+                gather_clip_outputs(packed)                    # the single exchange step: head outputs over NVLink (stays on device)
+            return packed                                      # this rank's shard: what its host process reads back
+        return step
+
+    with torch.no_grad():
+        host = {k: v.pin_memory() for k, v in synth_batch(clips).items()}
+        m = measure(step_clips(clips), host, args.steps, args.warmup, instrument=True)
         # roofline kernel: CUDA-event pair around every attention launch of two extra instrumented steps (kept out of the
         # timed region: an event record between two kernels breaks their programmatic-dependent-launch overlap)
         ops.ATTN_EVENTS = []
         for _ in range(2):
-            step(batch)
+            step_clips(clips)(m["batch"])
         sync_all()
         att = ops.ATTN_EVENTS
         ops.ATTN_EVENTS = None
         att_ms = sum(a.elapsed_time(b) for a, b, _ in att) / max(len(att), 1)
         att_flops = sum(f for _, _, f in att) / max(len(att), 1)
-        # ---------------- end-to-end timed region: pinned host inputs -> H2D -> forward -> D2H of all head outputs
-        sync_all()
-        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e2.record()
-        for _ in range(args.steps):
-            b = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
-            r = step(b)
-            host_out.copy_(r, non_blocking=True)
-        e3.record()
-        sync_all()
-        ms_e2e = e2.elapsed_time(e3) / args.steps
 
-    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e = t.tolist()
+        extra_cfgs = {}
+        if not args.skip_configs:
+            # ------------------------------------------------------------ cfg 3: 4 clips per GPU as one batch
+            c3 = 4
+            host3 = {k: v.pin_memory() for k, v in synth_batch(c3).items()}
+            m3 = measure(step_clips(c3), host3, steps=4, warmup=2)
+            f3 = 16 * c3 * world
+            extra_cfgs["cfg3"] = {
+                "workload": f"BASELINE.json configs[2] scaled to N GPUs: {c3} clips per GPU as one batch (encoder + DPT heads "
+                            f"batched over clips, tracker per clip, 128 queries each), all heads; {c3 * world} clips total",
+                "value": f3 / (m3["ms"] * 1e-3), "unit": "frames/s", "ms_per_step": m3["ms"], "steps": 4, "warmup": 2,
+                "e2e": {"value": f3 / (m3["ms_e2e"] * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": m3["h2d"],
+                        "d2h_bytes_per_step": m3["d2h"]},
+                "gpu_launches": m3["launches"], "scaling": "weak"}
+            del m3
+            # ------------------------------------------------------------ cfg 4: long video, depth + camray, joint alignment
+            keys4 = ["depth_est_b1thw", "traj3d_est_b16t", "traj3d_intrinsics_est_b16t"]
+            tasks4 = ["depth", "camray"]
+            if world > 1:
+                model.enable_window_sharding(True)
+
+            def step_video(b):
+                out = model.forward(b if b["rgb_b3thw"].is_cuda else {k: v.to(dev, non_blocking=True) for k, v in b.items()}, tasks4)
+                return pack_outputs(out, keys4, 1)
+
+            for T in (264, 512):
+                hostv = {k: v.pin_memory() for k, v in synth_batch(1, T, queries=False).items()}
+                mv = measure(step_video, hostv, steps=2, warmup=1)
+                nW = (T - 16) // 8 + 1
+                extra_cfgs[f"cfg4_T{T}"] = {
+                    "workload": f"BASELINE.json configs[3]: one {T}-frame video = {nW} overlapping 16-frame windows, depth + camray "
+                                f"heads, joint Sim(3) window alignment on the GPU; windows sharded over {world} GPU(s), one "
+                                f"all-gather of per-window depth + ray maps, alignment chain on every rank",
+                    "value": T / (mv["ms"] * 1e-3), "unit": "video frames/s", "windows_per_s": nW / (mv["ms"] * 1e-3),
+                    "ms_per_step": mv["ms"], "steps": 2, "warmup": 1,
+                    "e2e": {"value": T / (mv["ms_e2e"] * 1e-3), "unit": "video frames/s", "h2d_bytes_per_step": mv["h2d"],
+                            "d2h_bytes_per_step": mv["d2h"]},
+                    "gpu_launches": mv["launches"], "scaling": "strong"}
+                del mv, hostv
+            if world > 1:
+                # sharded == unsharded on real NCCL ranks: a 5-window clip through both paths on every rank
+                b5 = {k: v.to(dev) for k, v in synth_batch(1, 48, queries=False).items()}
+                sh = model.forward(b5, tasks4)
+                model.enable_window_sharding(False)
+                un = model.forward(b5, tasks4)
+                diffs = {}
+                for k in keys4:
+                    a, b = sh[k].float(), un[k].float()
+                    diffs[k] = float((a - b).norm() / (b.norm() + 1e-30))
+                d = torch.tensor([diffs[k] for k in keys4], device=dev, dtype=torch.float64)
+                dist.all_reduce(d, op=dist.ReduceOp.MAX)
+                extra_cfgs["cfg4_sharded_vs_unsharded_rel_l2"] = dict(zip(keys4, d.tolist()))
+            torch.cuda.empty_cache()
+
     frames = 16 * clips * world
     if rank == 0:
         pk = peaks()
         ach = att_flops / (att_ms * 1e-3) / 1e12
+        ncu = {}
+        pj = ROOT / "profiles" / "attention_ncu_r2.json"
+        if pj.exists():
+            ncu = json.loads(pj.read_text())
         line = {
-            "metric": "frames/sec (16x224x224, all heads)", "value": frames / (ms * 1e-3), "unit": "frames/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "metric": "frames/sec (16x224x224, all heads)", "value": frames / (m["ms"] * 1e-3), "unit": "frames/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": m["ms"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-            "config": {"workload": "single 16x224x224 clip per GPU, all heads (flow, depth, dyn-mask, camray pose, 128-query "
-                                   "2D/3D tracks), BASELINE.json configs[1]; N>1: one clip per GPU + one all-gather of head outputs",
+            "config": {"workload": WORKLOAD + "; N>1: one clip per GPU + one all-gather of head outputs",
                        "clips_per_gpu": clips, "track_queries": NQ, "weights": "random (seeded), reference architecture",
+                       "api": "L4PLitModule.predict_step(batch, 0)",
                        "l2": "per-step working set (2.8 GB weights + >1 GB activations) exceeds the 126 MB L2; no explicit flush"},
-            "e2e": {"value": frames / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": int(launches),
-            "clocks": cs.summary(),
+            "e2e": {"value": frames / (m["ms_e2e"] * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": m["h2d"],
+                    "d2h_bytes_per_step": m["d2h"],
+                    "note": "per rank: pinned host batch -> predict_step (H2D inside) -> D2H of this rank's packed head outputs "
+                            "(double-buffered pinned memory, copy stream); the all-gathered buffer stays on the device"},
+            "gpu_launches": m["launches"],
+            "clocks": m["clocks"],
             "roofline": {"kernel": "attention_kernel (fused QK^T+softmax+PV, tcgen05)", "bound": "tensor", "achieved": ach,
                          "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"],
-                         # dram__bytes_read + write per launch from the ncu --set full capture profiles/attention_ncu_r1b.txt
-                         # (B=1: Q, K, V^T 3 x 6.3 MB read; the 5.8 MB output stays in L2 inside the capture window)
-                         "traffic": 19117824,
+                         # dram__bytes_read + write per launch of the shipped kernel, from the committed ncu --set full capture
+                         "traffic": ncu.get("dram_bytes_per_launch"), "traffic_source": ncu.get("source"),
+                         "tensor_pipe_pct_ncu": ncu.get("tensor_pipe_pct"),
                          "peak_source": pk["src"], "launch_us": att_ms * 1e3,
                          "algorithmic_flops_per_launch": att_flops},
         }
+        if extra_cfgs:
+            line["configs"] = extra_cfgs
+        pp = ROOT / "profiles" / "parity_r2.json"
+        if pp.exists():
+            line["parity"] = json.loads(pp.read_text())
         if world == 1 and not args.no_cpu_baseline:
-            s, desc = cpu_baseline_sample()
-            line["cpu_baseline"] = {"value": s["frames_per_s"], "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
-                                    "sample": desc, "detail": {k: round(v, 4) for k, v in s.items()}}
+            del m
+            torch.cuda.empty_cache()
+            prior = next((p for p in REF_ARM_FILES if p.exists()), None)
+            cb, extra = reference_cpu(steps=1, warmup=0, budget_s=1.0, with_cuda=False)
+            line["cpu_baseline"] = dict(cb, window_ms=extra["window_ms"])
+            if prior is not None:   # the --impl reference run of this box (the driver runs it right before this arm)
+                try:
+                    pr = json.loads(prior.read_text())
+                    line["reference_arm"] = {k: pr[k] for k in ("value", "unit", "steps_timed", "cpu_baseline", "reference_eager_cuda")
+                                             if k in pr}
+                    line["reference_arm"]["source"] = str(prior)
+                except Exception:  # noqa: BLE001
+                    pass
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

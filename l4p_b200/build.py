@@ -14,8 +14,11 @@ from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
-OBJ = PKG / "csrc" / "build"
-LIB = PKG / "libl4p_b200.so"
+# L4P_BUILD_TAG=<tag> builds an experiment variant next to the production library (own object directory, own .so:
+# l4p_b200/libl4p_b200_<tag>.so, selected at run time with L4P_LIB=<path>); the untagged build is what ships.
+_TAG = os.environ.get("L4P_BUILD_TAG", "")
+OBJ = PKG / "csrc" / ("build" if not _TAG else f"build_{_TAG}")
+LIB = PKG / ("libl4p_b200.so" if not _TAG else f"libl4p_b200_{_TAG}.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -9,8 +9,14 @@
 //                (M128 N96 K128) into TMEM; S_t(j+1) is issued before P_t(j) V_j so the tensor pipe
 //                works while the softmax warps run
 //   warp 2       TMEM allocator (512 columns: S0 | S1 | O0 | O1 | P0)
-//   warps 4..7   softmax warpgroup for tile 0, one query row per thread
-//   warps 8..11  softmax warpgroup for tile 1
+//   SPLIT = false (384 threads): warps 4..7 softmax warpgroup for tile 0, warps 8..11 for tile 1, one query row per thread
+//   SPLIT = true  (640 threads, default): FOUR softmax warpgroups, two per tile: warps 4..7 / 8..11 own key columns
+//                [0,64) / [64,128) of tile 0's rows, warps 12..15 / 16..19 the same for tile 1. Measured (round 2,
+//                profiles/attention_r2.md): the UMMAs of one key block need ~1600 cycles of the tensor pipe, the two
+//                full-row warpgroups needed ~2850 (two warps per SM sub-partition cannot hide the MUFU / TMEM / FMA
+//                latencies: 57 % issue utilisation); four half-row warpgroups issue the same instructions from four
+//                warps per sub-partition. The halves exchange their partial row maximum through shared memory (one
+//                store, one 256-thread named barrier, one load per key block) so both use the same reference maximum.
 //
 // Softmax: fp32 scores from TMEM, running max with lazy rescale (O is only rescaled in TMEM when the row max
 // grew by more than 2^8), exp2 with the scale folded into one FFMA, fp32 row sums, P rounded to the operand
@@ -27,7 +33,8 @@
 
 namespace l4p {
 
-constexpr int kAttThreads = 384;
+constexpr int kAttThreads = 384;    // SPLIT = false
+constexpr int kAttThreads4 = 640;   // SPLIT = true
 constexpr int kDPad = 96;
 constexpr int kTileM = 128;   // query rows per tile
 constexpr int kTileN = 128;   // keys per block
@@ -39,28 +46,10 @@ constexpr int kKS = 2, kVS = 2;
 constexpr int kAttSmem = 2 * kQTileBytes + kKS * kKBytes + kVS * kVBytes + 2 * kPBytes + 1024;
 constexpr uint32_t kColS0 = 0, kColS1 = 128, kColO0 = 256, kColO1 = 352, kColP0 = 448;  // P0: tile 0's probabilities (64 columns)
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
-#ifndef L4P_ATT_P_TMEM
-#define L4P_ATT_P_TMEM 1
-#endif
-#ifndef L4P_ATT_S_FIRST
-#define L4P_ATT_S_FIRST 0
-#endif
-#ifndef L4P_ATT_P_ALIAS
-#define L4P_ATT_P_ALIAS 0
-#endif
-// experiment (build with L4P_NVCC_EXTRA=-DL4P_ATT_P_ALIAS=1): FA4-style, BOTH tiles' P overwrite the first 64 columns of
-// their own S tile in TMEM (TS-mode PV for both, no P staging in shared memory); S_t(j+1) is then issued right after
-// PV_t(j) - the tensor pipe executes one thread's UMMAs in order, so PV_t(j) has read P_t(j) before S_t(j+1) overwrites it
-constexpr bool kPAlias = L4P_ATT_P_ALIAS != 0;
-#ifndef L4P_ATT_LSUM_MMA
-#define L4P_ATT_LSUM_MMA 0
-#endif
-// experiment (build with L4P_NVCC_EXTRA=-DL4P_ATT_LSUM_MMA=1 AND run with L4P_ATT_LSUM_MMA=1 so that l4p_b200.ops fills row
-// `head_dim` of V^T with ones): the softmax denominator is column `head_dim` of O (= sum of the ROUNDED P, accumulated by the
-// PV UMMA for free since N = 96 costs the same as 128) instead of 64 FADD2 per key block and thread; needs head_dim < 96
-constexpr bool kLsumMma = L4P_ATT_LSUM_MMA != 0;
-constexpr bool kPTmem = L4P_ATT_P_TMEM != 0;  // tile 0's P through the 64 spare TMEM columns (TS-mode UMMA)
-
+// Variants measured on hardware in round 2 and removed (profiles/attention_r2.md): both tiles' P aliased onto S in TMEM
+// (FA4-style; S(j+1) then queues behind PV(j): -11 %), a cta_group::2 kernel sharing K/V between two SMs (-20 %: the
+// shared-memory operand port is NOT the limiter), S(j+1) of both tiles issued before PV(j) (-2 %), and the softmax
+// denominator taken from a ones-row of V^T through the PV UMMA (+-0 %).
 struct AttParams {
   uint16_t* out;
   int B, H, N, head_dim;
@@ -95,8 +84,8 @@ L4P_DEVICE uint64_t exp2_poly2(uint64_t t2) {
   return pk2(pa, pb);
 }
 
-template <bool BF16, int POLY>
-__global__ void __launch_bounds__(kAttThreads, 1)
+template <bool BF16, int POLY, bool SPLIT>
+__global__ void __launch_bounds__(SPLIT ? kAttThreads4 : kAttThreads, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const AttParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -105,6 +94,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   __shared__ __align__(8) uint64_t bar_vfull[kVS], bar_vempty[kVS];
   __shared__ __align__(8) uint64_t bar_sfull[2], bar_sfree[2], bar_pfull[2], bar_pvdone[2];
   __shared__ uint32_t tmem_base_slot;
+  __shared__ float s_xchg[SPLIT ? 2 : 1][2][2][kTileM];  // SPLIT: [key-block parity][tile][half][row] partial row maxima / sums
+  constexpr uint32_t kSoftmaxThreads = SPLIT ? 256u : 128u;  // per tile
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -136,8 +127,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     for (int s = 0; s < kVS; ++s) { mbar_init(smem_u32(&bar_vfull[s]), 1); mbar_init(smem_u32(&bar_vempty[s]), 1); }
     for (int t = 0; t < 2; ++t) {
       mbar_init(smem_u32(&bar_sfull[t]), 1);
-      mbar_init(smem_u32(&bar_sfree[t]), 128);
-      mbar_init(smem_u32(&bar_pfull[t]), 128);
+      mbar_init(smem_u32(&bar_sfree[t]), kSoftmaxThreads);
+      mbar_init(smem_u32(&bar_pfull[t]), kSoftmaxThreads);
       mbar_init(smem_u32(&bar_pvdone[t]), 1);
     }
     fence_mbar_init();
@@ -210,9 +201,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         for (int kk = 0; kk < kTileN / 16; ++kk) {
           const uint32_t o = ((uint32_t)(kk & 3) * 32) >> 4;
           const uint64_t vdesc = umma_desc_make(va + (uint32_t)(kk >> 2) * ((kDPad * 128) >> 4) + o, hi128);
-          if (kPAlias)
-            umma_ts(d, tmem_base + (t == 0 ? kColS0 : kColS1) + (uint32_t)kk * 8u, vdesc, idesc_o, kk != 0 ? 1u : acc);
-          else if (kPTmem && t == 0)  // P_0 is the TMEM A operand: 8 columns per K = 16 step, no shared-memory traffic for P
+          if (t == 0)  // P_0 is the TMEM A operand: 8 columns per K = 16 step, no shared-memory traffic for P
             umma_ts(d, tmem_base + kColP0 + (uint32_t)kk * 8u, vdesc, idesc_o, kk != 0 ? 1u : acc);
           else
             umma_ss(d, umma_desc_make(pa + (uint32_t)(kk >> 2) * ((kTileM * 128) >> 4) + o, hi128), vdesc, idesc_o,
@@ -233,51 +222,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       for (int j = 0; j < nblk; ++j) {
         const int jn = j + 1;
         const int sk = jn % kKS, sv = j % kVS;
-#if L4P_ATT_P_ALIAS
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          mbar_wait(smem_u32(&bar_pfull[t]), (uint32_t)j & 1u);  // P_t(j) sits in S_t's columns, O_t rescaled
-          if (t == 0) mbar_wait(smem_u32(&bar_vfull[sv]), ((uint32_t)(j / kVS)) & 1u);
-          if (jn < nblk && t == 0) mbar_wait(smem_u32(&bar_kfull[sk]), ((uint32_t)(jn / kKS)) & 1u);
-          tc_fence_after();
-          if (leader) {
-            issue_pv(t, sv, j != 0 ? 1u : 0u);
-            if (t == 1) umma_commit(smem_u32(&bar_vempty[sv]));
-            if (jn < nblk) {
-              issue_s(t, sk);  // overwrites S_t / P_t(j) after PV_t(j) in pipe order
-              if (t == 1) umma_commit(smem_u32(&bar_kempty[sk]));
-            }
-          }
-          __syncwarp();
-        }
-#elif L4P_ATT_S_FIRST
-        // experiment (build with L4P_NVCC_EXTRA=-DL4P_ATT_S_FIRST=1): both tiles' S(j+1) before the first PV(j), so that
-        // S_1(j+1) does not queue behind P_0(j)
-        if (jn < nblk) {
-          mbar_wait(smem_u32(&bar_kfull[sk]), ((uint32_t)(jn / kKS)) & 1u);
-#pragma unroll
-          for (int t = 0; t < 2; ++t) {
-            mbar_wait(smem_u32(&bar_sfree[t]), (uint32_t)j & 1u);
-            tc_fence_after();
-            if (leader) {
-              issue_s(t, sk);
-              if (t == 1) umma_commit(smem_u32(&bar_kempty[sk]));
-            }
-            __syncwarp();
-          }
-        }
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          mbar_wait(smem_u32(&bar_pfull[t]), (uint32_t)j & 1u);
-          if (t == 0) mbar_wait(smem_u32(&bar_vfull[sv]), ((uint32_t)(j / kVS)) & 1u);
-          tc_fence_after();
-          if (leader) {
-            issue_pv(t, sv, j != 0 ? 1u : 0u);
-            if (t == 1) umma_commit(smem_u32(&bar_vempty[sv]));
-          }
-          __syncwarp();
-        }
-#else
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
           if (jn < nblk) {
@@ -302,70 +246,85 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           __syncwarp();
           ATT_STAMP(2, j, t * 4 + 2);
         }
-#endif
       }
     }
   } else {
     // ------------------------------------------------------------------ softmax warpgroups
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
-    const int t = (warp - 4) >> 2;            // tile
+    // NC = key columns of a 128-key block owned by one thread: the whole row (SPLIT = false) or half of it (SPLIT = true)
+    constexpr int NC = SPLIT ? 64 : 128;
+    if (SPLIT) asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+    else asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
+    const int wg = (warp - 4) >> 2;            // softmax warpgroup
+    const int t = SPLIT ? (wg >> 1) : wg;      // tile
+    const int h = SPLIT ? (wg & 1) : 0;        // column half
     const int q4 = warp & 3;                   // TMEM lane quarter
     const int r = q4 * 32 + lane;              // row in tile
     const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
-    const uint32_t tS = tmem_base + lane_addr + (t == 0 ? kColS0 : kColS1);
+    const uint32_t tS = tmem_base + lane_addr + (t == 0 ? kColS0 : kColS1) + (uint32_t)(h * NC);
     const uint32_t tO = tmem_base + lane_addr + (t == 0 ? kColO0 : kColO1);
     const uint32_t pRow = sP + t * kPBytes + (uint32_t)r * 128u;
     const uint32_t swz = (uint32_t)(r & 7);
     const float c = p.scale_log2;
+    const bool stamp = h == 0;                 // timeline role = tile
+    // this thread's share of the O row (rescale + epilogue): all 96 columns, or 48 per half
+    constexpr int OC = SPLIT ? kDPad / 2 : kDPad;
+    const uint32_t tOmine = tO + (uint32_t)(h * OC);
 
     float m_used = -INFINITY;
     float l = 0.f;
 
     for (int j = 0; j < nblk; ++j) {
-      ATT_STAMP(t, j, 0);
+      if (stamp) ATT_STAMP(t, j, 0);
       mbar_wait(smem_u32(&bar_sfull[t]), (uint32_t)j & 1u);
       tc_fence_after();
-      ATT_STAMP(t, j, 1);
-      uint32_t s[128];
-      tmem_ld32(tS + 0, s + 0);
-      tmem_ld32(tS + 32, s + 32);
-      tmem_ld32(tS + 64, s + 64);
-      tmem_ld32(tS + 96, s + 96);
+      if (stamp) ATT_STAMP(t, j, 1);
+      uint32_t s[NC];
+#pragma unroll
+      for (int cc = 0; cc < NC; cc += 32) tmem_ld32(tS + cc, s + cc);
       tmem_ld_wait();
-      ATT_STAMP(t, j, 2);
+      if (stamp) ATT_STAMP(t, j, 2);
       tc_fence_before();
       mbar_arrive(smem_u32(&bar_sfree[t]));
 
       float mx0 = __uint_as_float(s[0]), mx1 = __uint_as_float(s[1]), mx2 = __uint_as_float(s[2]),
             mx3 = __uint_as_float(s[3]);
 #pragma unroll
-      for (int i = 4; i < 128; i += 4) {
+      for (int i = 4; i < NC; i += 4) {
         mx0 = fmaxf(mx0, __uint_as_float(s[i]));
         mx1 = fmaxf(mx1, __uint_as_float(s[i + 1]));
         mx2 = fmaxf(mx2, __uint_as_float(s[i + 2]));
         mx3 = fmaxf(mx3, __uint_as_float(s[i + 3]));
       }
-      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * c;
+      float mxr = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      if (SPLIT) {
+        // both halves of a row must use the same reference maximum (they feed the same O accumulator): exchange the partial
+        // maxima. Double-buffered by key-block parity: the partner reads buffer (j & 1) after barrier j, this thread's next
+        // write to the same buffer happens after barrier j + 1, which the partner only reaches after that read.
+        s_xchg[j & 1][t][h][r] = mxr;
+        named_bar_sync(1u + (uint32_t)t, kSoftmaxThreads);
+        mxr = fmaxf(mxr, s_xchg[j & 1][t][h ^ 1][r]);
+      }
+      const float mx = mxr * c;
 
       if (j == 0) {
         m_used = mx;
       } else {
         const bool need = mx > m_used + kRescaleThreshold;
         if (__any_sync(0xffffffffu, need)) {
-          // rare: rescale the running output in TMEM (whole warp, each row with its own factor)
+          // rare: rescale the running output in TMEM (whole warp, each row with its own factor; the partner warp of the
+          // other half sees the same 32 row maxima, takes the same branch and rescales its own 48 columns)
           const float m_new = fmaxf(m_used, mx);
           const float alpha = ex2(m_used - m_new);
           mbar_wait(smem_u32(&bar_pvdone[t]), (uint32_t)(j - 1) & 1u);
           tc_fence_after();
 #pragma unroll
-          for (int cc = 0; cc < kDPad; cc += 32) {
-            uint32_t o[32];
-            tmem_ld32(tO + cc, o);
+          for (int cc = 0; cc < OC; cc += 16) {
+            uint32_t o[16];
+            tmem_ld16(tOmine + cc, o);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st16(tO + cc, o);
-            tmem_st16(tO + cc + 16, o + 16);
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st16(tOmine + cc, o);
           }
           tmem_st_wait();
           tc_fence_before();
@@ -374,14 +333,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
       }
 
-      ATT_STAMP(t, j, 3);
+      if (stamp) ATT_STAMP(t, j, 3);
       // p = exp2(s*c - m_used), row sum in fp32, pack pairs in place
-      // scale/subtract and the row sum run as packed f32x2; of every 16 scores, 6 take the polynomial exp2 on the
-      // FMA pipe and 10 the MUFU, which balances the two pipes (MUFU alone is the measured bound of this kernel)
+      // scale/subtract and the row sum run as packed f32x2; of every 16 scores, 2*POLY take the polynomial exp2 on the
+      // FMA pipe and the rest the MUFU, which balances the two pipes (16 MUFU results per clock and SM would otherwise need
+      // 2048 cycles per key block, more than the ~1600 cycles of its UMMAs)
       const uint64_t c2 = pk2(c, c), nm2 = pk2(-m_used, -m_used);
       uint64_t lsum0 = pk2(0.f, 0.f), lsum1 = pk2(0.f, 0.f);
 #pragma unroll
-      for (int i = 0; i < 128; i += 2) {
+      for (int i = 0; i < NC; i += 2) {
         const uint64_t t2 = fma2(pk2(__uint_as_float(s[i]), __uint_as_float(s[i + 1])), c2, nm2);
         uint64_t p2;
         const int slot = (i >> 1) & 7;  // pair index inside a group of 16 scores
@@ -393,7 +353,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           upk2(t2, a, b);
           p2 = pk2(ex2(a), ex2(b));
         }
-        if (!kLsumMma) { if (i & 2) lsum1 = add2(lsum1, p2); else lsum0 = add2(lsum0, p2); }
+        if (i & 2) lsum1 = add2(lsum1, p2); else lsum0 = add2(lsum0, p2);
         float p0, p1;
         upk2(p2, p0, p1);
         s[i >> 1] = pack2<BF16>(p0, p1);
@@ -404,24 +364,24 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         upk2(lsum1, b0, b1);
         l += (a0 + a1) + (b0 + b1);
       }
-      ATT_STAMP(t, j, 4);
+      if (stamp) ATT_STAMP(t, j, 4);
 
-      if (j > 0) mbar_wait(smem_u32(&bar_pvdone[t]), (uint32_t)(j - 1) & 1u);  // P_t smem is free again
-      ATT_STAMP(t, j, 5);
-      if (kPAlias || (kPTmem && t == 0)) {
+      if (j > 0) mbar_wait(smem_u32(&bar_pvdone[t]), (uint32_t)(j - 1) & 1u);  // P_t is free again
+      if (stamp) ATT_STAMP(t, j, 5);
+      if (t == 0) {
         // tile 0: P goes straight back to TMEM (row = lane, two probabilities per 32-bit column) as the A operand of PV
-        const uint32_t tP = kPAlias ? tS : tmem_base + lane_addr + kColP0;
-        tmem_st16(tP + 0, s + 0);
-        tmem_st16(tP + 16, s + 16);
-        tmem_st16(tP + 32, s + 32);
-        tmem_st16(tP + 48, s + 48);
+        const uint32_t tP = tmem_base + lane_addr + kColP0 + (uint32_t)(h * (NC / 2));
+#pragma unroll
+        for (int cc = 0; cc < NC / 2; cc += 16) tmem_st16(tP + cc, s + cc);
         tmem_st_wait();
         tc_fence_before();
       } else {
 #pragma unroll
-        for (int u = 0; u < 16; ++u) {
-          // 16-byte unit u: keys [8u, 8u+8); chunk = u/8; swizzled unit inside the 128-byte row
-          const uint32_t addr = pRow + (uint32_t)(u >> 3) * (kTileM * 128) + ((((uint32_t)u & 7u) ^ swz) << 4);
+        for (int u = 0; u < NC / 8; ++u) {
+          // 16-byte unit: keys [8 uu, 8 uu + 8) of the block; chunk = uu / 8 (= the column half when SPLIT); swizzled unit
+          // inside the 128-byte row
+          const int uu = u + h * (NC / 8);
+          const uint32_t addr = pRow + (uint32_t)(uu >> 3) * (kTileM * 128) + ((((uint32_t)uu & 7u) ^ swz) << 4);
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(s[4 * u]), "r"(s[4 * u + 1]),
                        "r"(s[4 * u + 2]), "r"(s[4 * u + 3])
                        : "memory");
@@ -429,30 +389,29 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         fence_proxy_async();
       }
       mbar_arrive(smem_u32(&bar_pfull[t]));
-      ATT_STAMP(t, j, 6);
+      if (stamp) ATT_STAMP(t, j, 6);
     }
 
     // ---- epilogue: O_t / l -> global
     mbar_wait(smem_u32(&bar_pvdone[t]), (uint32_t)(nblk - 1) & 1u);
     tc_fence_after();
-    if (kLsumMma) {  // l = O[:, head_dim] (head_dim is a multiple of 8 < 96: column head_dim is index 0 of a 16-column load)
-      uint32_t lo[16];
-      tmem_ld16(tO + (uint32_t)p.head_dim, lo);
-      tmem_ld_wait();
-      l = __uint_as_float(lo[0]);
+    if (SPLIT) {  // row sum = sum of both halves (buffer of parity nblk: not in use by the last key block's exchange)
+      s_xchg[nblk & 1][t][h][r] = l;
+      named_bar_sync(1u + (uint32_t)t, kSoftmaxThreads);
+      l += s_xchg[nblk & 1][t][h ^ 1][r];
     }
     const float inv_l = 1.0f / l;
-    const int b = bh / p.H, h = bh - b * p.H;
+    const int b = bh / p.H, hh = bh - b * p.H;
     const long long row = (long long)b * p.N + (long long)pair * 2 * kTileM + t * kTileM + r;
-    uint16_t* dst = p.out + row * ((long long)p.H * p.head_dim) + (long long)h * p.head_dim;
+    uint16_t* dst = p.out + row * ((long long)p.H * p.head_dim) + (long long)hh * p.head_dim;
 #pragma unroll
-    for (int cc = 0; cc < kDPad; cc += 32) {
-      uint32_t o[32];
-      tmem_ld32(tO + cc, o);
+    for (int cc = 0; cc < OC; cc += 16) {
+      uint32_t o[16];
+      tmem_ld16(tOmine + cc, o);
       tmem_ld_wait();
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const int col = cc + g * 8;
+      for (int g = 0; g < 2; ++g) {
+        const int col = h * OC + cc + g * 8;
         if (col < p.head_dim) {  // head_dim is a multiple of 8
           float f[8];
 #pragma unroll
@@ -477,10 +436,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     tmem_dealloc(tmem_base, 512);
   }
 }
-
-// csrc/attention_pair.cu: experimental cta_group::2 variant (opt-in, L4P_ATT_PAIR=1)
-int attention_pair_launch(const void* q, const void* k, const void* vt, void* out, int B, int H, int N, int head_dim,
-                          float scale, int bf16, int poly, void* stream);
 
 }  // namespace l4p
 
@@ -524,24 +479,29 @@ extern "C" int l4p_attention(const void* q, const void* k, const void* vt, void*
     poly = e ? atoi(e) : 2;
     if (poly < 0 || poly > 3) poly = 0;
   }
-  static int pair_mode = -1;
-  if (pair_mode < 0) {
-    const char* e = getenv("L4P_ATT_PAIR");
-    pair_mode = (e && atoi(e) == 1) ? 1 : 0;
+  // 4 half-row softmax warpgroups by default; L4P_ATT_SPLIT=0 selects the round-1 kernel (2 full-row warpgroups)
+  static int split = -1;
+  if (split < 0) {
+    const char* e = getenv("L4P_ATT_SPLIT");
+    split = (e && atoi(e) == 0) ? 0 : 1;
   }
-  if (pair_mode == 1 && prof == nullptr && N % (4 * kTileM) == 0)
-    return attention_pair_launch(q, k, vt, out, B, H, N, head_dim, scale, bf16, poly, stream);
   typedef void (*KFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const AttParams);
-  static const KFn table[2][4] = {
-      {attention_kernel<false, 0>, attention_kernel<false, 1>, attention_kernel<false, 2>, attention_kernel<false, 3>},
-      {attention_kernel<true, 0>, attention_kernel<true, 1>, attention_kernel<true, 2>, attention_kernel<true, 3>}};
-  KFn kfn = table[bf16 ? 1 : 0][poly];
-  static bool attr_set[2][4] = {};
-  if (!attr_set[bf16 ? 1 : 0][poly]) {
+  static const KFn table[2][2][4] = {
+      {{attention_kernel<false, 0, false>, attention_kernel<false, 1, false>, attention_kernel<false, 2, false>,
+        attention_kernel<false, 3, false>},
+       {attention_kernel<true, 0, false>, attention_kernel<true, 1, false>, attention_kernel<true, 2, false>,
+        attention_kernel<true, 3, false>}},
+      {{attention_kernel<false, 0, true>, attention_kernel<false, 1, true>, attention_kernel<false, 2, true>,
+        attention_kernel<false, 3, true>},
+       {attention_kernel<true, 0, true>, attention_kernel<true, 1, true>, attention_kernel<true, 2, true>,
+        attention_kernel<true, 3, true>}}};
+  KFn kfn = table[split][bf16 ? 1 : 0][poly];
+  static bool attr_set[2][2][4] = {};
+  if (!attr_set[split][bf16 ? 1 : 0][poly]) {
     L4P_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmem));
-    attr_set[bf16 ? 1 : 0][poly] = true;
+    attr_set[split][bf16 ? 1 : 0][poly] = true;
   }
   const int grid = B * H * (N / (2 * kTileM));
-  L4P_CHECK_CUDA(launch_pdl(kfn, dim3(grid), dim3(kAttThreads), (size_t)kAttSmem, (cudaStream_t)stream, tmQ, tmK, tmV, p));
+  L4P_CHECK_CUDA(launch_pdl(kfn, dim3(grid), dim3(split ? kAttThreads4 : kAttThreads), (size_t)kAttSmem, (cudaStream_t)stream, tmQ, tmK, tmV, p));
   return L4P_OK;
 }

@@ -10,7 +10,8 @@ from pathlib import Path
 from typing import Optional
 
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "libl4p_b200.so"
+# L4P_LIB selects an experiment build of the same ABI (tools/ A/B runs only; see l4p_b200/build.py L4P_BUILD_TAG)
+LIB_PATH = Path(os.environ["L4P_LIB"]).resolve() if os.environ.get("L4P_LIB") else _PKG / "libl4p_b200.so"
 
 ACT_NONE, ACT_GELU, ACT_RELU, ACT_EXP = 0, 1, 2, 3
 STORE_ROWMAJOR, STORE_QKV, STORE_CONVT, STORE_HEAD1X1, STORE_HYPER = 0, 1, 2, 3, 4

@@ -169,21 +169,38 @@ class L4P_VideoMAE(torch.nn.Module):
         # The heads only read the encoder features: they are independent jobs (the reference runs them one after the
         # other, l4p_videomae.py:299-328). Each job runs on its own CUDA stream so that the low-occupancy kernels of
         # one head (low-resolution pyramid levels, token-side GEMMs, small solves) overlap the big kernels of another.
-        common = dict(enc_features_bpc_2dlist=enc_features_bpc_2dlist, time_strides=time_strides, _batched_windows=batched)
+        common = dict(enc_features_bpc_2dlist=enc_features_bpc_2dlist, time_strides=time_strides, _batched_windows=batched,
+                      _max_windows_per_pass=self.max_windows_per_pass)
         if shard is not None:
             common["_window_shard"] = shard
+
+        def head_job(task: str):
+            head = self.task_heads[task]
+            if task != "track_2d" or B == 1:
+                return head.forward_windowed(**common, **data)
+            # Batched clips (BASELINE.json configs[2]): the encoder and the dense heads run on all clips at once; the tracker
+            # keeps the reference's per-clip semantics (sparse_heads.py:241 asserts B == 1), so it is called clip by clip
+            # on that clip's rows of the batched encoder result and the per-clip tracks are stacked along the batch axis.
+            per_clip = []
+            for b in range(B):
+                feats_b = [[None if f is None else f[b:b + 1] for f in win] for win in enc_features_bpc_2dlist]
+                data_b = {k: (v[b:b + 1] if torch.is_tensor(v) and v.dim() > 0 and v.shape[0] == B else v)
+                          for k, v in data.items()}
+                per_clip.append(head.forward_windowed(enc_features_bpc_2dlist=feats_b, time_strides=time_strides, **data_b))
+            return {k: torch.cat([o[k] for o in per_clip], dim=0) for k in per_clip[0]}
+
         jobs = []
         joint_alignment_possible = "depth" in tasks and "camray" in tasks
         if self.joint_alignment and joint_alignment_possible:
             for task in ["track_2d", "dyn_mask", "flow_2d_backward"]:
                 if task in tasks:
-                    jobs.append(lambda task=task: self.task_heads[task].forward_windowed(**common, **data))
+                    jobs.append(lambda task=task: head_job(task))
             jobs.append(lambda: joint_windowed_estimation(["depth", "camray"], self.task_heads, **common, **data))
         else:
             if self.joint_alignment:
                 print("Joint alignment is not possible as depth or camray tasks are not present")
             for task in tasks:
-                jobs.append(lambda task=task: self.task_heads[task].forward_windowed(**common, **data))
+                jobs.append(lambda task=task: head_job(task))
         for res in self._run_jobs(jobs, data["rgb_b3thw"].device):
             out.update(res)
         return out

@@ -41,6 +41,17 @@ def _taps16(feats: Sequence[torch.Tensor], hooks: Sequence[int], dtype: torch.dt
     return out, B
 
 
+def _decode_chunked(fn, batched, chunk: Optional[int]) -> torch.Tensor:
+    """`fn(feature_list) -> [rows, ...]` over the rows (windows x clips) of a batched encoder result in chunks of `chunk` rows,
+    concatenated. Keeps the DPT activation memory (~1.5-2 GB per window and head) independent of the video length, like the
+    reference's one-window-at-a-time decode (dense_heads.py:99-106), while each pass still batches `chunk` windows."""
+    n = next(f for f in batched if f is not None).shape[0]
+    if not chunk or n <= chunk:
+        return fn(batched)
+    from ..videomae import slice_features
+    return torch.cat([fn(slice_features(batched, i, min(n, i + chunk))) for i in range(0, n, chunk)], dim=0)
+
+
 class VideoMAEFlowDPTHead(nn.Module):
     """2D optical flow DPT head (dense_heads.py:20-143)."""
 
@@ -86,19 +97,21 @@ class VideoMAEFlowDPTHead(nn.Module):
         encoder result (L4P_VideoMAE passes `_batched_windows`) is consumed in one DPT launch sequence."""
         batched = kwargs.pop("_batched_windows", None)
         shard = kwargs.pop("_window_shard", None)
+        chunk = kwargs.pop("_max_windows_per_pass", None)
         window_size = img_info[0] if self.output_size is None else self.output_size[0]
         key = f"{self.task_name}_est_{self.task_suffix}"
+        run = lambda f: self.forward(f, img_info=img_info, **kwargs)[key]
         if shard is not None:
             # multi-GPU: this rank holds the features of windows [shard.start, shard.start + shard.count) only
             from ...parallel import gather_window_outputs
             local = []
             if shard.count > 0:
-                out = self.forward(batched, img_info=img_info, **kwargs)[key]
+                out = _decode_chunked(run, batched, chunk)
                 local = list(out.reshape(shard.count, -1, *out.shape[1:]).unbind(0))
             return gather_window_outputs([local], shard)[0]
         if batched is not None:
             nW = len(enc_features_bpc_2dlist)
-            out = self.forward(batched, img_info=img_info, **kwargs)[key]  # [(B*nW), C, T, H, W], window-major
+            out = _decode_chunked(run, batched, chunk)  # [(B*nW), C, T, H, W], window-major
             return list(out.reshape(nW, -1, *out.shape[1:]).unbind(0))
         outs = []
         for win_id in range(len(enc_features_bpc_2dlist)):
@@ -113,6 +126,7 @@ class VideoMAEFlowDPTHead(nn.Module):
                          **kwargs) -> Dict[str, torch.Tensor]:
         if time_strides is None:
             kwargs.pop("_batched_windows", None)
+            kwargs.pop("_max_windows_per_pass", None)
             return self.forward(enc_features_bpc_2dlist[0], img_info=img_info, intrinsics_b44t=intrinsics_b44t, **kwargs)
         if self.output_size is None:
             window_size, H, W = img_info
@@ -234,21 +248,23 @@ class VideoMAETraj3DDPTHead(VideoMAEFlowDPTHead):
                          intrinsics_b44t=None, **kwargs):
         batched = kwargs.pop("_batched_windows", None)
         shard = kwargs.pop("_window_shard", None)
+        chunk = kwargs.pop("_max_windows_per_pass", None)
         if time_strides is None:
             return self.forward(enc_features_bpc_2dlist[0], img_info=img_info, intrinsics_b44t=intrinsics_b44t, **kwargs)
         window_size = self.output_size[0] if self.output_size is not None else img_info[0]
         T = int(time_strides[-1] + window_size)
         nW = time_strides.shape[0]
         rays_all = None
+        run = lambda f: self.rays(f, img_info)
         if shard is not None:
             from ...parallel import gather_window_outputs
             local = []
             if shard.count > 0:
-                r = self.rays(batched, img_info)
+                r = _decode_chunked(run, batched, chunk)
                 local = list(r.reshape(shard.count, -1, *r.shape[1:]).unbind(0))
             rays_all = gather_window_outputs([local], shard)[0]
         elif batched is not None:
-            r = self.rays(batched, img_info)
+            r = _decode_chunked(run, batched, chunk)
             rays_all = r.reshape(nW, -1, *r.shape[1:])
         key = f"{self.task_name}_est_{self.task_suffix}"
         est = None
@@ -276,6 +292,7 @@ def joint_windowed_estimation(task_names: List[str], task_heads: nn.ModuleDict, 
     sequential across windows and runs on the device (KabaschUmeyama3DAligner)."""
     batched = kwargs.pop("_batched_windows", None)
     shard = kwargs.pop("_window_shard", None)
+    chunk = kwargs.pop("_max_windows_per_pass", None)
     out_all_tasks: Dict[str, torch.Tensor] = {}
     if time_strides is None:
         for task_name in task_names:
@@ -297,15 +314,15 @@ def joint_windowed_estimation(task_names: List[str], task_heads: nn.ModuleDict, 
         from ...parallel import gather_window_outputs
         dl, rl = [], []
         if shard.count > 0:
-            d = depth_head.forward(batched, img_info=img_info)[dkey]
+            d = _decode_chunked(lambda f: depth_head.forward(f, img_info=img_info)[dkey], batched, chunk)
             dl = list(d.reshape(shard.count, -1, *d.shape[1:]).unbind(0))
-            r = cam_head.rays(batched, img_info)
+            r = _decode_chunked(lambda f: cam_head.rays(f, img_info), batched, chunk)
             rl = list(r.reshape(shard.count, -1, *r.shape[1:]).unbind(0))
         depth_w, rays_w = gather_window_outputs([dl, rl], shard)
     elif batched is not None:
-        d = depth_head.forward(batched, img_info=img_info)[dkey]
+        d = _decode_chunked(lambda f: depth_head.forward(f, img_info=img_info)[dkey], batched, chunk)
         depth_w = list(d.reshape(nW, -1, *d.shape[1:]).unbind(0))
-        r = cam_head.rays(batched, img_info)
+        r = _decode_chunked(lambda f: cam_head.rays(f, img_info), batched, chunk)
         rays_w = list(r.reshape(nW, -1, *r.shape[1:]).unbind(0))
     else:
         depth_w = [depth_head.forward(enc_features_bpc_2dlist[w], img_info=img_info)[dkey] for w in range(nW)]

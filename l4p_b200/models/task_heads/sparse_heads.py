@@ -166,7 +166,6 @@ class MaskDecoder(nn.Module):
 # ------------------------------------------------------------------------------------------- the head
 class VideoMAETrack2DSamHead(nn.Module):
     compute_dtype = torch.float16
-    residual16 = __import__("os").environ.get("L4P_TRACK_RES16", "0") == "1"   # experiment, see _decode step (4)
 
     def __init__(self, task_name: str = "track_2d", prompt_embed_dim: int = 1408,
                  image_size: Tuple[int, int, int] = (16, 224, 224), patch_size: Tuple[int, int, int] = (2, 14, 14),
@@ -365,19 +364,6 @@ class VideoMAETrack2DSamHead(nn.Module):
                 q16 = q16.unsqueeze(0).expand(G, -1, -1).reshape(G * Pn, -1)
             ao = torch.empty(G * Pn, q16.shape[-1], device=dev, dtype=dt)
             ops.image_attention(q16.contiguous(), k.contiguous(), v.contiguous(), ao, G, a["heads"], 1.0 / math.sqrt(a["hd"]))
-            if self.residual16:
-                # experiment (L4P_TRACK_RES16=1): the per-query video-token stream stays 16-bit between the two layers
-                # (residual read, out-projection store and LayerNorm input 2 instead of 4 bytes per element)
-                new16 = torch.empty(G * Pn, C, device=dev, dtype=dt)
-                if shared:     # residual = the shared fp32 tokens as a broadcast table (row % P)
-                    ops.linear(ao, a["o"]["w"], bias=a["o"]["b"], res_f32=keys32, res_row_mod=Pn, out_16=new16)
-                else:
-                    ops.linear(ao, a["o"]["w"], bias=a["o"]["b"], res_16=keys16, out_16=new16)
-                keys16 = torch.empty(G * Pn, C, device=dev, dtype=dt)
-                ops.layernorm16(new16, w["n4"][0], w["n4"][1], w["n4"][2], keys16)
-                keys32 = None
-                shared = False
-                continue
             new32 = torch.empty(G * Pn, C, device=dev, dtype=torch.float32)
             ops.linear(ao, a["o"]["w"], bias=a["o"]["b"], res_f32=keys32, res_row_mod=Pn if shared else 0, out_f32=new32)
             keys16 = torch.empty(G * Pn, C, device=dev, dtype=dt)

@@ -97,6 +97,17 @@ class FeatureList(list):
         self.taps16 = taps16
 
 
+def slice_features(feats: "FeatureList", start: int, stop: int) -> "FeatureList":
+    """Rows [start, stop) of the batch dimension of a batched FeatureList (views, no copies): lets the heads decode a long
+    video's windows in bounded chunks while the encoder result stays one batch."""
+    items = [None if f is None else f[start:stop] for f in feats]
+    taps = {}
+    for k, t in getattr(feats, "taps16", {}).items():
+        ntok = feats[k].shape[1]
+        taps[k] = t[start * ntok:stop * ntok]
+    return FeatureList(items, taps)
+
+
 def _require_device(x: torch.Tensor) -> None:
     if not x.is_cuda:
         raise _l.L4PError("VideoMAEEncoder.forward needs a CUDA tensor: the l4p_b200 hot path has no CPU fallback")

@@ -79,7 +79,6 @@ SPLITK = True
 
 
 IMGATT_TC = __import__("os").environ.get("L4P_IMGATT_TC", "0") == "1"
-ATT_LSUM_MMA = __import__("os").environ.get("L4P_ATT_LSUM_MMA", "0") == "1"  # experiment, needs a -DL4P_ATT_LSUM_MMA=1 build
 _IMGATT_WS: Dict[Tuple[int, int], torch.Tensor] = {}
 
 
@@ -259,10 +258,6 @@ def attention(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, out: torch.Ten
         raise _l.L4PError(f"attention: shapes q{tuple(q.shape)} k{tuple(k.shape)} vt{tuple(vt.shape)}")
     if out.numel() != B * N * H * head_dim:
         raise _l.L4PError(f"attention: out has {out.numel()} elements, expected {B * N * H * head_dim}")
-    if ATT_LSUM_MMA:  # experiment: the kernel takes the softmax denominator from a ones row in the pad of V^T
-        if not head_dim < dpad:
-            raise _l.L4PError("L4P_ATT_LSUM_MMA needs head_dim < head_dim_pad")
-        vt[:, :, head_dim, :] = 1
     ev = None
     if ATTN_EVENTS is not None:
         ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))

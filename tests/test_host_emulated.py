@@ -215,7 +215,9 @@ def test_orchestrator_single_window_dispatch(g, cpu_kernels):
 
 
 def test_window_chunking_is_transparent(cpu_kernels):
-    """`max_windows_per_pass` only changes how many encoder passes are made, not the result."""
+    """`max_windows_per_pass` only changes how many encoder / per-head decoder passes are made, not the result (the decode of
+    a long video is chunked too since round 2; the stand-in's CPU convolutions pick batch-size-dependent algorithms, hence
+    fp32 round-off that flips 16-bit roundings (~2e-4 rel-L2 on flow, like batched vs per-window decode) instead of bit equality)."""
     tasks = ["flow_2d_backward"]
     rgb = rnd((1, 3, 8, 56, 56), 16)
     outs = []
@@ -223,7 +225,7 @@ def test_window_chunking_is_transparent(cpu_kernels):
         model = _tiny_model(tasks)
         model.max_windows_per_pass = per_pass
         outs.append(model.forward(dict(rgb_b3thw=rgb, intrinsics_b44t=None, img_info=IMG), tasks)["flow_2d_backward_est_b2thw"])
-    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    assert rel_l2(outs[1], outs[0]) < 1e-3 and rel_l2(outs[2], outs[0]) < 1e-3, (rel_l2(outs[1], outs[0]), rel_l2(outs[2], outs[0]))
 
 
 def test_two_window_stitching_rules_against_oracle(cpu_kernels):
@@ -418,18 +420,3 @@ def test_bf16_operands_through_the_same_path(g, cpu_kernels):
     assert feats[-1].dtype == torch.float32
     assert rel_l2(out["depth_est_b1thw"], g["depth_windowed"]) < 5e-3
     assert rel_l2(out["flow_2d_backward_est_b2thw"], g["flow_windowed"]) < 1.5e-2
-
-
-def test_track_head_16bit_token_stream_experiment(g, cpu_kernels):
-    """Opt-in `L4P_TRACK_RES16=1` (VideoMAETrack2DSamHead.residual16): the per-query video-token stream between the two
-    two-way layers kept 16-bit (existing RES32|OUT16 / RES16|OUT16 GEMM epilogues + layernorm16). Same tracks as the
-    reference goldens within the same bounds as the default path; at full size vs the live reference: 0.005-0.007 px."""
-    enc = _encoder()
-    rgb = rnd((1, 3, 8, 56, 56), 16)
-    starts = torch.arange(0, 8 - 4 + 1, 2)
-    f2d = _windows(enc, rgb, starts)
-    trk = _tracker()
-    trk.residual16 = True
-    o = trk.forward_windowed(f2d, Q, torch.ones(1, 4), time_strides=starts)
-    _check_tracks(o, g)
-    assert cpu_kernels.CALLS["layernorm16"] > 3      # LayerNorm3d of the mask decoder + the two token-stream norms per call

@@ -212,7 +212,8 @@ def test_product_path_never_imports_the_oracle():
         assert not pat.search(f.read_text()), f"{f} references the oracle / the reference tree"
     bench = (root / "bench.py").read_text()
     uses = [m.start() for m in re.finditer(r"^\s*(from|import)\s+oracle\b", bench, re.M)]
-    lo, hi = bench.index("def cpu_baseline_sample"), bench.index("def run_reference")
+    # only the comparator legs (`_port_sample`, `reference_cpu`: the cpu_baseline block and the --impl reference arm)
+    lo, hi = bench.index("def _port_sample"), bench.index("def run_reference")
     assert uses and all(lo < u < hi for u in uses)
 
 

@@ -1,8 +1,9 @@
-"""A/B of the production attention kernel against the experimental CTA-pair variant (csrc/attention_pair.cu, L4P_ATT_PAIR=1):
-parity vs fp32 torch on the same rounded operands, then back-to-back timing. The env var is read once per process, so each
-arm runs in its own subprocess; wrap the whole call in `timeout` on the GPU box (every device-side wait is bounded and traps).
+"""A/B of two arms of the attention kernel selected by an environment variable (default: L4P_ATT_SPLIT=0 -> the round-1
+kernel with two full-row softmax warpgroups, 1 -> four half-row warpgroups): parity vs fp32 torch on the same rounded
+operands, then back-to-back timing. The variable is read once per process, so each arm runs in its own subprocess; wrap the
+whole call in `timeout` on the GPU box (every device-side wait is bounded and traps).
 
-    timeout 300 python tools/att_pair_ab.py            # both arms, B=1 and B=8
+    timeout 300 python tools/att_pair_ab.py [ENVVAR [value ...]]      # e.g. L4P_ATT_POLY 0 1 2 3
 """
 import os
 import subprocess
@@ -10,10 +11,11 @@ import sys
 
 ARM = os.environ.get("_ATT_ARM")
 if ARM is None:
-    for arm in ("0", "1"):
-        env = dict(os.environ, _ATT_ARM=arm, L4P_ATT_PAIR=arm)
+    var = sys.argv[1] if len(sys.argv) > 1 else "L4P_ATT_SPLIT"
+    for arm in (sys.argv[2:] or ["0", "1"]):
+        env = dict(os.environ, _ATT_ARM=arm, **{var: arm})
         r = subprocess.run([sys.executable, __file__], env=env, capture_output=True, text=True, timeout=240)
-        print(f"--- L4P_ATT_PAIR={arm} (exit {r.returncode})\n{r.stdout}{r.stderr[-2000:]}")
+        print(f"--- {var}={arm} (exit {r.returncode})\n{r.stdout}{r.stderr[-2000:]}")
     sys.exit(0)
 
 import torch  # noqa: E402
