@@ -252,7 +252,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     // ------------------------------------------------------------------ softmax warpgroups
     // NC = key columns of a 128-key block owned by one thread: the whole row (SPLIT = false) or half of it (SPLIT = true)
     constexpr int NC = SPLIT ? 64 : 128;
-    if (SPLIT) asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+    // setmaxnreg moves registers inside the CTA's launch-time allocation only (640 threads x 96): 128 x 56 + 512 x 104 fits,
+    // 112 does not (the third warpgroup's request would block forever)
+    if (SPLIT) asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
     else asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
     const int wg = (warp - 4) >> 2;            // softmax warpgroup
     const int t = SPLIT ? (wg >> 1) : wg;      // tile

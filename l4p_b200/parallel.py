@@ -14,6 +14,17 @@ import torch
 import torch.distributed as dist
 
 
+def _all_gather_into(out: torch.Tensor, inp: torch.Tensor, group=None) -> None:
+    """`dist.all_gather_into_tensor`; gloo has no CUDA all-gather, so under gloo (the CPU test backend, also used to put two
+    test ranks on ONE GPU) device tensors are staged through the host. NCCL - the product path - gathers in place."""
+    if inp.is_cuda and dist.get_backend(group) == "gloo":
+        host = torch.empty(out.shape, dtype=out.dtype)
+        dist.all_gather_into_tensor(host, inp.detach().cpu().contiguous(), group=group)
+        out.copy_(host)
+    else:
+        dist.all_gather_into_tensor(out, inp, group=group)
+
+
 def contiguous_partition(n_units: int, world: int) -> List[Tuple[int, int]]:
     """(start, count) per rank: contiguous blocks of ceil(n/world) units, so that overlap neighbours of a long video
     are mostly local (cfg 4); trailing ranks may get fewer (or zero) units."""
@@ -75,7 +86,7 @@ def gather_window_outputs(local: Sequence[Sequence[torch.Tensor]], shard: Window
             packed[w, off:off + n] = local[k][w].reshape(-1).float()
             off += n
     gathered = torch.empty(world * per, unit, device=dev, dtype=torch.float32)
-    dist.all_gather_into_tensor(gathered, packed, group=shard.group)
+    _all_gather_into(gathered, packed, shard.group)
     parts = contiguous_partition(shard.n_windows, world)
     out: List[List[torch.Tensor]] = [[] for _ in sizes]
     for r, (_, cnt) in enumerate(parts):
@@ -111,7 +122,7 @@ def gather_query_outputs(local: Sequence[Optional[torch.Tensor]], n_queries: int
     if count > 0:
         packed[:count] = torch.cat([t[0].reshape(count, -1).float() for t in local], dim=1)
     gathered = torch.empty(world * per, unit, device=dev, dtype=torch.float32)
-    dist.all_gather_into_tensor(gathered, packed, group=group)
+    _all_gather_into(gathered, packed, group)
     rows = torch.cat([gathered[r * per:r * per + cnt] for r, (_, cnt) in enumerate(parts)], dim=0)   # [n_queries, unit]
     out, off = [], 0
     for n, (shape, dtype) in zip(sizes, meta0):
@@ -125,5 +136,5 @@ def gather_clip_outputs(packed: torch.Tensor, group=None) -> torch.Tensor:
     [world, clips_per_rank, unit] on every rank (clip i sits at [i % world, i // world])."""
     world = dist.get_world_size(group)
     out = torch.empty(world, *packed.shape, device=packed.device, dtype=packed.dtype)
-    dist.all_gather_into_tensor(out.view(world * packed.shape[0], *packed.shape[1:]), packed.contiguous(), group=group)
+    _all_gather_into(out.view(world * packed.shape[0], *packed.shape[1:]), packed.contiguous(), group)
     return out

@@ -13,6 +13,9 @@ from typing import Dict, Iterable, Tuple
 import torch
 
 
+PEAKY_HEATMAP = 8.0
+
+
 def _gen(seed: int, key: str) -> torch.Generator:
     g = torch.Generator(device="cpu")
     g.manual_seed((zlib.crc32(key.encode()) ^ (seed * 0x9E3779B1)) & 0x7FFFFFFF)
@@ -39,6 +42,11 @@ def synth_tensor(key: str, shape: Tuple[int, ...], seed: int = 0, peaky: bool = 
         w = (torch.rand(shape, generator=g) * 2 - 1) * a
         if peaky and key.endswith("attn.qkv.weight"):
             w *= 4.0
+        if peaky and key.endswith("output_hypernetworks_mlps.0.layers.2.weight"):
+            # the track head's trajectory heat-map logits x PEAKY_HEATMAP: with reference-style initialisation the logits have
+            # a standard deviation of ~1.3 over 16x64x64 cells, i.e. a near-uniform soft-argmax that sits at the image centre
+            # for every query; x8 makes the expectation follow the logit maxima across the image
+            w *= PEAKY_HEATMAP
         return w
     u = torch.rand(shape, generator=g) * 2 - 1
     if key.endswith("weight"):  # norm scales
