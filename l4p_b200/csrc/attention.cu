@@ -10,13 +10,12 @@
 //                works while the softmax warps run
 //   warp 2       TMEM allocator (512 columns: S0 | S1 | O0 | O1 | P0)
 //   SPLIT = false (384 threads): warps 4..7 softmax warpgroup for tile 0, warps 8..11 for tile 1, one query row per thread
-//   SPLIT = true  (640 threads, default): FOUR softmax warpgroups, two per tile: warps 4..7 / 8..11 own key columns
-//                [0,64) / [64,128) of tile 0's rows, warps 12..15 / 16..19 the same for tile 1. Measured (round 2,
-//                profiles/attention_r2.md): the UMMAs of one key block need ~1600 cycles of the tensor pipe, the two
-//                full-row warpgroups needed ~2850 (two warps per SM sub-partition cannot hide the MUFU / TMEM / FMA
-//                latencies: 57 % issue utilisation); four half-row warpgroups issue the same instructions from four
-//                warps per sub-partition. The halves exchange their partial row maximum through shared memory (one
-//                store, one 256-thread named barrier, one load per key block) so both use the same reference maximum.
+//   SPLIT = true  (640 threads, opt-in L4P_ATT_SPLIT=1): FOUR softmax warpgroups, two per tile: warps 4..7 / 8..11 own key columns
+//                [0,64) / [64,128) of tile 0's rows, warps 12..15 / 16..19 the same for tile 1; the halves exchange their
+//                partial row maximum through shared memory (one store, one 256-thread named barrier, one load per key
+//                block) so both use the same reference maximum. Measured in round 2 (profiles/attention_r2.md): the exp
+//                phase does not get shorter with half the scores per thread (the MUFU / FMA pipes of the sub-partition are
+//                shared by the two halves, which run in lockstep), the exchange adds ~200 cycles: 241 vs 218 us at B = 8.
 //
 // Softmax: fp32 scores from TMEM, running max with lazy rescale (O is only rescaled in TMEM when the row max
 // grew by more than 2^8), exp2 with the scale folded into one FFMA, fp32 row sums, P rounded to the operand
@@ -481,11 +480,12 @@ extern "C" int l4p_attention(const void* q, const void* k, const void* vt, void*
     poly = e ? atoi(e) : 2;
     if (poly < 0 || poly > 3) poly = 0;
   }
-  // 4 half-row softmax warpgroups by default; L4P_ATT_SPLIT=0 selects the round-1 kernel (2 full-row warpgroups)
+  // 2 full-row softmax warpgroups by default; L4P_ATT_SPLIT=1 selects the 4 half-row warpgroup variant (measured 10 % slower,
+  // kept parity-tested: tests/test_gemm_gpu.py::test_attention_split_variant)
   static int split = -1;
   if (split < 0) {
     const char* e = getenv("L4P_ATT_SPLIT");
-    split = (e && atoi(e) == 0) ? 0 : 1;
+    split = (e && atoi(e) == 1) ? 1 : 0;
   }
   typedef void (*KFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const AttParams);
   static const KFn table[2][2][4] = {

@@ -1,0 +1,78 @@
+"""Checkpoint ingestion end to end on the device (SURVEY.md §8f N1 + N4): seeded weights -> a Lightning-layout checkpoint
+file ({"state_dict": {"l4p_model....": tensor}}, the reference's key set incl. the aliased DPT keys) -> `prepare_model`
+(l4p/models/utils.py:15-60 signature) -> strict load -> ONE packed weight arena, fp32 masters released -> `predict_step`.
+The reloaded, packed model must compute what the directly-filled model computes."""
+import os
+import shutil
+from pathlib import Path
+
+import pytest
+import torch
+
+from tests.util import rel_l2, synth_intrinsics, synth_rgb
+
+pytestmark = pytest.mark.gpu
+
+
+def _scratch(tmp_path: Path) -> Path:
+    shm = Path("/dev/shm")
+    if shm.is_dir() and shutil.disk_usage(shm).free > 8 << 30:     # 5.7 GB of fp32 parameters
+        d = shm / f"l4p_ckpt_{os.getpid()}"
+        d.mkdir(exist_ok=True)
+        return d
+    return tmp_path
+
+
+def test_lightning_checkpoint_round_trip_through_prepare_model(tmp_path):
+    from l4p_b200 import weights
+    from l4p_b200.config import DEFAULT_CONFIG, load_model
+    from l4p_b200.models.utils import prepare_model
+
+    dev = torch.device("cuda", 0)
+    q = torch.tensor([[[0.5, 30.5 + 20.0 * i, 40.5 + 15.0 * i] for i in range(8)]])
+    batch = dict(rgb_b3thw=synth_rgb(1, 16, seed=4), intrinsics_b44t=synth_intrinsics(1, 16), track_2d_pointquerries_bn3=q,
+                 track_2d_pointlabels_bn=torch.ones(1, 8))
+    lit = load_model(device=dev, max_queries=17)
+    weights.fill_module_fast_(lit.l4p_model, seed=5)
+    with torch.no_grad():
+        want = lit.predict_step(dict(batch), 0)
+    torch.cuda.synchronize()
+    want = {k: v.float().cpu() for k, v in want.items() if torch.is_tensor(v)}
+    tap40 = lit.l4p_model.video_encoder(batch["rgb_b3thw"].to(dev))[40].cpu()
+    scratch = _scratch(tmp_path)
+    ckpt = scratch / "l4p_seeded.ckpt"
+    try:
+        sd = lit.state_dict()
+        assert all(k.startswith("l4p_model.") for k in sd) and len(sd) == 916
+        torch.save({"state_dict": sd, "pytorch-lightning_version": "2.x (layout only)"}, ckpt)
+        del lit, sd
+        torch.cuda.empty_cache()
+        base = torch.cuda.memory_allocated(dev)
+        m2 = prepare_model(str(DEFAULT_CONFIG), str(ckpt), max_queries=17, precision="16-mixed", accelerator="gpu", device=dev)
+    finally:
+        if ckpt.exists():
+            ckpt.unlink()
+        if scratch != tmp_path:
+            shutil.rmtree(scratch, ignore_errors=True)
+    arena = m2.l4p_model._weight_arena
+    torch.cuda.empty_cache()
+    resident = torch.cuda.memory_allocated(dev) - base
+    print(f"weight arena: {arena.tensors} tensors, {arena.total_bytes / 2**30:.2f} GiB ({arena.bytes_16bit / 2**30:.2f} 16-bit + "
+          f"{arena.bytes_fp32 / 2**20:.1f} MiB fp32); masters released {arena.masters_released_bytes / 2**30:.2f} GiB; "
+          f"resident after load {resident / 2**30:.2f} GiB")
+    assert 2.6 * 2**30 < arena.total_bytes < 3.2 * 2**30
+    assert arena.masters_released_bytes > 5.2 * 2**30
+    assert resident < arena.total_bytes + (256 << 20)            # nothing but the arena (+ small tables) stays on the device
+    with torch.no_grad():
+        got = m2.predict_step(dict(batch), 0)
+        torch.cuda.synchronize()
+        tap40b = m2.l4p_model.video_encoder(batch["rgb_b3thw"].to(dev))[40].cpu()
+    assert torch.equal(tap40, tap40b)                            # encoder: same kernels, same operands, no atomics
+    for k, w in want.items():
+        g = got[k].float().cpu()
+        assert g.shape == w.shape, k
+        r = rel_l2(g, w)
+        # split-K sums of the low-resolution DPT levels are accumulated with atomics (order-dependent round-off)
+        assert r < 5e-4, (k, r)
+    # inference-frozen: the large fp32 masters are gone (state_dict holds empty tensors for them)
+    assert m2.l4p_model.video_encoder.blocks[0].mlp.fc1.weight.numel() == 0

@@ -275,3 +275,23 @@ def test_attention(dtype, B, H, N, peaky):
     _close(out, ref, 2 ** -6 if dtype == torch.bfloat16 else 2 ** -9)
     rel_l2 = ((out.float() - ref).norm() / ref.norm()).item()
     assert rel_l2 < (6e-3 if dtype == torch.bfloat16 else 1e-3), rel_l2
+
+
+def test_attention_split_variant():
+    """The opt-in four-warpgroup softmax variant (L4P_ATT_SPLIT=1: two half-row warpgroups per query tile, partial row maxima
+    exchanged through shared memory) against fp32 attention, incl. a peaky case that triggers the split TMEM rescale. The
+    selector is read once per process, so the variant runs in a subprocess (tools/att_ab.py prints rel-L2 per case)."""
+    import os
+    import re
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parents[1]
+    r = subprocess.run([sys.executable, str(root / "tools" / "att_ab.py"), "L4P_ATT_SPLIT", "1"], cwd=root, capture_output=True,
+                       text=True, timeout=280, env=dict(os.environ))
+    assert r.returncode == 0 and "exit 0" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    rels = [(m.group(1), float(m.group(2))) for m in re.finditer(r"(float16|bfloat16) peaky=[\d.]+: rel-L2 ([\d.e+-]+)", r.stdout)]
+    assert len(rels) == 5, r.stdout
+    for dt, rel in rels:
+        assert rel < (6e-3 if dt == "bfloat16" else 1e-3), (dt, rel)
