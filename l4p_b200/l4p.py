@@ -47,7 +47,9 @@ class L4PLitModule(_Base):
         dev = self._device()
         for key in batch.keys():
             if torch.is_tensor(batch[key]):
-                batch[key] = batch[key].to(device=dev)
+                # non_blocking: a pinned host batch is copied asynchronously on the compute stream (ordering with the kernels
+                # that read it is the stream's), so the host keeps enqueueing instead of waiting for the previous step
+                batch[key] = batch[key].to(device=dev, non_blocking=True)
         out = self.forward(batch, self.tasks)
         if phase == "predict":
             return out

@@ -205,7 +205,9 @@ class VideoMAETraj3DDPTHead(VideoMAEFlowDPTHead):
         self.last_rays_b6thw: Optional[torch.Tensor] = None  # exposed for parity tests (the DPT output)
 
     def rays(self, enc_features_bpc_list, img_info=(16, 224, 224)) -> torch.Tensor:
-        return self._run_dpt(enc_features_bpc_list, img_info).to(dtype=torch.float32)
+        rays = self._run_dpt(enc_features_bpc_list, img_info).to(dtype=torch.float32)
+        self.last_rays_b6thw = rays
+        return rays
 
     def pose_from_rays(self, rays_est_b6thw, img_info, intrinsics_b44t=None, **kwargs) -> Dict[str, torch.Tensor]:
         T, H, W = img_info

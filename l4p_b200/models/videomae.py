@@ -203,8 +203,9 @@ class VideoMAEEncoder(nn.Module):
             hd = D // H
             dpad = 96
             dt = self.compute_dtype
-            hidden = self.blocks[0].mlp.fc1.out_features
-            kdim = self.patch_embed.proj.weight[0].numel()
+            hidden = self.blocks[0].mlp.fc1.out_features   # module attributes, not parameter shapes: the fp32 masters may
+            # have been released after packing (l4p_b200/arena.py)
+            kdim = self.patch_embed.proj.in_channels * self.tubelet_size * self.patch_size * self.patch_size
             M = B * ntok
             e = lambda *s, dtype=dt: torch.empty(*s, device=device, dtype=dtype)
             ws = dict(
