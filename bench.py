@@ -373,18 +373,25 @@ def main():
                     "gpu_launches": mv["launches"], "scaling": "strong"}
                 del mv, hostv
             if world > 1:
-                # sharded == unsharded on real NCCL ranks: a 5-window clip through both paths on every rank
+                # sharded == unsharded on real NCCL ranks: a 5-window clip through both paths on every rank. Compared on the
+                # per-head windowed path (depth with its least-squares affine overlap alignment, poses stitched): with RANDOM
+                # weights the windows do not describe one scene, so the joint Sim(3) consensus between them is ill-posed and
+                # amplifies 1e-4 round-off differences arbitrarily - its sharded == unsharded equality is asserted on a
+                # consistent scene by tests/test_dist_gpu.py instead.
                 b5 = {k: v.to(dev) for k, v in synth_batch(1, 48, queries=False).items()}
+                model.joint_alignment = False
+                keys5 = ["depth_est_b1thw", "traj3d_est_b16t"]
                 sh = model.forward(b5, tasks4)
                 model.enable_window_sharding(False)
                 un = model.forward(b5, tasks4)
-                diffs = {}
-                for k in keys4:
+                model.joint_alignment = True
+                diffs = []
+                for k in keys5:
                     a, b = sh[k].float(), un[k].float()
-                    diffs[k] = float((a - b).norm() / (b.norm() + 1e-30))
-                d = torch.tensor([diffs[k] for k in keys4], device=dev, dtype=torch.float64)
+                    diffs.append(float((a - b).norm() / (b.norm() + 1e-30)))
+                d = torch.tensor(diffs, device=dev, dtype=torch.float64)
                 dist.all_reduce(d, op=dist.ReduceOp.MAX)
-                extra_cfgs["cfg4_sharded_vs_unsharded_rel_l2"] = dict(zip(keys4, d.tolist()))
+                extra_cfgs["cfg4_sharded_vs_unsharded_rel_l2"] = dict(zip(keys5, d.tolist()))
             torch.cuda.empty_cache()
 
     frames = 16 * clips * world

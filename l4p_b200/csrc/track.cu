@@ -565,11 +565,193 @@ extern "C" int l4p_token_attention(const float* q, const void* k16, const void* 
   return L4P_OK;
 }
 
+
+namespace l4p {
+// ----------------------------------------------------------------------------------------------------------------------
+// Streaming image -> token attention (round 2): persistent CTAs, 32-row tiles of the 16-bit query stream moved by 1-D bulk
+// TMA copies through a 4-deep shared-memory ring (three tiles = 135 KB in flight per SM, the round-1 kernel had one
+// synchronous tile: 0.24 of the HBM roofline, ncu: long-scoreboard bound), computed IN PLACE (each thread owns one
+// (row, head) slice of 176 bytes: scores against the nk <= 6 keys, softmax, weighted sum of the values, written over its own
+// query slice) and written back with bulk stores. Lane mapping: lane = 8 * (row % 4) + head, warp w owns rows 4w .. 4w+3 of
+// the tile - the 16-byte accesses of a warp then fall into four conflict-free 128-byte wavefronts although the tile has the
+// dense 1408-byte row pitch a bulk copy produces. K (pre-scaled) and V sit in shared memory as fp32 [nk][head][92] (pad 88
+// -> 92 floats: the eight heads' float4 reads hit eight different bank groups).
+// ----------------------------------------------------------------------------------------------------------------------
+constexpr int kIaRows = 32, kIaStages = 4, kIaThreads = 256, kIaD = 88, kIaDP = 92, kIaH = 8;
+constexpr int kIaRowBytes = kIaH * kIaD * 2;              // 1408
+constexpr int kIaTileBytes = kIaRows * kIaRowBytes;       // 45056
+
+L4P_DEVICE void bulk_load(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+L4P_DEVICE void bulk_store(void* dst, uint32_t src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes) : "memory");
+}
+L4P_DEVICE void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+L4P_DEVICE void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N>
+L4P_DEVICE void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <bool BF16>
+__global__ void __launch_bounds__(kIaThreads, 1)
+image_attention_stream_kernel(const uint16_t* __restrict__ q16, const float* __restrict__ kf, const float* __restrict__ vf,
+                              uint16_t* __restrict__ out16, int Np, int nk, float scale, long long n_tiles) {
+  extern __shared__ __align__(128) uint8_t ia_smem[];
+  __shared__ __align__(8) uint64_t bar_full[kIaStages];
+  float* s_k = reinterpret_cast<float*>(ia_smem);                       // [kTokMaxQ][8][92]
+  float* s_v = s_k + kTokMaxQ * kIaH * kIaDP;
+  const uint32_t ring = smem_u32(ia_smem) + 2u * kTokMaxQ * kIaH * kIaDP * 4u;   // 4 x 45056, 128-byte aligned
+  uint8_t* ring_ptr = ia_smem + 2 * kTokMaxQ * kIaH * kIaDP * 4;
+
+  // contiguous tile range of this CTA
+  const long long per = (n_tiles + gridDim.x - 1) / gridDim.x;
+  const long long t_begin = (long long)blockIdx.x * per;
+  const long long t_end = t_begin + per < n_tiles ? t_begin + per : n_tiles;
+  const int tiles_per_group = Np / kIaRows;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kIaStages; ++s) mbar_init(smem_u32(&bar_full[s]), 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (t_begin >= t_end) return;
+  const int n_local = (int)(t_end - t_begin);
+  // prologue: the first kIaStages - 1 tiles
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kIaStages - 1 && i < n_local; ++i) {
+      const uint32_t fb = smem_u32(&bar_full[i]);
+      mbar_expect_tx(fb, kIaTileBytes);
+      bulk_load(ring + (uint32_t)i * kIaTileBytes, q16 + (t_begin + i) * (long long)kIaRows * (kIaH * kIaD), kIaTileBytes, fb);
+    }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = lane & 7, rr = warp * 4 + (lane >> 3);          // head, row inside the tile
+  int cur_g = -1;
+  for (int i = 0; i < n_local; ++i) {
+    const long long tile = t_begin + i;
+    const int g = (int)(tile / tiles_per_group);
+    if (g != cur_g) {   // (re)load this group's keys / values; rare: a group spans Np / 32 consecutive tiles
+      __syncthreads();
+      for (int e = threadIdx.x; e < nk * kIaH * kIaD; e += kIaThreads) {
+        const int j = e / (kIaH * kIaD), c = e - j * (kIaH * kIaD);
+        const int hh = c / kIaD, dd = c - hh * kIaD;
+        s_k[(j * kIaH + hh) * kIaDP + dd] = kf[((long long)g * nk + j) * (kIaH * kIaD) + c] * scale;
+        s_v[(j * kIaH + hh) * kIaDP + dd] = vf[((long long)g * nk + j) * (kIaH * kIaD) + c];
+      }
+      __syncthreads();
+      cur_g = g;
+    }
+    const int s = i % kIaStages;
+    mbar_wait(smem_u32(&bar_full[s]), (uint32_t)(i / kIaStages) & 1u);
+    uint16_t* mine = reinterpret_cast<uint16_t*>(ring_ptr + (size_t)s * kIaTileBytes) + rr * (kIaH * kIaD) + h * kIaD;
+    // ---- scores: packed f32x2 partial sums (even / odd channel) per key
+    uint4 raw[kIaD / 8];
+#pragma unroll
+    for (int c8 = 0; c8 < kIaD / 8; ++c8) raw[c8] = *reinterpret_cast<const uint4*>(mine + c8 * 8);
+    uint64_t sc2[kTokMaxQ];
+#pragma unroll
+    for (int j = 0; j < kTokMaxQ; ++j) sc2[j] = pk2(0.f, 0.f);
+#pragma unroll
+    for (int c8 = 0; c8 < kIaD / 8; ++c8) {
+      const float2 q0 = unpack2<BF16>(raw[c8].x), q1 = unpack2<BF16>(raw[c8].y), q2 = unpack2<BF16>(raw[c8].z),
+                   q3 = unpack2<BF16>(raw[c8].w);
+      const uint64_t p0 = pk2(q0.x, q0.y), p1 = pk2(q1.x, q1.y), p2 = pk2(q2.x, q2.y), p3 = pk2(q3.x, q3.y);
+#pragma unroll
+      for (int j = 0; j < kTokMaxQ; ++j) {
+        if (j < nk) {
+          const ulonglong2* kk = reinterpret_cast<const ulonglong2*>(s_k + (j * kIaH + h) * kIaDP + c8 * 8);
+          const ulonglong2 ka = kk[0], kb = kk[1];
+          uint64_t a = sc2[j];
+          a = fma2(p0, ka.x, a); a = fma2(p1, ka.y, a); a = fma2(p2, kb.x, a); a = fma2(p3, kb.y, a);
+          sc2[j] = a;
+        }
+      }
+    }
+    float sc[kTokMaxQ];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < kTokMaxQ; ++j) {
+      float a, b;
+      upk2(sc2[j], a, b);
+      sc[j] = a + b;
+      if (j < nk) mx = fmaxf(mx, sc[j]);
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < kTokMaxQ; ++j) {
+      sc[j] = j < nk ? __expf(sc[j] - mx) : 0.f;
+      sum += sc[j];
+    }
+    const float inv = 1.f / sum;
+    uint64_t pj2[kTokMaxQ];
+#pragma unroll
+    for (int j = 0; j < kTokMaxQ; ++j) pj2[j] = pk2(sc[j] * inv, sc[j] * inv);
+    // ---- output: sum_j p_j v_j, written over this thread's own (fully consumed) query slice
+#pragma unroll
+    for (int c8 = 0; c8 < kIaD / 8; ++c8) {
+      uint64_t o0 = pk2(0.f, 0.f), o1 = o0, o2 = o0, o3 = o0;
+#pragma unroll
+      for (int j = 0; j < kTokMaxQ; ++j) {
+        if (j < nk) {
+          const ulonglong2* vv = reinterpret_cast<const ulonglong2*>(s_v + (j * kIaH + h) * kIaDP + c8 * 8);
+          const ulonglong2 va = vv[0], vb = vv[1];
+          o0 = fma2(pj2[j], va.x, o0); o1 = fma2(pj2[j], va.y, o1); o2 = fma2(pj2[j], vb.x, o2); o3 = fma2(pj2[j], vb.y, o3);
+        }
+      }
+      float a0, a1, b0, b1, c0, c1, d0, d1;
+      upk2(o0, a0, a1); upk2(o1, b0, b1); upk2(o2, c0, c1); upk2(o3, d0, d1);
+      *reinterpret_cast<uint4*>(mine + c8 * 8) =
+          make_uint4(pack2<BF16>(a0, a1), pack2<BF16>(b0, b1), pack2<BF16>(c0, c1), pack2<BF16>(d0, d1));
+    }
+    fence_proxy_async();   // generic-proxy writes of the tile -> visible to the bulk store (async proxy)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      bulk_store(out16 + tile * (long long)kIaRows * (kIaH * kIaD), ring + (uint32_t)s * kIaTileBytes, kIaTileBytes);
+      bulk_commit();
+      // the slot that tile i + kIaStages - 1 will use held tile i - 1: its store (the second newest group) must have finished
+      // READING shared memory before the next load overwrites it
+      const int nxt = i + kIaStages - 1;
+      if (nxt < n_local) {
+        bulk_wait_read<1>();
+        const int ns = nxt % kIaStages;
+        const uint32_t fb = smem_u32(&bar_full[ns]);
+        mbar_expect_tx(fb, kIaTileBytes);
+        bulk_load(ring + (uint32_t)ns * kIaTileBytes, q16 + (t_begin + nxt) * (long long)kIaRows * (kIaH * kIaD), kIaTileBytes, fb);
+      }
+    }
+  }
+  if (threadIdx.x == 0) bulk_wait_all<0>();   // all stores complete before the CTA (and its shared memory) goes away
+}
+}  // namespace l4p
+
 extern "C" int l4p_image_attention(const void* q16, const float* k, const float* v, void* out16, int G, int Np, int nk,
                                    int H, int d, float scale, int bf16, void* stream) {
   L4P_REQUIRE(q16 && k && v && out16, L4P_ERR_ARG, "l4p_image_attention: null pointer");
   L4P_REQUIRE(d == 88, L4P_ERR_SHAPE, "l4p_image_attention: head_dim=%d (this build: 88)", d);
   L4P_REQUIRE(G > 0 && nk > 0 && nk <= kTokMaxQ && H > 0 && H <= 8, L4P_ERR_SHAPE, "l4p_image_attention: nk=%d H=%d (<= 8)", nk, H);
+  static int stream_mode = -1;   // L4P_IMGATT_STREAM=0 selects the round-1 kernel (A/B runs)
+  if (stream_mode < 0) {
+    const char* e = getenv("L4P_IMGATT_STREAM");
+    stream_mode = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  if (stream_mode == 1 && H == kIaH && Np % kIaRows == 0) {
+    const long long n_tiles = (long long)G * Np / kIaRows;
+    const size_t smem_s = 2 * (size_t)kTokMaxQ * kIaH * kIaDP * 4 + (size_t)kIaStages * kIaTileBytes;
+    typedef void (*SFn)(const uint16_t*, const float*, const float*, uint16_t*, int, int, float, long long);
+    SFn sfn = bf16 ? image_attention_stream_kernel<true> : image_attention_stream_kernel<false>;
+    static bool attr[2] = {false, false};
+    if (!attr[bf16 ? 1 : 0]) {
+      L4P_CHECK_CUDA(cudaFuncSetAttribute(sfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
+      attr[bf16 ? 1 : 0] = true;
+    }
+    const long long sms = host_num_sms();
+    const unsigned grid_s = (unsigned)(n_tiles < sms ? n_tiles : sms);
+    sfn<<<grid_s, kIaThreads, smem_s, (cudaStream_t)stream>>>((const uint16_t*)q16, k, v, (uint16_t*)out16, Np, nk, scale, n_tiles);
+    L4P_CHECK_CUDA(cudaGetLastError());
+    return L4P_OK;
+  }
   const int rows_per_block = 128;
   L4P_REQUIRE(Np % rows_per_block == 0, L4P_ERR_SHAPE, "l4p_image_attention: Np=%d must be a multiple of %d", Np, rows_per_block);
   L4P_REQUIRE(32 * H <= 256 && (H * d) % 8 == 0, L4P_ERR_SHAPE, "l4p_image_attention: H=%d", H);
