@@ -204,6 +204,8 @@ def main():
     ap.add_argument("--dtype", default="fp16", choices=["fp16", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-configs", action="store_true", help="headline only (no cfg3 / cfg4 legs)")
+    ap.add_argument("--no-graph", action="store_true", help="enqueue every kernel from Python instead of replaying the "
+                    "captured CUDA graph of the step (l4p_b200/graph.py)")
     ap.add_argument("--ncu-range", action="store_true", help="bracket the timed region with cudaProfilerStart/Stop "
                     "(run under `ncu --profile-from-start off`)")
     args = ap.parse_args()
@@ -235,6 +237,8 @@ def main():
     lit = load_model(device=dev, max_queries=NQ + 1, compute_dtype=dt)   # configs/model.yaml: all five tasks, joint alignment
     model = lit.l4p_model
     weights.fill_module_fast_(model, seed=rank)
+    use_graph = not args.no_graph
+    lit.enable_cuda_graph(use_graph)     # predict_step replays one captured graph per input signature
     copy_stream = torch.cuda.Stream(device=dev)
 
     def sync_all():
@@ -309,12 +313,14 @@ def main():
         m = measure(step_clips(clips), host, args.steps, args.warmup, instrument=True)
         # roofline kernel: CUDA-event pair around every attention launch of two extra instrumented steps (kept out of the
         # timed region: an event record between two kernels breaks their programmatic-dependent-launch overlap)
+        lit.use_cuda_graph = False          # eager for the instrumented steps (timing events are not capturable)
         ops.ATTN_EVENTS = []
         for _ in range(4):
             step_clips(clips)(m["batch"])
         sync_all()
         att = ops.ATTN_EVENTS
         ops.ATTN_EVENTS = None
+        lit.use_cuda_graph = use_graph
         att_times = sorted(a.elapsed_time(b) for a, b, _ in att)
         att_ms = sum(att_times) / max(len(att_times), 1)             # mean over 160 launches (reported as `achieved`)
         att_ms_median = att_times[len(att_times) // 2] if att_times else 0.0
@@ -348,19 +354,30 @@ def main():
                         "d2h_bytes_per_step": m3["d2h"]},
                 "gpu_launches": m3["launches"], "scaling": "weak"}
             del m3
+            lit.enable_cuda_graph(False)     # drop the captured graphs (and their memory pools) of the clip legs
+            torch.cuda.empty_cache()
             # ------------------------------------------------------------ cfg 4: long video, depth + camray, joint alignment
             keys4 = ["depth_est_b1thw", "traj3d_est_b16t", "traj3d_intrinsics_est_b16t"]
             tasks4 = ["depth", "camray"]
             if world > 1:
                 model.enable_window_sharding(True)
 
-            def step_video(b):
+            from l4p_b200.graph import StepGraph
+
+            def step_video_eager(b):
                 out = model.forward(b if b["rgb_b3thw"].is_cuda else {k: v.to(dev, non_blocking=True) for k, v in b.items()}, tasks4)
                 return pack_outputs(out, keys4, 1)
 
             for T in (264, 512):
                 hostv = {k: v.pin_memory() for k, v in synth_batch(1, T, queries=False).items()}
+                step_video = step_video_eager
+                if use_graph and world == 1:   # sharded runs exchange window metadata on the host: eager there
+                    vg = StepGraph(lambda b: {"packed": pack_outputs(model.forward(b, tasks4), keys4, 1)}, hostv, dev, warmup=1)
+                    step_video = lambda b, vg=vg: vg(b)["packed"]
                 mv = measure(step_video, hostv, steps=2, warmup=1)
+                step_video = None
+                vg = None
+                torch.cuda.empty_cache()
                 nW = (T - 16) // 8 + 1
                 extra_cfgs[f"cfg4_T{T}"] = {
                     "workload": f"BASELINE.json configs[3]: one {T}-frame video = {nW} overlapping 16-frame windows, depth + camray "
@@ -408,7 +425,8 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": WORKLOAD + "; N>1: one clip per GPU + one all-gather of head outputs",
                        "clips_per_gpu": clips, "track_queries": NQ, "weights": "random (seeded), reference architecture",
-                       "api": "L4PLitModule.predict_step(batch, 0)",
+                       "api": "L4PLitModule.predict_step(batch, 0)" + (" replaying the captured CUDA graph of the step" if use_graph else ""),
+                       "cuda_graph": use_graph,
                        "l2": "per-step working set (2.8 GB weights + >1 GB activations) exceeds the 126 MB L2; no explicit flush"},
             "e2e": {"value": frames / (m["ms_e2e"] * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": m["h2d"],
                     "d2h_bytes_per_step": m["d2h"],

@@ -30,6 +30,9 @@ class L4PLitModule(_Base):
         self.optimizer_opts = optimizer_opts
         self.scheduler_opts = scheduler_opts
         self.strict_loading = strict_loading
+        # opt-in CUDA-graph replay of predict_step (l4p_b200/graph.py): one captured graph per input signature
+        self.use_cuda_graph = False
+        self._graphs: Dict[Any, Any] = {}
 
     def _device(self) -> torch.device:
         dev = getattr(super(), "device", None)
@@ -43,8 +46,23 @@ class L4PLitModule(_Base):
     def forward(self, batch, tasks):
         return self.l4p_model.forward(batch, tasks)
 
+    def enable_cuda_graph(self, enabled: bool = True) -> None:
+        """Replay `predict_step` from a CUDA graph (captured on the first call with a given set of input shapes / tasks).
+        The returned tensors are the graph's static outputs: consume or copy them before the next call."""
+        self.use_cuda_graph = bool(enabled)
+        if not enabled:
+            self._graphs.clear()
+
     def step(self, phase, batch, batch_idx):
         dev = self._device()
+        if phase == "predict" and self.use_cuda_graph and dev.type == "cuda":
+            from .graph import StepGraph, signature
+
+            key = signature(batch, tuple(self.tasks))
+            g = self._graphs.get(key)
+            if g is None:
+                g = self._graphs[key] = StepGraph(lambda b: self.forward(b, self.tasks), batch, dev)
+            return g(batch)
         for key in batch.keys():
             if torch.is_tensor(batch[key]):
                 # non_blocking: a pinned host batch is copied asynchronously on the compute stream (ordering with the kernels

@@ -128,9 +128,10 @@ class L4P_VideoMAE(torch.nn.Module):
             st.wait_event(start)
             with torch.cuda.stream(st):
                 res = job()
-                for v in res.values():
-                    if torch.is_tensor(v):
-                        v.record_stream(main)  # the caller consumes the outputs on its own stream
+                if not torch.cuda.is_current_stream_capturing():   # (a graph's private pool never recycles mid-replay)
+                    for v in res.values():
+                        if torch.is_tensor(v):
+                            v.record_stream(main)  # the caller consumes the outputs on its own stream
                 e = torch.cuda.Event()
                 e.record(st)
             results.append(res)

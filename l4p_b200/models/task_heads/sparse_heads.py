@@ -76,7 +76,9 @@ class PromptEncoder(nn.Module):
         T, H, W = self.input_image_size
         pts = torch.cat([coords_g13, torch.zeros(G, 1, 3, device=coords_g13.device, dtype=coords_g13.dtype)], dim=1)
         lab = torch.cat([labels_g1, -torch.ones(G, 1, device=labels_g1.device, dtype=labels_g1.dtype)], dim=1)
-        scale = torch.tensor([T, W, H], device=pts.device, dtype=torch.float32)  # (t, x, y)
+        # (t, x, y) extents, built on the device without a host->device copy (CUDA-graph capturable)
+        scale = torch.stack([torch.full((), float(T), device=pts.device), torch.full((), float(W), device=pts.device),
+                             torch.full((), float(H), device=pts.device)])
         pe = self._pe_encoding(pts.float() / scale)
         pe = torch.where((lab == -1)[..., None], self.not_a_point_embed.weight.expand_as(pe), pe)
         for i in range(self.num_point_embeddings):  # label 2 ("estimated") adds nothing when only 2 embeddings exist

@@ -1,0 +1,51 @@
+"""CUDA-graph replay of the all-heads step (l4p_b200/graph.py): `L4PLitModule.enable_cuda_graph()` must return what the eagerly
+enqueued step returns - for the inputs the graph was captured with AND for new inputs of the same shapes (pinned host batch
+copied into the graph's static buffers) - with every kernel of the step inside ONE graph launch."""
+import pytest
+import torch
+
+from tests.util import rel_l2, synth_intrinsics, synth_rgb
+
+pytestmark = pytest.mark.gpu
+
+
+def _batch(seed, nq=8):
+    g = torch.Generator().manual_seed(seed)
+    q = torch.cat([torch.full((1, nq, 1), 0.5), torch.rand(1, nq, 2, generator=g) * 200 + 12], dim=-1)
+    return dict(rgb_b3thw=synth_rgb(1, 16, seed=seed), intrinsics_b44t=synth_intrinsics(1, 16),
+                track_2d_pointquerries_bn3=q, track_2d_pointlabels_bn=torch.ones(1, nq))
+
+
+def test_graph_replay_equals_eager_step():
+    from l4p_b200 import ops, weights
+    from l4p_b200.config import load_model
+
+    dev = torch.device("cuda", 0)
+    lit = load_model(device=dev, max_queries=17)
+    weights.fill_module_fast_(lit.l4p_model, seed=9)
+    b1, b2 = _batch(1), _batch(2)
+    with torch.no_grad():
+        eager = []
+        for b in (b1, b2):
+            out = lit.predict_step(dict(b), 0)
+            eager.append({k: v.float().cpu() for k, v in out.items() if torch.is_tensor(v)})
+        lit.enable_cuda_graph(True)
+        l0 = ops.LAUNCHES
+        got1 = {k: v.float().cpu() for k, v in lit.predict_step(dict(b1), 0).items() if torch.is_tensor(v)}   # captures
+        assert len(lit._graphs) == 1
+        per_replay = next(iter(lit._graphs.values())).launches
+        assert per_replay > 300, per_replay                     # the whole step is inside the graph
+        pinned = {k: v.pin_memory() for k, v in b2.items()}
+        got2 = {k: v.float().cpu() for k, v in lit.predict_step(pinned, 0).items() if torch.is_tensor(v)}      # replays
+        assert len(lit._graphs) == 1 and ops.LAUNCHES - l0 >= 2 * per_replay
+        other = _batch(3, nq=4)                                   # another signature -> a second graph
+        lit.predict_step(dict(other), 0)
+        assert len(lit._graphs) == 2
+    torch.cuda.synchronize()
+    for want, got in ((eager[0], got1), (eager[1], got2)):
+        assert set(want) == set(got)
+        for k, w in want.items():
+            r = rel_l2(got[k], w)
+            # same kernels, same operands; split-K atomics make low-resolution sums order-dependent (tests/test_ckpt_gpu.py)
+            assert r < (2e-3 if k.startswith("track_2d") else 5e-4), (k, r)
+    assert rel_l2(got2["depth_est_b1thw"], got1["depth_est_b1thw"]) > 1e-3      # the second call really used the new inputs

@@ -29,7 +29,7 @@ for dt in (torch.float16, torch.bfloat16):
     torch.cuda.synchronize()
     worst = 0.0
     for gi in (0, 63, 127):
-        rows = slice(gi * Np + 1024, gi * Np + 1024 + 1365)
+        rows = slice(gi * Np + 512, gi * Np + 512 + 1365)
         qf = q16[rows].float().view(-1, H, d)
         kf, vf = k[gi].view(nk, H, d), v[gi].view(nk, H, d)
         a = torch.softmax(torch.einsum("rhd,jhd->rhj", qf, kf) * d ** -0.5, dim=-1)
