@@ -726,17 +726,193 @@ image_attention_stream_kernel(const uint16_t* __restrict__ q16, const float* __r
 }
 }  // namespace l4p
 
+
+namespace l4p {
+// ----------------------------------------------------------------------------------------------------------------------
+// Image -> token attention, tensor-core formulation (round 2, default). The limiter of the FMA kernels above is not HBM but
+// the shared-memory -> register path: every (row, head) thread re-reads all of K and V (4.2 KB) for 1056 FMAs, and an LDS.128
+// returns 512 bytes per warp whether or not the lanes broadcast (measured: 356 us = 0.32 of the HBM roofline even with three
+// bulk-TMA tiles in flight). Here K^T (pre-scaled) and V of one head live in REGISTERS as mma.sync B fragments for the whole
+// kernel (12 + 11 registers), the query tile is the A operand fetched with ldmatrix (each byte of the tile is read once), the
+// probabilities stay in the accumulator layout, which is already the A layout of the P V product (the FA2 trick), and the
+// result overwrites the query slice in place. Warp w = head w; a 32-row tile = two 16-row MMA units per warp.
+//   scores  S[16 x 8 keys]  = Q[16 x 96] K^T[96 x 8]    6 x mma.m16n8k16   (dims 88..95 of a head's slice are the next head's
+//                                                                          first channels: multiplied by zero rows of K^T)
+//   output  O[16 x 88]      = P[16 x 8]  V[8 x 88]      11 x mma.m16n8k8
+// Tiles move as 32 per-row bulk copies (1408 B each) into rows of pitch 1424 B, so that the eight 16-byte row segments of an
+// ldmatrix phase fall into eight different bank groups; four tiles in the ring. K, V and P are rounded to the operand type
+// (like the tcgen05 variant of round 1 and like every other contraction of the path); accumulation is fp32.
+// ----------------------------------------------------------------------------------------------------------------------
+constexpr int kImPitch = kIaRowBytes + 16;                 // 1424
+constexpr int kImTileBytes = kIaRows * kImPitch;           // 45568
+constexpr int kImStages = 4;
+
+L4P_DEVICE void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+template <bool BF16>
+L4P_DEVICE void mma_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  if constexpr (BF16)
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+  else
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+template <bool BF16>
+L4P_DEVICE void mma_1688(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t b0) {
+  if constexpr (BF16)
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(b0));
+  else
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(b0));
+}
+
+template <bool BF16>
+__global__ void __launch_bounds__(kIaThreads, 1)
+image_attention_mma_kernel(const uint16_t* __restrict__ q16, const float* __restrict__ kf, const float* __restrict__ vf,
+                           uint16_t* __restrict__ out16, int Np, int nk, float scale, long long n_tiles) {
+  extern __shared__ __align__(128) uint8_t im_smem[];
+  __shared__ __align__(8) uint64_t bar_full[kImStages];
+  const uint32_t ring = smem_u32(im_smem);
+  constexpr int ld = kIaH * kIaD;   // 704 elements per row
+  const long long per = (n_tiles + gridDim.x - 1) / gridDim.x;
+  const long long t_begin = (long long)blockIdx.x * per;
+  const long long t_end = t_begin + per < n_tiles ? t_begin + per : n_tiles;
+  const int tiles_per_group = Np / kIaRows;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kImStages; ++s) mbar_init(smem_u32(&bar_full[s]), 1);
+    fence_mbar_init();
+  }
+  // the 16 pad bytes of every ring row are read (times zero) by the last k-step of head 7: never leave NaN patterns there
+  for (int i = threadIdx.x; i < kImStages * kIaRows; i += kIaThreads)
+    *reinterpret_cast<uint4*>(im_smem + (size_t)i * kImPitch + kIaRowBytes) = make_uint4(0, 0, 0, 0);
+  fence_proxy_async();
+  __syncthreads();
+  if (t_begin >= t_end) return;
+  const int n_local = (int)(t_end - t_begin);
+  auto load_tile = [&](int i) {   // warp 0, all lanes: lane = row
+    const int s = i % kImStages;
+    const uint32_t fb = smem_u32(&bar_full[s]);
+    if (lane == 0) mbar_expect_tx(fb, kIaRows * kIaRowBytes);
+    __syncwarp();
+    bulk_load(ring + (uint32_t)s * kImTileBytes + (uint32_t)lane * kImPitch,
+              q16 + ((t_begin + i) * (long long)kIaRows + lane) * ld, kIaRowBytes, fb);
+  };
+  if (warp == 0)
+    for (int i = 0; i < kImStages - 1 && i < n_local; ++i) load_tile(i);
+
+  const int h = warp;               // head of this warp
+  const int g4 = lane >> 2, c4 = lane & 3;
+  uint32_t kfrag[6][2], vfrag[11];
+  int cur_g = -1;
+  for (int i = 0; i < n_local; ++i) {
+    const long long tile = t_begin + i;
+    const int g = (int)(tile / tiles_per_group);
+    if (g != cur_g) {   // this group's K^T / V B-fragments (rare: a group spans Np / 32 consecutive tiles)
+      const float* kg = kf + (long long)g * nk * ld + h * kIaD;
+      const float* vg = vf + (long long)g * nk * ld + h * kIaD;
+#pragma unroll
+      for (int ks = 0; ks < 6; ++ks)
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int d0 = ks * 16 + half * 8 + 2 * c4;   // B[k = dim][n = key g4]
+          float a = 0.f, b = 0.f;
+          if (g4 < nk && d0 < kIaD) { a = kg[g4 * ld + d0] * scale; b = kg[g4 * ld + d0 + 1] * scale; }
+          kfrag[ks][half] = pack2<BF16>(a, b);
+        }
+#pragma unroll
+      for (int nt = 0; nt < 11; ++nt) {                  // B[k = key 2 c4 (+1)][n = dim 8 nt + g4]
+        const int j0 = 2 * c4, dd = nt * 8 + g4;
+        const float a = j0 < nk ? vg[j0 * ld + dd] : 0.f, b = j0 + 1 < nk ? vg[(j0 + 1) * ld + dd] : 0.f;
+        vfrag[nt] = pack2<BF16>(a, b);
+      }
+      cur_g = g;
+    }
+    const int s = i % kImStages;
+    mbar_wait(smem_u32(&bar_full[s]), (uint32_t)(i / kImStages) & 1u);
+    const uint32_t tbase = ring + (uint32_t)s * kImTileBytes + (uint32_t)h * (kIaD * 2);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {                         // 16-row units
+      const uint32_t ubase = tbase + (uint32_t)(u * 16) * kImPitch;
+      // ldmatrix.x4 row addresses: lanes 0-7 rows 0-7, 8-15 rows 8-15 (dims +0), 16-23 rows 0-7, 24-31 rows 8-15 (dims +8)
+      const uint32_t lrow = ubase + (uint32_t)((lane & 7) + ((lane >> 3) & 1) * 8) * kImPitch + (uint32_t)((lane >> 4) & 1) * 16;
+      float sc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int ks = 0; ks < 6; ++ks) {
+        uint32_t a0, a1, a2, a3;
+        ldsm_x4(lrow + ks * 32, a0, a1, a2, a3);
+        mma_16816<BF16>(sc, a0, a1, a2, a3, kfrag[ks][0], kfrag[ks][1]);
+      }
+      // softmax over the nk valid keys: this thread holds keys 2 c4, 2 c4 + 1 of rows g4 (sc[0..1]) and g4 + 8 (sc[2..3])
+      const bool v0 = 2 * c4 < nk, v1 = 2 * c4 + 1 < nk;
+      float m0 = fmaxf(v0 ? sc[0] : -INFINITY, v1 ? sc[1] : -INFINITY), m1 = fmaxf(v0 ? sc[2] : -INFINITY, v1 ? sc[3] : -INFINITY);
+      m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+      m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+      const float p00 = v0 ? __expf(sc[0] - m0) : 0.f, p01 = v1 ? __expf(sc[1] - m0) : 0.f;
+      const float p10 = v0 ? __expf(sc[2] - m1) : 0.f, p11 = v1 ? __expf(sc[3] - m1) : 0.f;
+      float l0 = p00 + p01, l1 = p10 + p11;
+      l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+      l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+      const float i0 = 1.f / l0, i1 = 1.f / l1;
+      const uint32_t pa0 = pack2<BF16>(p00 * i0, p01 * i0), pa1 = pack2<BF16>(p10 * i1, p11 * i1);
+      // all lanes of the warp have fetched their A fragments (ldmatrix is warp-synchronous): the slice may be overwritten
+      const uint32_t orow0 = ubase + (uint32_t)g4 * kImPitch + (uint32_t)c4 * 4, orow1 = orow0 + 8u * kImPitch;
+#pragma unroll
+      for (int nt = 0; nt < 11; ++nt) {
+        float o[4] = {0.f, 0.f, 0.f, 0.f};
+        mma_1688<BF16>(o, pa0, pa1, vfrag[nt]);
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(orow0 + nt * 16), "r"(pack2<BF16>(o[0], o[1])) : "memory");
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(orow1 + nt * 16), "r"(pack2<BF16>(o[2], o[3])) : "memory");
+      }
+    }
+    fence_proxy_async();   // generic-proxy writes of the tile -> visible to the bulk stores (async proxy)
+    __syncthreads();
+    if (warp == 0) {
+      bulk_store(out16 + (tile * (long long)kIaRows + lane) * ld, ring + (uint32_t)s * kImTileBytes + (uint32_t)lane * kImPitch,
+                 kIaRowBytes);
+      bulk_commit();
+      const int nxt = i + kImStages - 1;   // reuses the slot of tile i - 1: this lane's store of ITS row of that tile must have
+      if (nxt < n_local) {                 // finished reading shared memory before this lane's load overwrites the row
+        bulk_wait_read<1>();
+        load_tile(nxt);
+      }
+    }
+  }
+  if (warp == 0) bulk_wait_all<0>();
+}
+}  // namespace l4p
+
 extern "C" int l4p_image_attention(const void* q16, const float* k, const float* v, void* out16, int G, int Np, int nk,
                                    int H, int d, float scale, int bf16, void* stream) {
   L4P_REQUIRE(q16 && k && v && out16, L4P_ERR_ARG, "l4p_image_attention: null pointer");
   L4P_REQUIRE(d == 88, L4P_ERR_SHAPE, "l4p_image_attention: head_dim=%d (this build: 88)", d);
   L4P_REQUIRE(G > 0 && nk > 0 && nk <= kTokMaxQ && H > 0 && H <= 8, L4P_ERR_SHAPE, "l4p_image_attention: nk=%d H=%d (<= 8)", nk, H);
-  static int stream_mode = -1;   // L4P_IMGATT_STREAM=0 selects the round-1 kernel (A/B runs)
+  // L4P_IMGATT_STREAM: 2 (default) tensor-core streaming kernel, 1 FMA streaming kernel, 0 round-1 kernel (A/B runs)
+  static int stream_mode = -1;
   if (stream_mode < 0) {
     const char* e = getenv("L4P_IMGATT_STREAM");
-    stream_mode = (e && atoi(e) == 0) ? 0 : 1;
+    stream_mode = e ? atoi(e) : 2;
   }
-  if (stream_mode == 1 && H == kIaH && Np % kIaRows == 0) {
+  if (stream_mode == 2 && H == kIaH && Np % kIaRows == 0 && nk <= 8) {
+    const long long n_tiles = (long long)G * Np / kIaRows;
+    const size_t smem_m = (size_t)kImStages * kImTileBytes;
+    typedef void (*MFn)(const uint16_t*, const float*, const float*, uint16_t*, int, int, float, long long);
+    MFn mfn = bf16 ? image_attention_mma_kernel<true> : image_attention_mma_kernel<false>;
+    static bool attr_m[2] = {false, false};
+    if (!attr_m[bf16 ? 1 : 0]) {
+      L4P_CHECK_CUDA(cudaFuncSetAttribute(mfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m));
+      attr_m[bf16 ? 1 : 0] = true;
+    }
+    const long long sms = host_num_sms();
+    const unsigned grid_m = (unsigned)(n_tiles < sms ? n_tiles : sms);
+    mfn<<<grid_m, kIaThreads, smem_m, (cudaStream_t)stream>>>((const uint16_t*)q16, k, v, (uint16_t*)out16, Np, nk, scale, n_tiles);
+    L4P_CHECK_CUDA(cudaGetLastError());
+    return L4P_OK;
+  }
+  if (stream_mode >= 1 && H == kIaH && Np % kIaRows == 0) {
     const long long n_tiles = (long long)G * Np / kIaRows;
     const size_t smem_s = 2 * (size_t)kTokMaxQ * kIaH * kIaDP * 4 + (size_t)kIaStages * kIaTileBytes;
     typedef void (*SFn)(const uint16_t*, const float*, const float*, uint16_t*, int, int, float, long long);
