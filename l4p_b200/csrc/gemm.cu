@@ -82,6 +82,16 @@ extern "C" int l4p_gemm(const l4p_gemm_desc* d, void* stream_) {
   L4P_REQUIRE(d->N % 16 == 0, L4P_ERR_SHAPE, "l4p_gemm: N=%lld must be a multiple of 16", (long long)d->N);
   L4P_REQUIRE(d->ldw % 8 == 0 && d->ldw >= d->K, L4P_ERR_SHAPE, "l4p_gemm: ldw=%lld", (long long)d->ldw);
 
+  L4P_REQUIRE(d->a_mode == L4P_A_MATRIX || d->a_mode == L4P_A_CONV3D, L4P_ERR_ARG, "l4p_gemm: a_mode=%d", d->a_mode);
+  if (d->a_mode == L4P_A_CONV3D) {
+    // validate the box before it is used as a divisor: a zeroed / malformed conv descriptor is an argument error, not a SIGFPE
+    L4P_REQUIRE(d->bT > 0 && d->bH > 0 && d->bW > 0 && d->bT * d->bH * d->bW == kBlockM, L4P_ERR_SHAPE,
+                "l4p_gemm: conv box %dx%dx%d must have %d voxels", d->bT, d->bH, d->bW, kBlockM);
+    L4P_REQUIRE(d->cB > 0 && d->cT > 0 && d->cH > 0 && d->cW > 0 && d->cCin > 0 && d->kT > 0 && d->kH > 0 && d->kW > 0,
+                L4P_ERR_SHAPE, "l4p_gemm: conv geometry B=%d T=%d H=%d W=%d Cin=%d k=%dx%dx%d", d->cB, d->cT, d->cH, d->cW,
+                d->cCin, d->kT, d->kH, d->kW);
+  }
+
   GemmKParams p;
   memset(&p, 0, sizeof(p));
   p.M = (int)d->M;
@@ -114,9 +124,7 @@ extern "C" int l4p_gemm(const l4p_gemm_desc* d, void* stream_) {
   if (d->block_n <= 0 && d->store_mode != L4P_STORE_HEAD1X1 && split_k == 1) {
     // few output tiles (low-resolution pyramid levels, token-side GEMMs): trade tile width for CTAs so that more
     // than a handful of SMs work on the (long) K loop
-    const long long tm = d->a_mode == L4P_A_CONV3D
-                             ? (long long)d->cB * ((d->cT + d->bT - 1) / d->bT) * ((d->cH + d->bH - 1) / d->bH) * ((d->cW + d->bW - 1) / d->bW)
-                             : (d->M + kBlockM - 1) / kBlockM;
+    const long long tm = tm_all;
     while (p.block_n >= 64 && (p.block_n / 2) % 16 == 0 && tm * ((d->N + p.block_n - 1) / p.block_n) < 96)
       p.block_n /= 2;
   }

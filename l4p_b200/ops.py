@@ -24,6 +24,13 @@ def _dev_init(t: torch.Tensor) -> None:
     if not t.is_cuda:
         raise _l.L4PError("l4p_b200 ops need CUDA tensors (no CPU fallback exists for this path)")
     idx = t.device.index if t.device.index is not None else torch.cuda.current_device()
+    # One process per GPU: kernels are launched on the CURRENT device's current stream and the
+    # library's per-function attributes / SM count are per process, so operands on another device are an error, not a
+    # silent launch on the wrong stream.
+    cur = torch.cuda.current_device()
+    if idx != cur:
+        raise _l.L4PError(f"tensor on cuda:{idx} but the current device is cuda:{cur}: l4p_b200 runs one process per GPU "
+                          f"(call torch.cuda.set_device first)")
     if idx not in _initialised:
         _l.check(_l.load().l4p_init(idx, 1), "l4p_init")
         _initialised.add(idx)

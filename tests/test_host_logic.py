@@ -242,3 +242,27 @@ def test_attention_synchronisation_protocol_model():
     caught = sim.self_test(seeds=20)
     assert all(v > 0 for v in caught.values()), caught
     sim.check_all(seeds=25, verbose=False)
+
+
+def test_malformed_conv_descriptor_is_an_argument_error():
+    """A zeroed / malformed conv descriptor must come back as an error code from the C ABI (argument validation before any
+    use of the box as a divisor), never as a SIGFPE inside the library (round-1 advisor finding on gemm.cu)."""
+    import ctypes as C
+
+    from l4p_b200 import lib
+
+    L = lib.load()
+    out = (C.c_int * 6)()
+    d = lib.GemmDesc()
+    d.a, d.w, d.out_16 = 0x10000, 0x10000, 0x10000
+    d.M, d.N, d.K, d.lda, d.ldw, d.ld_out = 256, 256, 27 * 64, 64, 27 * 64, 256
+    d.a_mode, d.store_mode = lib.A_CONV3D, lib.STORE_ROWMAJOR          # every conv field left at zero
+    assert L.l4p_gemm_plan(C.byref(d), out) != 0
+    assert b"conv box" in L.l4p_last_error()
+    d.bT, d.bH, d.bW = 2, 8, 7                                           # 112 voxels: not a 128-row tile
+    assert L.l4p_gemm_plan(C.byref(d), out) != 0
+    d.bW = 8                                                             # box ok, geometry still zero
+    assert L.l4p_gemm_plan(C.byref(d), out) != 0
+    assert b"conv geometry" in L.l4p_last_error()
+    d.a_mode = 7
+    assert L.l4p_gemm_plan(C.byref(d), out) != 0
