@@ -568,18 +568,14 @@ extern "C" int l4p_token_attention(const float* q, const void* k16, const void* 
 
 namespace l4p {
 // ----------------------------------------------------------------------------------------------------------------------
-// Streaming image -> token attention (round 2): persistent CTAs, 32-row tiles of the 16-bit query stream moved by 1-D bulk
-// TMA copies through a 4-deep shared-memory ring (three tiles = 135 KB in flight per SM, the round-1 kernel had one
-// synchronous tile: 0.24 of the HBM roofline, ncu: long-scoreboard bound), computed IN PLACE (each thread owns one
-// (row, head) slice of 176 bytes: scores against the nk <= 6 keys, softmax, weighted sum of the values, written over its own
-// query slice) and written back with bulk stores. Lane mapping: lane = 8 * (row % 4) + head, warp w owns rows 4w .. 4w+3 of
-// the tile - the 16-byte accesses of a warp then fall into four conflict-free 128-byte wavefronts although the tile has the
-// dense 1408-byte row pitch a bulk copy produces. K (pre-scaled) and V sit in shared memory as fp32 [nk][head][92] (pad 88
-// -> 92 floats: the eight heads' float4 reads hit eight different bank groups).
+// Streaming image -> token attention (round 2): persistent CTAs, 32-row tiles of the 16-bit query stream moved by bulk TMA
+// copies through a 4-deep shared-memory ring (three tiles = 135 KB in flight per SM; the round-1 kernel above has one
+// synchronous tile: 467 us = 0.24 of the HBM roofline, long-scoreboard bound), computed in place, written back with bulk
+// stores. A first version kept the FMA formulation (thread = (row, head), K / V as fp32 in shared memory): 356 us = 0.32 -
+// not HBM- but LDS-bound (see the tensor-core kernel below, which replaced it: 184 us = 0.62).
 // ----------------------------------------------------------------------------------------------------------------------
-constexpr int kIaRows = 32, kIaStages = 4, kIaThreads = 256, kIaD = 88, kIaDP = 92, kIaH = 8;
+constexpr int kIaRows = 32, kIaThreads = 256, kIaD = 88, kIaH = 8;
 constexpr int kIaRowBytes = kIaH * kIaD * 2;              // 1408
-constexpr int kIaTileBytes = kIaRows * kIaRowBytes;       // 45056
 
 L4P_DEVICE void bulk_load(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
@@ -595,135 +591,6 @@ L4P_DEVICE void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %
 template <int N>
 L4P_DEVICE void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <bool BF16>
-__global__ void __launch_bounds__(kIaThreads, 1)
-image_attention_stream_kernel(const uint16_t* __restrict__ q16, const float* __restrict__ kf, const float* __restrict__ vf,
-                              uint16_t* __restrict__ out16, int Np, int nk, float scale, long long n_tiles) {
-  extern __shared__ __align__(128) uint8_t ia_smem[];
-  __shared__ __align__(8) uint64_t bar_full[kIaStages];
-  float* s_k = reinterpret_cast<float*>(ia_smem);                       // [kTokMaxQ][8][92]
-  float* s_v = s_k + kTokMaxQ * kIaH * kIaDP;
-  const uint32_t ring = smem_u32(ia_smem) + 2u * kTokMaxQ * kIaH * kIaDP * 4u;   // 4 x 45056, 128-byte aligned
-  uint8_t* ring_ptr = ia_smem + 2 * kTokMaxQ * kIaH * kIaDP * 4;
-
-  // contiguous tile range of this CTA
-  const long long per = (n_tiles + gridDim.x - 1) / gridDim.x;
-  const long long t_begin = (long long)blockIdx.x * per;
-  const long long t_end = t_begin + per < n_tiles ? t_begin + per : n_tiles;
-  const int tiles_per_group = Np / kIaRows;
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < kIaStages; ++s) mbar_init(smem_u32(&bar_full[s]), 1);
-    fence_mbar_init();
-  }
-  __syncthreads();
-  if (t_begin >= t_end) return;
-  const int n_local = (int)(t_end - t_begin);
-  // prologue: the first kIaStages - 1 tiles
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < kIaStages - 1 && i < n_local; ++i) {
-      const uint32_t fb = smem_u32(&bar_full[i]);
-      mbar_expect_tx(fb, kIaTileBytes);
-      bulk_load(ring + (uint32_t)i * kIaTileBytes, q16 + (t_begin + i) * (long long)kIaRows * (kIaH * kIaD), kIaTileBytes, fb);
-    }
-  }
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int h = lane & 7, rr = warp * 4 + (lane >> 3);          // head, row inside the tile
-  int cur_g = -1;
-  for (int i = 0; i < n_local; ++i) {
-    const long long tile = t_begin + i;
-    const int g = (int)(tile / tiles_per_group);
-    if (g != cur_g) {   // (re)load this group's keys / values; rare: a group spans Np / 32 consecutive tiles
-      __syncthreads();
-      for (int e = threadIdx.x; e < nk * kIaH * kIaD; e += kIaThreads) {
-        const int j = e / (kIaH * kIaD), c = e - j * (kIaH * kIaD);
-        const int hh = c / kIaD, dd = c - hh * kIaD;
-        s_k[(j * kIaH + hh) * kIaDP + dd] = kf[((long long)g * nk + j) * (kIaH * kIaD) + c] * scale;
-        s_v[(j * kIaH + hh) * kIaDP + dd] = vf[((long long)g * nk + j) * (kIaH * kIaD) + c];
-      }
-      __syncthreads();
-      cur_g = g;
-    }
-    const int s = i % kIaStages;
-    mbar_wait(smem_u32(&bar_full[s]), (uint32_t)(i / kIaStages) & 1u);
-    uint16_t* mine = reinterpret_cast<uint16_t*>(ring_ptr + (size_t)s * kIaTileBytes) + rr * (kIaH * kIaD) + h * kIaD;
-    // ---- scores: packed f32x2 partial sums (even / odd channel) per key
-    uint4 raw[kIaD / 8];
-#pragma unroll
-    for (int c8 = 0; c8 < kIaD / 8; ++c8) raw[c8] = *reinterpret_cast<const uint4*>(mine + c8 * 8);
-    uint64_t sc2[kTokMaxQ];
-#pragma unroll
-    for (int j = 0; j < kTokMaxQ; ++j) sc2[j] = pk2(0.f, 0.f);
-#pragma unroll
-    for (int c8 = 0; c8 < kIaD / 8; ++c8) {
-      const float2 q0 = unpack2<BF16>(raw[c8].x), q1 = unpack2<BF16>(raw[c8].y), q2 = unpack2<BF16>(raw[c8].z),
-                   q3 = unpack2<BF16>(raw[c8].w);
-      const uint64_t p0 = pk2(q0.x, q0.y), p1 = pk2(q1.x, q1.y), p2 = pk2(q2.x, q2.y), p3 = pk2(q3.x, q3.y);
-#pragma unroll
-      for (int j = 0; j < kTokMaxQ; ++j) {
-        if (j < nk) {
-          const ulonglong2* kk = reinterpret_cast<const ulonglong2*>(s_k + (j * kIaH + h) * kIaDP + c8 * 8);
-          const ulonglong2 ka = kk[0], kb = kk[1];
-          uint64_t a = sc2[j];
-          a = fma2(p0, ka.x, a); a = fma2(p1, ka.y, a); a = fma2(p2, kb.x, a); a = fma2(p3, kb.y, a);
-          sc2[j] = a;
-        }
-      }
-    }
-    float sc[kTokMaxQ];
-    float mx = -INFINITY;
-#pragma unroll
-    for (int j = 0; j < kTokMaxQ; ++j) {
-      float a, b;
-      upk2(sc2[j], a, b);
-      sc[j] = a + b;
-      if (j < nk) mx = fmaxf(mx, sc[j]);
-    }
-    float sum = 0.f;
-#pragma unroll
-    for (int j = 0; j < kTokMaxQ; ++j) {
-      sc[j] = j < nk ? __expf(sc[j] - mx) : 0.f;
-      sum += sc[j];
-    }
-    const float inv = 1.f / sum;
-    uint64_t pj2[kTokMaxQ];
-#pragma unroll
-    for (int j = 0; j < kTokMaxQ; ++j) pj2[j] = pk2(sc[j] * inv, sc[j] * inv);
-    // ---- output: sum_j p_j v_j, written over this thread's own (fully consumed) query slice
-#pragma unroll
-    for (int c8 = 0; c8 < kIaD / 8; ++c8) {
-      uint64_t o0 = pk2(0.f, 0.f), o1 = o0, o2 = o0, o3 = o0;
-#pragma unroll
-      for (int j = 0; j < kTokMaxQ; ++j) {
-        if (j < nk) {
-          const ulonglong2* vv = reinterpret_cast<const ulonglong2*>(s_v + (j * kIaH + h) * kIaDP + c8 * 8);
-          const ulonglong2 va = vv[0], vb = vv[1];
-          o0 = fma2(pj2[j], va.x, o0); o1 = fma2(pj2[j], va.y, o1); o2 = fma2(pj2[j], vb.x, o2); o3 = fma2(pj2[j], vb.y, o3);
-        }
-      }
-      float a0, a1, b0, b1, c0, c1, d0, d1;
-      upk2(o0, a0, a1); upk2(o1, b0, b1); upk2(o2, c0, c1); upk2(o3, d0, d1);
-      *reinterpret_cast<uint4*>(mine + c8 * 8) =
-          make_uint4(pack2<BF16>(a0, a1), pack2<BF16>(b0, b1), pack2<BF16>(c0, c1), pack2<BF16>(d0, d1));
-    }
-    fence_proxy_async();   // generic-proxy writes of the tile -> visible to the bulk store (async proxy)
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      bulk_store(out16 + tile * (long long)kIaRows * (kIaH * kIaD), ring + (uint32_t)s * kIaTileBytes, kIaTileBytes);
-      bulk_commit();
-      // the slot that tile i + kIaStages - 1 will use held tile i - 1: its store (the second newest group) must have finished
-      // READING shared memory before the next load overwrites it
-      const int nxt = i + kIaStages - 1;
-      if (nxt < n_local) {
-        bulk_wait_read<1>();
-        const int ns = nxt % kIaStages;
-        const uint32_t fb = smem_u32(&bar_full[ns]);
-        mbar_expect_tx(fb, kIaTileBytes);
-        bulk_load(ring + (uint32_t)ns * kIaTileBytes, q16 + (t_begin + nxt) * (long long)kIaRows * (kIaH * kIaD), kIaTileBytes, fb);
-      }
-    }
-  }
-  if (threadIdx.x == 0) bulk_wait_all<0>();   // all stores complete before the CTA (and its shared memory) goes away
-}
 }  // namespace l4p
 
 
@@ -774,7 +641,7 @@ __global__ void __launch_bounds__(kIaThreads, 1)
 image_attention_mma_kernel(const uint16_t* __restrict__ q16, const float* __restrict__ kf, const float* __restrict__ vf,
                            uint16_t* __restrict__ out16, int Np, int nk, float scale, long long n_tiles) {
   extern __shared__ __align__(128) uint8_t im_smem[];
-  __shared__ __align__(8) uint64_t bar_full[kImStages];
+  __shared__ __align__(8) uint64_t bar_full[kImStages], bar_done[kImStages];
   const uint32_t ring = smem_u32(im_smem);
   constexpr int ld = kIaH * kIaD;   // 704 elements per row
   const long long per = (n_tiles + gridDim.x - 1) / gridDim.x;
@@ -783,7 +650,10 @@ image_attention_mma_kernel(const uint16_t* __restrict__ q16, const float* __rest
   const int tiles_per_group = Np / kIaRows;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kImStages; ++s) mbar_init(smem_u32(&bar_full[s]), 1);
+    for (int s = 0; s < kImStages; ++s) {
+      mbar_init(smem_u32(&bar_full[s]), 1);
+      mbar_init(smem_u32(&bar_done[s]), kIaThreads / 32);   // one arrival per warp: its head's slice of the tile is final
+    }
     fence_mbar_init();
   }
   // the 16 pad bytes of every ring row are read (times zero) by the last k-step of head 7: never leave NaN patterns there
@@ -868,9 +738,13 @@ image_attention_mma_kernel(const uint16_t* __restrict__ q16, const float* __rest
         asm volatile("st.shared.b32 [%0], %1;" ::"r"(orow1 + nt * 16), "r"(pack2<BF16>(o[2], o[3])) : "memory");
       }
     }
-    fence_proxy_async();   // generic-proxy writes of the tile -> visible to the bulk stores (async proxy)
-    __syncthreads();
+    // no CTA-wide barrier per tile: every warp publishes its slice (generic-proxy writes -> async proxy) and moves on to
+    // the next tile of the ring; only warp 0, which owns the bulk copies, waits until all eight heads of the tile are final
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(smem_u32(&bar_done[s]));
     if (warp == 0) {
+      mbar_wait(smem_u32(&bar_done[s]), (uint32_t)(i / kImStages) & 1u);
       bulk_store(out16 + (tile * (long long)kIaRows + lane) * ld, ring + (uint32_t)s * kImTileBytes + (uint32_t)lane * kImPitch,
                  kIaRowBytes);
       bulk_commit();
@@ -890,13 +764,13 @@ extern "C" int l4p_image_attention(const void* q16, const float* k, const float*
   L4P_REQUIRE(q16 && k && v && out16, L4P_ERR_ARG, "l4p_image_attention: null pointer");
   L4P_REQUIRE(d == 88, L4P_ERR_SHAPE, "l4p_image_attention: head_dim=%d (this build: 88)", d);
   L4P_REQUIRE(G > 0 && nk > 0 && nk <= kTokMaxQ && H > 0 && H <= 8, L4P_ERR_SHAPE, "l4p_image_attention: nk=%d H=%d (<= 8)", nk, H);
-  // L4P_IMGATT_STREAM: 2 (default) tensor-core streaming kernel, 1 FMA streaming kernel, 0 round-1 kernel (A/B runs)
+  // L4P_IMGATT_STREAM=0 selects the round-1 kernel (A/B runs; it also serves shapes the streaming kernel does not take)
   static int stream_mode = -1;
   if (stream_mode < 0) {
     const char* e = getenv("L4P_IMGATT_STREAM");
-    stream_mode = e ? atoi(e) : 2;
+    stream_mode = e ? atoi(e) : 1;
   }
-  if (stream_mode == 2 && H == kIaH && Np % kIaRows == 0 && nk <= 8) {
+  if (stream_mode != 0 && H == kIaH && Np % kIaRows == 0 && nk <= 8) {
     const long long n_tiles = (long long)G * Np / kIaRows;
     const size_t smem_m = (size_t)kImStages * kImTileBytes;
     typedef void (*MFn)(const uint16_t*, const float*, const float*, uint16_t*, int, int, float, long long);
@@ -909,22 +783,6 @@ extern "C" int l4p_image_attention(const void* q16, const float* k, const float*
     const long long sms = host_num_sms();
     const unsigned grid_m = (unsigned)(n_tiles < sms ? n_tiles : sms);
     mfn<<<grid_m, kIaThreads, smem_m, (cudaStream_t)stream>>>((const uint16_t*)q16, k, v, (uint16_t*)out16, Np, nk, scale, n_tiles);
-    L4P_CHECK_CUDA(cudaGetLastError());
-    return L4P_OK;
-  }
-  if (stream_mode >= 1 && H == kIaH && Np % kIaRows == 0) {
-    const long long n_tiles = (long long)G * Np / kIaRows;
-    const size_t smem_s = 2 * (size_t)kTokMaxQ * kIaH * kIaDP * 4 + (size_t)kIaStages * kIaTileBytes;
-    typedef void (*SFn)(const uint16_t*, const float*, const float*, uint16_t*, int, int, float, long long);
-    SFn sfn = bf16 ? image_attention_stream_kernel<true> : image_attention_stream_kernel<false>;
-    static bool attr[2] = {false, false};
-    if (!attr[bf16 ? 1 : 0]) {
-      L4P_CHECK_CUDA(cudaFuncSetAttribute(sfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
-      attr[bf16 ? 1 : 0] = true;
-    }
-    const long long sms = host_num_sms();
-    const unsigned grid_s = (unsigned)(n_tiles < sms ? n_tiles : sms);
-    sfn<<<grid_s, kIaThreads, smem_s, (cudaStream_t)stream>>>((const uint16_t*)q16, k, v, (uint16_t*)out16, Np, nk, scale, n_tiles);
     L4P_CHECK_CUDA(cudaGetLastError());
     return L4P_OK;
   }

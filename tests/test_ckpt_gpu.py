@@ -77,7 +77,7 @@ def test_lightning_checkpoint_round_trip_through_prepare_model(tmp_path):
             continue
         # split-K sums (low-resolution DPT levels, the track head's skinny token GEMMs) are accumulated with atomics:
         # order-dependent fp32 round-off that flips 16-bit roundings downstream (measured run to run: <= 8e-4 on the
-        # small-magnitude visibility logits, <= 1e-4 on the dense maps)
-        assert r < (2e-3 if k.startswith("track_2d") else 5e-4), (k, r)
+        # small-magnitude visibility logits, <= 7e-4 on the dense logit maps)
+        assert r < (2e-3 if k.startswith("track_2d") else 1.5e-3), (k, r)
     # inference-frozen: the large fp32 masters are gone (state_dict holds empty tensors for them)
     assert m2.l4p_model.video_encoder.blocks[0].mlp.fc1.weight.numel() == 0

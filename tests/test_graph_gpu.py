@@ -53,5 +53,5 @@ def test_graph_replay_equals_eager_step():
                 assert torch.isfinite(got[k]).all()
                 continue
             # same kernels, same operands; split-K atomics make low-resolution sums order-dependent (tests/test_ckpt_gpu.py)
-            assert r < (2e-3 if k.startswith("track_2d") else 5e-4), (k, r)
+            assert r < (2e-3 if k.startswith("track_2d") else 1.5e-3), (k, r)
     assert rel_l2(got2["depth_est_b1thw"], got1["depth_est_b1thw"]) > 1e-3      # the second call really used the new inputs

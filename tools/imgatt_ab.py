@@ -1,6 +1,6 @@
 """A/B at the real size (128 queries x 2048 video tokens, 8 heads of 88, 6 keys): round-1 image-attention kernel
-(L4P_IMGATT_STREAM=0) vs the round-2 streaming kernels (1: FMA formulation on a bulk-TMA ring, 2: tensor-core formulation with
-K / V in registers, default), each in its own subprocess (the selector is
+(L4P_IMGATT_STREAM=0) vs the round-2 streaming kernel (default: bulk-TMA ring + tensor-core formulation with K / V in
+registers), each in its own subprocess (the selector is
 read once per process): parity of 4096 sampled rows against fp32 torch, time per launch, achieved HBM GB/s
 (algorithmic bytes = read + write of the [G*Np, 704] 16-bit stream = 738 MB)."""
 import os
@@ -8,7 +8,7 @@ import subprocess
 import sys
 
 if os.environ.get("_IA_ARM") is None:
-    for arm in (sys.argv[1:] or ["0", "1", "2"]):
+    for arm in (sys.argv[1:] or ["0", "1"]):
         r = subprocess.run([sys.executable, __file__], env=dict(os.environ, _IA_ARM=arm, L4P_IMGATT_STREAM=arm),
                            capture_output=True, text=True, timeout=240)
         print(f"--- L4P_IMGATT_STREAM={arm} (exit {r.returncode})\n{r.stdout}{r.stderr[-1500:]}")

@@ -52,7 +52,7 @@ with torch.no_grad():
     for _ in range(2):
         records.clear()
         for c in range(1):
-            bench.run_clip(model, batch, 0)
+            lit.predict_step(dict(batch), 0)
         torch.cuda.synchronize()
 agg = collections.OrderedDict()
 for name, desc, fl, e0, e1 in records:
