@@ -8,16 +8,31 @@ namespace l4p {
 
 constexpr int kLnMaxVec = 12;  // float4 per lane: cols <= 12*4*32 = 1536
 
-template <bool BF16>
+// PRE: fetch gamma / beta before the programmatic-dependency wait (the launch-latency-bound small-row case: +96 registers
+// are free there); the large-row, bandwidth-bound case keeps the registers for occupancy and reads them at the end.
+template <bool BF16, bool PRE>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                  uint16_t* __restrict__ y16, float* __restrict__ y32, long long rows, int cols, float eps) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+  const int nvec = cols >> 2;  // float4 per row
+  // gamma / beta are weights: fetched BEFORE the programmatic-dependency wait, so their L2 latency overlaps the
+  // predecessor's tail instead of sitting between the two reductions and the store
+  float4 gam[PRE ? kLnMaxVec : 1], bet[PRE ? kLnMaxVec : 1];
+  if constexpr (PRE) {
+#pragma unroll
+    for (int i = 0; i < kLnMaxVec; ++i) {
+      const int j = lane + i * 32;
+      if (j < nvec) {
+        gam[i] = reinterpret_cast<const float4*>(gamma)[j];
+        bet[i] = reinterpret_cast<const float4*>(beta)[j];
+      }
+    }
+  }
   pdl_launch_dependents();
   pdl_wait();
   if (row >= rows) return;
-  const int nvec = cols >> 2;  // float4 per row
   const float4* xr = reinterpret_cast<const float4*>(x + row * cols);
   float4 v[kLnMaxVec];
   float s = 0.f;
@@ -44,8 +59,8 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
   for (int i = 0; i < kLnMaxVec; ++i) {
     const int j = lane + i * 32;
     if (j < nvec) {
-      const float4 g = reinterpret_cast<const float4*>(gamma)[j];
-      const float4 b = reinterpret_cast<const float4*>(beta)[j];
+      const float4 g = PRE ? gam[PRE ? i : 0] : reinterpret_cast<const float4*>(gamma)[j];
+      const float4 b = PRE ? bet[PRE ? i : 0] : reinterpret_cast<const float4*>(beta)[j];
       float4 o;
       o.x = (v[i].x - mean) * rstd * g.x + b.x;
       o.y = (v[i].y - mean) * rstd * g.y + b.y;
@@ -75,15 +90,15 @@ extern "C" int l4p_layernorm(const float* x, const float* gamma, const float* be
   const long long llrows = rows;
   if (grid <= 2048u) {
     if (bf16)
-      L4P_CHECK_CUDA(launch_pdl(layernorm_kernel<true>, dim3(grid), dim3(wpb * 32), 0, (cudaStream_t)stream, x, gamma, beta, (uint16_t*)y16, y32, llrows, cols, eps));
+      L4P_CHECK_CUDA(launch_pdl(layernorm_kernel<true, true>, dim3(grid), dim3(wpb * 32), 0, (cudaStream_t)stream, x, gamma, beta, (uint16_t*)y16, y32, llrows, cols, eps));
     else
-      L4P_CHECK_CUDA(launch_pdl(layernorm_kernel<false>, dim3(grid), dim3(wpb * 32), 0, (cudaStream_t)stream, x, gamma, beta, (uint16_t*)y16, y32, llrows, cols, eps));
+      L4P_CHECK_CUDA(launch_pdl(layernorm_kernel<false, true>, dim3(grid), dim3(wpb * 32), 0, (cudaStream_t)stream, x, gamma, beta, (uint16_t*)y16, y32, llrows, cols, eps));
     return L4P_OK;
   }
   if (bf16)
-    layernorm_kernel<true><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>(x, gamma, beta, (uint16_t*)y16, y32, rows, cols, eps);
+    layernorm_kernel<true, false><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>(x, gamma, beta, (uint16_t*)y16, y32, rows, cols, eps);
   else
-    layernorm_kernel<false><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>(x, gamma, beta, (uint16_t*)y16, y32, rows, cols, eps);
+    layernorm_kernel<false, false><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>(x, gamma, beta, (uint16_t*)y16, y32, rows, cols, eps);
   L4P_CHECK_CUDA(cudaGetLastError());
   return L4P_OK;
 }
