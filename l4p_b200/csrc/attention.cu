@@ -48,13 +48,13 @@ constexpr float kRescaleThreshold = 8.0f;  // log2 units
 // Variants measured on hardware in round 2 and removed (profiles/attention_r2.md): both tiles' P aliased onto S in TMEM
 // (FA4-style; S(j+1) then queues behind PV(j): -11 %), a cta_group::2 kernel sharing K/V between two SMs (-20 %: the
 // shared-memory operand port is NOT the limiter), S(j+1) of both tiles issued before PV(j) (-2 %), and the softmax
-// denominator taken from a ones-row of V^T through the PV UMMA (+-0 %).
+// denominator taken from a ones-row of V^T through the PV UMMA (+-0 %), an event-driven issuer that polls the four
+// operand-ready conditions instead of the fixed S0 PV0 S1 PV1 order (-3 %).
 struct AttParams {
   uint16_t* out;
   int B, H, N, head_dim;
   float scale_log2;  // scale * log2(e)
   long long* prof;   // optional [3 roles][64 iters][8] clock64 stamps of CTA 0 (debug; NULL in production)
-  int issue_mode;    // UMMA issuer: 0 = fixed order S0 PV0 S1 PV1 per key block, 1 = event-driven (whatever is ready)
 };
 
 #define ATT_STAMP(role, it, slot) \
@@ -219,47 +219,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         umma_commit(smem_u32(&bar_kempty[0]));
       }
       __syncwarp();
-      if (p.issue_mode == 1) {
-        // Event-driven issue: in the fixed order below S_0(j+1) sits behind the wait for P_1(j-1), i.e. it is issued about half
-        // a softmax period after warpgroup 0 asked for it (head-of-line blocking of the single in-order issuer); here one
-        // thread polls the four conditions and issues whichever contraction has its operands ready.
-        if (leader) {
-          int s_next[2] = {1, 1}, pv_next[2] = {0, 0};
-          long long t0 = clock64();
-          while (pv_next[0] < nblk || pv_next[1] < nblk) {
-            bool progress = false;
-#pragma unroll
-            for (int t = 0; t < 2; ++t) {
-              const int jn = s_next[t];
-              if (jn < nblk && mbar_try_wait(smem_u32(&bar_sfree[t]), (uint32_t)(jn - 1) & 1u) &&
-                  mbar_try_wait(smem_u32(&bar_kfull[jn % kKS]), ((uint32_t)(jn / kKS)) & 1u)) {
-                tc_fence_after();
-                issue_s(t, jn % kKS);
-                s_next[t] = jn + 1;
-                if (s_next[t ^ 1] > jn) umma_commit(smem_u32(&bar_kempty[jn % kKS]));   // both tiles have issued S(jn)
-                progress = true;
-              }
-              const int j = pv_next[t];
-              if (j < nblk && mbar_try_wait(smem_u32(&bar_pfull[t]), (uint32_t)j & 1u) &&
-                  mbar_try_wait(smem_u32(&bar_vfull[j % kVS]), ((uint32_t)(j / kVS)) & 1u)) {
-                tc_fence_after();
-                issue_pv(t, j % kVS, j != 0 ? 1u : 0u);
-                pv_next[t] = j + 1;
-                if (pv_next[t ^ 1] > j) umma_commit(smem_u32(&bar_vempty[j % kVS]));     // both tiles have issued PV(j)
-                progress = true;
-              }
-            }
-            if (progress) {
-              t0 = clock64();
-            } else if (clock64() - t0 > L4P_MBAR_TIMEOUT_CYCLES) {
-              printf("l4p: attention issuer stalled block %d (s %d %d pv %d %d)\n", blockIdx.x, s_next[0], s_next[1], pv_next[0],
-                     pv_next[1]);
-              __trap();
-            }
-          }
-        }
-        __syncwarp();
-      } else
       for (int j = 0; j < nblk; ++j) {
         const int jn = j + 1;
         const int sk = jn % kKS, sv = j % kVS;
@@ -515,12 +474,6 @@ extern "C" int l4p_attention(const void* q, const void* k, const void* vt, void*
   p.B = B; p.H = H; p.N = N; p.head_dim = head_dim;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.prof = (long long*)prof;
-  static int issue_mode = -1;
-  if (issue_mode < 0) {
-    const char* e = getenv("L4P_ATT_ISSUE");
-    issue_mode = e ? atoi(e) : 0;
-  }
-  p.issue_mode = issue_mode;
   // POLY = number of score pairs (of every 8) whose exp2 runs as an FMA-pipe polynomial instead of MUFU
   static int poly = -1;
   if (poly < 0) {
