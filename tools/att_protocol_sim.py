@@ -1,4 +1,6 @@
-"""Discrete-event model of the attention kernels' synchronisation protocol (csrc/attention.cu and csrc/attention_pair.cu):
+"""Discrete-event model of the attention kernel's synchronisation protocol (csrc/attention.cu; it also still models the
+round-1 experiment variants - CTA pair, S-first, P-alias - that were measured on hardware in round 2 and removed from the
+tree, see profiles/attention_r2.md: the model is how their protocols were validated before they ever ran):
 mbarriers with phase parity and transaction counts, the TMA producer(s), the single UMMA-issuing thread, the in-order
 tensor pipe with tcgen05.commit arrivals (multicast for the CTA pair), and the softmax warpgroups. Every buffer (Q tiles,
 K / V ring slots, S_t, P_t, O_t) carries a version tag; each consumer asserts that it sees exactly the version it is

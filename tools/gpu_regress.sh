@@ -1,7 +1,8 @@
 #!/usr/bin/env bash
-# Round-2 GPU call 12: full GPU suite, both bench arms, ncu launch list of one step + fresh attention capture.
+# One gpurun call that regenerates the evidence under profiles/: full GPU suite, both bench arms, the ncu launch list of one
+# step, a fresh ncu --set full capture of the attention kernel, smoke().   gpurun --timeout 3000 -- bash tools/gpu_regress.sh
 set -u
-OUT=gpurun_out/r2_call12
+OUT=gpurun_out/regress
 mkdir -p "$OUT"
 run() { local name=$1; shift; echo "=== $name: $*"; ( timeout "${T:-300}" "$@" ) > "$OUT/$name.log" 2>&1; echo "exit $? ($name)"; tail -n "${TAILN:-4}" "$OUT/$name.log"; }
 TAILN=6 T=1500 run pytest_gpu python -m pytest tests -m gpu -q
