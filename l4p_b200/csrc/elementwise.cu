@@ -64,10 +64,12 @@ L4P_DEVICE Axis axis_coord(int o, int in, int out, int align) {
   return a;
 }
 
-// grid (ceil(Wo * C/8 / 256), Ho, B * To): the (b, t, h) coordinates and their source planes are block-uniform, a
-// thread's (wo, channel group) comes from one 32-bit division. All eight corner loads are issued unconditionally
-// (zero-weight corners re-read an in-range neighbour) so that they are in flight together: the kernel is HBM-bound
-// (1 read of x through L1/L2 reuse, 1 write of y), not integer-math- or latency-bound.
+// grid (ceil(Wo * C/8 / 256), ceil(Ho / kUpRows), B * To): the (b, t) coordinates and their source planes are
+// block-uniform, a thread's (wo, channel group) comes from one 32-bit division and is reused for kUpRows output rows
+// (round 2: one row per thread was instruction-bound - ncu 77 % issue utilisation at 0.25 of the HBM roofline - so the
+// per-thread index math is amortised over four rows and the blend runs as packed f32x2 FMAs: 16 instead of 32 per corner
+// quartet). All corner loads of a row are issued before its arithmetic.
+constexpr int kUpRows = 4;
 template <bool BF16>
 __global__ void __launch_bounds__(256)
 upsample_cl_kernel(const uint16_t* __restrict__ x, uint16_t* __restrict__ y,
@@ -77,52 +79,59 @@ upsample_cl_kernel(const uint16_t* __restrict__ x, uint16_t* __restrict__ y,
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // (wo, g)
   if (idx >= Wo * cg) return;
   const int wo = idx / cg, g = idx - wo * cg;
-  const int ho = blockIdx.y;
   const int b = blockIdx.z / To, to = blockIdx.z - b * To;
   const Axis at = axis_coord(to, Ti, To, align);
-  const Axis ah = axis_coord(ho, Hi, Ho, align);
   const Axis aw = axis_coord(wo, Wi, Wo, align);
+  const bool two_t = at.w1 != 0.f;   // block-uniform: the DPT x2 upsampling keeps T
   const long long plane_t0 = ((long long)b * Ti + at.i0) * Hi, plane_t1 = ((long long)b * Ti + at.i1) * Hi;
-  const uint16_t* r00 = x + ((plane_t0 + ah.i0) * Wi) * (long long)C + g * 8;
-  const uint16_t* r01 = x + ((plane_t0 + ah.i1) * Wi) * (long long)C + g * 8;
-  const uint16_t* r10 = x + ((plane_t1 + ah.i0) * Wi) * (long long)C + g * 8;
-  const uint16_t* r11 = x + ((plane_t1 + ah.i1) * Wi) * (long long)C + g * 8;
-  const long long o0 = (long long)aw.i0 * C, o1 = (long long)aw.i1 * C;
-  uint4 raw[8];
-  raw[0] = *reinterpret_cast<const uint4*>(r00 + o0); raw[1] = *reinterpret_cast<const uint4*>(r00 + o1);
-  raw[2] = *reinterpret_cast<const uint4*>(r01 + o0); raw[3] = *reinterpret_cast<const uint4*>(r01 + o1);
-  if (at.w1 != 0.f) {  // block-uniform: the DPT x2 upsampling keeps T
-    raw[4] = *reinterpret_cast<const uint4*>(r10 + o0); raw[5] = *reinterpret_cast<const uint4*>(r10 + o1);
-    raw[6] = *reinterpret_cast<const uint4*>(r11 + o0); raw[7] = *reinterpret_cast<const uint4*>(r11 + o1);
-  } else {
-    raw[4] = raw[5] = raw[6] = raw[7] = make_uint4(0, 0, 0, 0);
-  }
-  const float wt[2] = {1.f - at.w1, at.w1}, wh[2] = {1.f - ah.w1, ah.w1}, ww[2] = {1.f - aw.w1, aw.w1};
-  float acc[8];
+  const long long o0 = (long long)aw.i0 * C + g * 8, o1 = (long long)aw.i1 * C + g * 8;
+  const float ww0 = 1.f - aw.w1, ww1 = aw.w1, wt0 = 1.f - at.w1, wt1 = at.w1;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-  // the kernel is instruction-bound (ncu: 77 % issue utilisation): only touch the second time plane when it contributes
-#pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    if (c >= 4 && at.w1 == 0.f) break;  // block-uniform
-    const float wgt = wt[c >> 2] * wh[(c >> 1) & 1] * ww[c & 1];
-    const uint32_t r[4] = {raw[c].x, raw[c].y, raw[c].z, raw[c].w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float2 f = unpack2<BF16>(r[i]);
-      acc[2 * i] = fmaf(wgt, f.x, acc[2 * i]);
-      acc[2 * i + 1] = fmaf(wgt, f.y, acc[2 * i + 1]);
+  for (int r = 0; r < kUpRows; ++r) {
+    const int ho = blockIdx.y * kUpRows + r;
+    if (ho >= Ho) break;
+    const Axis ah = axis_coord(ho, Hi, Ho, align);
+    const uint16_t* r00 = x + ((plane_t0 + ah.i0) * Wi) * (long long)C;
+    const uint16_t* r01 = x + ((plane_t0 + ah.i1) * Wi) * (long long)C;
+    uint4 raw[8];
+    raw[0] = *reinterpret_cast<const uint4*>(r00 + o0); raw[1] = *reinterpret_cast<const uint4*>(r00 + o1);
+    raw[2] = *reinterpret_cast<const uint4*>(r01 + o0); raw[3] = *reinterpret_cast<const uint4*>(r01 + o1);
+    if (two_t) {
+      const uint16_t* r10 = x + ((plane_t1 + ah.i0) * Wi) * (long long)C;
+      const uint16_t* r11 = x + ((plane_t1 + ah.i1) * Wi) * (long long)C;
+      raw[4] = *reinterpret_cast<const uint4*>(r10 + o0); raw[5] = *reinterpret_cast<const uint4*>(r10 + o1);
+      raw[6] = *reinterpret_cast<const uint4*>(r11 + o0); raw[7] = *reinterpret_cast<const uint4*>(r11 + o1);
     }
-  }
-  const long long o = ((((long long)b * To + to) * Ho + ho) * (long long)Wo + wo) * C + g * 8;
-  if (y != nullptr)
-    *reinterpret_cast<uint4*>(y + o) = make_uint4(pack2<BF16>(acc[0], acc[1]), pack2<BF16>(acc[2], acc[3]),
-                                                  pack2<BF16>(acc[4], acc[5]), pack2<BF16>(acc[6], acc[7]));
-  if (y_relu != nullptr) {
+    const float wh0 = 1.f - ah.w1, wh1 = ah.w1;
+    const float wgt[8] = {wt0 * wh0 * ww0, wt0 * wh0 * ww1, wt0 * wh1 * ww0, wt0 * wh1 * ww1,
+                          wt1 * wh0 * ww0, wt1 * wh0 * ww1, wt1 * wh1 * ww0, wt1 * wh1 * ww1};
+    uint64_t acc[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = fmaxf(acc[i], 0.f);
-    *reinterpret_cast<uint4*>(y_relu + o) = make_uint4(pack2<BF16>(acc[0], acc[1]), pack2<BF16>(acc[2], acc[3]),
-                                                       pack2<BF16>(acc[4], acc[5]), pack2<BF16>(acc[6], acc[7]));
+    for (int i = 0; i < 4; ++i) acc[i] = pk2(0.f, 0.f);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      if (c >= 4 && !two_t) break;  // block-uniform
+      const uint64_t w2 = pk2(wgt[c], wgt[c]);
+      const uint32_t rr[4] = {raw[c].x, raw[c].y, raw[c].z, raw[c].w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = unpack2<BF16>(rr[i]);
+        acc[i] = fma2(w2, pk2(f.x, f.y), acc[i]);
+      }
+    }
+    float a[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) upk2(acc[i], a[2 * i], a[2 * i + 1]);
+    const long long o = ((((long long)b * To + to) * Ho + ho) * (long long)Wo + wo) * C + g * 8;
+    if (y != nullptr)
+      *reinterpret_cast<uint4*>(y + o) = make_uint4(pack2<BF16>(a[0], a[1]), pack2<BF16>(a[2], a[3]),
+                                                    pack2<BF16>(a[4], a[5]), pack2<BF16>(a[6], a[7]));
+    if (y_relu != nullptr) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = fmaxf(a[i], 0.f);
+      *reinterpret_cast<uint4*>(y_relu + o) = make_uint4(pack2<BF16>(a[0], a[1]), pack2<BF16>(a[2], a[3]),
+                                                         pack2<BF16>(a[4], a[5]), pack2<BF16>(a[6], a[7]));
+    }
   }
 }
 
@@ -242,7 +251,7 @@ extern "C" int l4p_upsample3d(const void* x16, void* y16, void* y16_relu, int B,
   const long long total = (long long)B * To * Ho * Wo * (C / 8);
   L4P_REQUIRE((long long)Wo * (C / 8) < (1ll << 31) && Ho <= 65535 && (long long)B * To <= 65535, L4P_ERR_SHAPE,
               "l4p_upsample3d: grid too large");
-  const dim3 grid((unsigned)(((long long)Wo * (C / 8) + 255) / 256), (unsigned)Ho, (unsigned)(B * To));
+  const dim3 grid((unsigned)(((long long)Wo * (C / 8) + 255) / 256), (unsigned)((Ho + kUpRows - 1) / kUpRows), (unsigned)(B * To));
   if (bf16)
     upsample_cl_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>((const uint16_t*)x16, (uint16_t*)y16,
                                                                        (uint16_t*)y16_relu, B, Ti, Hi, Wi, To, Ho, Wo, C,

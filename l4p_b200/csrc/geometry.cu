@@ -54,14 +54,14 @@ __device__ void mul3(const double* a, const double* b, double* c) {
 // a cyclic Jacobi here (81 + 81 doubles in local memory, 6-9 sweeps x 36 rotations: 0.24 ms per solve on one thread, 4 solves
 // per call = 3 % of the whole all-heads step). Convergence factor (l1 + mu) / (l2 + mu): 1-2 iterations
 // on consistent correspondences (l1 ~ 0); near-degenerate problems (l1 ~ l2: any vector of that eigenspace is as good as
-// another) stop at the iteration cap. Returns the Rayleigh quotient.
+// another) stop at the iteration cap (24). Returns the Rayleigh quotient.
 __device__ double smallest_eigvec9(const double* M, double* x) {
   constexpr int n = 9;
   double tr = 0.0;
 #pragma unroll
   for (int i = 0; i < n; ++i) tr += M[i * n + i];
   double mu = 1e-13 * tr + 1e-300;
-  double L[n * (n + 1) / 2];
+  double L[n * (n + 1) / 2], rd[n];
   for (int attempt = 0; attempt < 4; ++attempt) {
     bool ok = true;
 #pragma unroll
@@ -74,8 +74,9 @@ __device__ double smallest_eigvec9(const double* M, double* x) {
         if (i == j) {
           if (!(a > 0.0)) { ok = false; a = 1.0; }
           L[i * (i + 1) / 2 + j] = sqrt(a);
+          rd[i] = 1.0 / L[i * (i + 1) / 2 + j];      // reciprocal diagonal: the solves below multiply instead of dividing
         } else {
-          L[i * (i + 1) / 2 + j] = a / L[j * (j + 1) / 2 + j];
+          L[i * (i + 1) / 2 + j] = a * rd[j];
         }
       }
     }
@@ -85,21 +86,21 @@ __device__ double smallest_eigvec9(const double* M, double* x) {
   double v[n];
 #pragma unroll
   for (int i = 0; i < n; ++i) v[i] = 1.0 / 3.0 + 0.01 * i;   // generic start (not orthogonal to any eigenvector by symmetry)
-  for (int it = 0; it < 48; ++it) {
+  for (int it = 0; it < 24; ++it) {
     double y[n];
 #pragma unroll
     for (int i = 0; i < n; ++i) {          // L y = v
       double a = v[i];
 #pragma unroll
       for (int k = 0; k < i; ++k) a -= L[i * (i + 1) / 2 + k] * y[k];
-      y[i] = a / L[i * (i + 1) / 2 + i];
+      y[i] = a * rd[i];
     }
 #pragma unroll
     for (int i = n - 1; i >= 0; --i) {     // L^T z = y  (z overwrites y)
       double a = y[i];
 #pragma unroll
       for (int k = i + 1; k < n; ++k) a -= L[k * (k + 1) / 2 + i] * y[k];
-      y[i] = a / L[i * (i + 1) / 2 + i];
+      y[i] = a * rd[i];
     }
     double nn = 0.0, dot = 0.0;
 #pragma unroll

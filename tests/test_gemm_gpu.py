@@ -295,3 +295,27 @@ def test_attention_split_variant():
     assert len(rels) == 5, r.stdout
     for dt, rel in rels:
         assert rel < (6e-3 if dt == "bfloat16" else 1e-3), (dt, rel)
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("shape,out,align", [
+    ((1, 16, 128, 128, 128), (16, 224, 224), True),     # DPT head1 -> head2 resize (dpt_head.py:81-83)
+    ((2, 16, 32, 32, 256), (16, 64, 64), True),          # RefineNet x2 (dpt_block.py:231-236), T kept
+    ((1, 4, 8, 8, 256), (8, 16, 16), True),              # low-resolution level: T scaled too (all eight corners)
+    ((1, 3, 9, 10, 64), (5, 30, 23), False),             # ragged sizes (rows not a multiple of the 4 rows per thread), half-pixel
+])
+def test_upsample3d(dtype, shape, out, align):
+    """Channels-last trilinear resampling (K9) vs F.interpolate on the same rounded input, incl. the fused ReLU copy."""
+    import torch.nn.functional as F
+
+    ops = _ops()
+    B, T, H, W, C = shape
+    x = _rand(shape, dtype, 77)
+    y = torch.empty(B, *out, C, device="cuda", dtype=dtype)
+    yr = torch.empty_like(y)
+    ops.upsample3d(x, out, align_corners=align, y=y, y_relu=yr)
+    torch.cuda.synchronize()
+    ref = F.interpolate(x.float().permute(0, 4, 1, 2, 3), size=out, mode="trilinear", align_corners=align).permute(0, 2, 3, 4, 1)
+    tol = 2 ** -7 if dtype == torch.bfloat16 else 2 ** -10
+    _close(y, ref, tol)
+    _close(yr, ref.clamp_min(0), tol)
