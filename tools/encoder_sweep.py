@@ -34,6 +34,23 @@ for dt in (torch.float16, torch.bfloat16):
         torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 5
     print(f"encoder B={B} {str(dt).split('.')[-1]}: {ms:.2f} ms/pass, {16 * B / ms * 1e3:.0f} frames/s, {ENC_FLOPS_PER_WINDOW * B / ms / 1e9:.0f} TFLOP/s (algorithmic)")
+    # the same pass replayed from a CUDA graph (no Python enqueue between the 280+ kernels)
+    from l4p_b200.graph import StepGraph  # noqa: E402
+    l0 = ops.LAUNCHES
+    g = StepGraph(lambda b: {"last": enc(b["rgb"])[40]}, {"rgb": rgb}, dev, warmup=1)
+    with torch.no_grad():
+        for _ in range(2):
+            g({"rgb": rgb})
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(5):
+            g({"rgb": rgb})
+        e1.record()
+        torch.cuda.synchronize()
+    msg = e0.elapsed_time(e1) / 5
+    print(f"encoder B={B} {str(dt).split('.')[-1]} CUDA graph ({g.launches} launches per pass): {msg:.2f} ms/pass, "
+          f"{ENC_FLOPS_PER_WINDOW * B / msg / 1e9:.0f} TFLOP/s (algorithmic)")
+    del g
     q = torch.randn(B, 16, 2048, 96, device=dev, dtype=dt); q[..., 88:] = 0
     k = torch.randn_like(q); k[..., 88:] = 0
     vt = torch.randn(B, 16, 96, 2048, device=dev, dtype=dt); vt[:, :, 88:] = 0
