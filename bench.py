@@ -236,7 +236,7 @@ def main():
     dt = torch.float16 if args.dtype == "fp16" else torch.bfloat16
     lit = load_model(device=dev, max_queries=NQ + 1, compute_dtype=dt)   # configs/model.yaml: all five tasks, joint alignment
     model = lit.l4p_model
-    weights.fill_module_fast_(model, seed=rank)
+    weights.fill_module_fast_(model, seed=0)    # the same (replicated) weights on every rank, as in deployment
     use_graph = not args.no_graph
     lit.enable_cuda_graph(use_graph)     # predict_step replays one captured graph per input signature
     copy_stream = torch.cuda.Stream(device=dev)
