@@ -168,6 +168,8 @@ class MaskDecoder(nn.Module):
 # ------------------------------------------------------------------------------------------- the head
 class VideoMAETrack2DSamHead(nn.Module):
     compute_dtype = torch.float16
+    # per-query video-token stream between the two-way layers: 16 bit (True) or fp32 (False); L4P_TRACK_STREAM16=0/1 overrides
+    token_stream16 = __import__("os").environ.get("L4P_TRACK_STREAM16", "0") == "1"
 
     def __init__(self, task_name: str = "track_2d", prompt_embed_dim: int = 1408,
                  image_size: Tuple[int, int, int] = (16, 224, 224), patch_size: Tuple[int, int, int] = (2, 14, 14),
@@ -366,6 +368,22 @@ class VideoMAETrack2DSamHead(nn.Module):
                 q16 = q16.unsqueeze(0).expand(G, -1, -1).reshape(G * Pn, -1)
             ao = torch.empty(G * Pn, q16.shape[-1], device=dev, dtype=dt)
             ops.image_attention(q16.contiguous(), k.contiguous(), v.contiguous(), ao, G, a["heads"], 1.0 / math.sqrt(a["hd"]))
+            if self.token_stream16:
+                # 16-bit per-query video-token stream between the two-way layers: the out-projection adds the residual in
+                # fp32 inside its epilogue (from the fp32 tokens in the first layer, from the previous layer's 16-bit LN
+                # output afterwards) and stores 16 bit; the LayerNorm reads and writes 16 bit. Per 128-query call this moves
+                # 5.2 GB instead of 10.4 GB through HBM (the fp32 stream is written, re-read by the LayerNorm, written again
+                # as the next residual and re-read by the next out-projection).
+                new16 = torch.empty(G * Pn, C, device=dev, dtype=dt)
+                if keys32 is not None:
+                    ops.linear(ao, a["o"]["w"], bias=a["o"]["b"], res_f32=keys32, res_row_mod=Pn if shared else 0, out_16=new16)
+                else:
+                    ops.linear(ao, a["o"]["w"], bias=a["o"]["b"], res_16=keys16, out_16=new16)
+                keys16 = torch.empty(G * Pn, C, device=dev, dtype=dt)
+                ops.layernorm16(new16, w["n4"][0], w["n4"][1], w["n4"][2], keys16)
+                keys32 = None
+                shared = False
+                continue
             new32 = torch.empty(G * Pn, C, device=dev, dtype=torch.float32)
             ops.linear(ao, a["o"]["w"], bias=a["o"]["b"], res_f32=keys32, res_row_mod=Pn if shared else 0, out_f32=new32)
             keys16 = torch.empty(G * Pn, C, device=dev, dtype=dt)

@@ -319,3 +319,34 @@ def test_upsample3d(dtype, shape, out, align):
     tol = 2 ** -7 if dtype == torch.bfloat16 else 2 ** -10
     _close(y, ref, tol)
     _close(yr, ref.clamp_min(0), tol)
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("M", [6144, 12288, 2048 * 9])
+def test_linear_16bit_residual_stream(dtype, M):
+    """The epilogue combinations of the track head's 16-bit token stream (sparse_heads.py step (4)) at its shapes
+    (N = 1408, K = 704, M = queries x 2048): fp32 broadcast residual (row % P) -> 16-bit store, 16-bit residual -> 16-bit
+    store, and the 16-bit LayerNorm over 1408 columns that follows."""
+    ops = _ops()
+    N, K, P = 1408, 704, 2048
+    a = _rand((M, K), dtype, 11)
+    w = _rand((N, K), dtype, 12, K ** -0.5)
+    b = _rand((N,), torch.float32, 13)
+    table = _rand((P, N), torch.float32, 14)
+    out = torch.empty(M, N, device="cuda", dtype=dtype)
+    ops.linear(a, w, bias=b, res_f32=table, res_row_mod=P, out_16=out)
+    torch.cuda.synchronize()
+    ref = a.float() @ w.float().t() + b + table.repeat(M // P, 1)
+    tol = 2 ** -7 if dtype == torch.bfloat16 else 2 ** -10
+    _close(out, ref, tol)
+    res16 = _rand((M, N), dtype, 15)
+    out2 = torch.empty_like(out)
+    ops.linear(a, w, bias=b, res_16=res16, out_16=out2)
+    torch.cuda.synchronize()
+    _close(out2, a.float() @ w.float().t() + b + res16.float(), tol)
+    g = 1.0 + 0.1 * _rand((N,), torch.float32, 16)
+    be = 0.02 * _rand((N,), torch.float32, 17)
+    y = torch.empty_like(out2)
+    ops.layernorm16(out2, g, be, 1e-5, y)
+    torch.cuda.synchronize()
+    _close(y, F.layer_norm(out2.float(), (N,), g, be, 1e-5), tol)
