@@ -104,6 +104,16 @@ typedef struct l4p_gemm_desc {
   void* splitk_ws;
   int64_t splitk_ws_bytes;
   int split_k;
+  /* Grouped weights (A_MATRIX + ROWMAJOR, 1-CTA kernel): the rows of A form groups of grp_a_rows consecutive rows, group g
+   * multiplies its OWN weight block: W rows [g*grp_b_rows, g*grp_b_rows + N) of a [groups*grp_b_rows, ldw] matrix
+   * (grp_a_rows = 0: one shared W). m_stride (0 = 128): consecutive 128-row tiles start m_stride rows apart and only the
+   * first m_stride rows of a tile are stored, so that groups smaller than a tile (grp_a_rows == m_stride < 128) still get
+   * one tile each. Used by the track head's token -> video-token attention: per-query score matrices
+   * S_g^T = Q'_g X_g^T (grp_a_rows = m_stride = 48 head-token rows, W = the query's 2048 video tokens) and the per-query
+   * output projection of the video-token -> token attention (sam/transformer.py:223-245 applied through
+   * (q W_k^T) x instead of q (W_k x)). */
+  int64_t grp_a_rows, grp_b_rows;
+  int m_stride;
 } l4p_gemm_desc;
 
 /* Replaces F.linear/addmm (modeling_finetune.py:62-69,171-177,188), the 1x1x1/3x3x3 Conv3d and k==s

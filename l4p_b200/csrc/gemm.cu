@@ -92,13 +92,30 @@ extern "C" int l4p_gemm(const l4p_gemm_desc* d, void* stream_) {
                 d->cCin, d->kT, d->kH, d->kW);
   }
 
+  // grouped weights / tile row stride (see l4p_b200.h): matrix mode, row-major store, 1-CTA kernel, no split-K
+  const bool grouped = d->grp_a_rows > 0;
+  const int m_stride = d->m_stride > 0 ? d->m_stride : kBlockM;
+  if (grouped || m_stride != kBlockM) {
+    L4P_REQUIRE(d->a_mode == L4P_A_MATRIX && d->store_mode == L4P_STORE_ROWMAJOR && d->cta_pair != 1, L4P_ERR_ARG,
+                "l4p_gemm(grouped): matrix mode, row-major store and the 1-CTA kernel only");
+    L4P_REQUIRE(m_stride >= 8 && m_stride <= kBlockM && m_stride % 8 == 0, L4P_ERR_SHAPE, "l4p_gemm: m_stride=%d", m_stride);
+    if (grouped)
+      L4P_REQUIRE(d->grp_a_rows % m_stride == 0 && d->grp_b_rows >= d->N && d->grp_a_rows < (1ll << 31) && d->grp_b_rows < (1ll << 31) &&
+                      ((d->M + d->grp_a_rows - 1) / d->grp_a_rows) * d->grp_b_rows < (1ll << 31),
+                  L4P_ERR_SHAPE, "l4p_gemm(grouped): grp_a_rows=%lld must be a multiple of m_stride=%d, grp_b_rows=%lld >= N",
+                  (long long)d->grp_a_rows, m_stride, (long long)d->grp_b_rows);
+  }
+
   GemmKParams p;
   memset(&p, 0, sizeof(p));
   p.M = (int)d->M;
   p.N = (int)d->N;
+  p.m_stride = m_stride;
+  p.grp_a_rows = (int)d->grp_a_rows;
+  p.grp_b_rows = (int)d->grp_b_rows;
   const long long tm_all = d->a_mode == L4P_A_CONV3D
                                ? (long long)d->cB * ((d->cT + d->bT - 1) / d->bT) * ((d->cH + d->bH - 1) / d->bH) * ((d->cW + d->bW - 1) / d->bW)
-                               : (d->M + kBlockM - 1) / kBlockM;
+                               : (d->M + m_stride - 1) / m_stride;
   p.block_n = d->block_n > 0 ? d->block_n : pick_block_n(d->N, tm_all);
   if (d->block_n <= 0 && d->store_mode == L4P_STORE_HYPER) p.block_n = d->ctCout;  // one tap per tile
   // split-K decision (needs the tile and k-block counts up front)
@@ -108,7 +125,7 @@ extern "C" int l4p_gemm(const l4p_gemm_desc* d, void* stream_) {
     const long long tiles = tm * ((d->N + p.block_n - 1) / p.block_n);
     const long long nkb = d->a_mode == L4P_A_CONV3D ? (long long)d->kT * d->kH * d->kW * (d->cCin / kBlockK) : (d->K + kBlockK - 1) / kBlockK;
     const bool can = d->store_mode == L4P_STORE_ROWMAJOR && d->splitk_ws != nullptr && d->splitk_ws_bytes >= d->M * d->N * 4 &&
-                     d->split_k != 1 && d->block_n <= 0;
+                     d->split_k != 1 && d->block_n <= 0 && !grouped && m_stride == kBlockM;
     if (can) {
       if (d->split_k > 1) {
         split_k = d->split_k;
@@ -138,7 +155,7 @@ extern "C" int l4p_gemm(const l4p_gemm_desc* d, void* stream_) {
   if (d->a_mode == L4P_A_MATRIX) {
     L4P_REQUIRE(d->lda % 8 == 0 && d->lda >= d->K, L4P_ERR_SHAPE, "l4p_gemm: lda=%lld", (long long)d->lda);
     p.num_kb = (int)((d->K + kBlockK - 1) / kBlockK);
-    p.tiles_m = (int)((d->M + kBlockM - 1) / kBlockM);
+    p.tiles_m = (int)tm_all;
     const uint64_t dims[2] = {(uint64_t)d->K, (uint64_t)d->M};
     const uint64_t strides[1] = {(uint64_t)d->lda * 2};
     const uint32_t box[2] = {kBlockK, kBlockM};
@@ -170,7 +187,9 @@ extern "C" int l4p_gemm(const l4p_gemm_desc* d, void* stream_) {
     return host_set_error(L4P_ERR_ARG, "l4p_gemm: a_mode=%d", d->a_mode);
   }
   {
-    const uint64_t dims[2] = {(uint64_t)d->K, (uint64_t)d->N};
+    // grouped: W holds one [grp_b_rows, ldw] block per group of A rows
+    const uint64_t w_rows = grouped ? (uint64_t)((d->M + d->grp_a_rows - 1) / d->grp_a_rows) * (uint64_t)d->grp_b_rows : (uint64_t)d->N;
+    const uint64_t dims[2] = {(uint64_t)d->K, w_rows};
     const uint64_t strides[1] = {(uint64_t)d->ldw * 2};
     const uint32_t box[2] = {kBlockK, (uint32_t)p.block_n};
     rc = t_plan ? L4P_OK : host_make_tmap_16b(&tmB, d->w, 2, dims, strides, box, 128);
@@ -286,6 +305,7 @@ extern "C" int l4p_gemm(const l4p_gemm_desc* d, void* stream_) {
   int use_pair = d->cta_pair;  // 0 = auto, 1 = force, -1 = never
   // the pair kernel halves the B traffic per SM: worth it even when it leaves a few pairs idle (M=2048, N=1408: 64 pair
   // tiles on 74 pairs beat 128 single tiles on 148 SMs by 6 % at K=6144, equal at K=1408)
+  if (grouped || m_stride != kBlockM) use_pair = -1;
   if (use_pair == 0) use_pair = (pair_tiles * 5 >= pairs * 4 && p.block_n >= 64 && p.tiles_m >= 2) ? 1 : -1;
   if (use_pair == 1) {
     L4P_REQUIRE(p.block_n % 32 == 0 || p.block_n % 16 == 0, L4P_ERR_SHAPE, "l4p_gemm(pair): block_n=%d", p.block_n);

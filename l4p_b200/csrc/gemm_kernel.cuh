@@ -110,6 +110,8 @@ struct GemmKParams {
   FastDiv fd_bW, fd_bH;                 // HEAD1X1 finalisation: row in tile -> (tl,hl,wl)
   int split_k;               // >1: work unit = (tile, k-range); partial sums are atomically added to splitk_ws [M,N] fp32
   float* splitk_ws;
+  int m_stride;              // matrix mode: rows between consecutive M tiles = rows stored per tile (128 unless grouped)
+  int grp_a_rows, grp_b_rows;  // grouped weights: tile rows / grp_a_rows = group, its W block starts at row group * grp_b_rows
   long long* prof;           // optional [3][512] clock64 timeline of CTA 0
 };
 
@@ -184,6 +186,14 @@ L4P_DEVICE float4 lds128(uint32_t addr) {
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
   return v;
 }
+// raw 8-byte global load of four 16-bit residual values (explicit state space: behind the null checks of the optional
+// residual pointers the compiler otherwise falls back to generic LD). Not volatile: it may be scheduled freely, the values
+// are only consumed one chunk later.
+L4P_DEVICE uint2 ldg_res16x4(const uint16_t* p) {
+  uint2 v;
+  asm("ld.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+  return v;
+}
 template <bool BF16>
 L4P_DEVICE void add_res16(float4& a, const uint16_t* p) {
   const uint2 u = *reinterpret_cast<const uint2*>(p);
@@ -236,8 +246,8 @@ L4P_DEVICE RowInfo row_info(const GemmKParams& p, const TileCoord& tc, const int
     ri.ok = (ri.ct < p.cT) && (ri.ch < p.cH) && (ri.cw < p.cW) && (ri.cb < p.cB);
     ri.row = (((long long)ri.cb * p.cT + ri.ct) * p.cH + ri.ch) * p.cW + ri.cw;
   } else {
-    ri.row = (long long)tc.m_blk * kBlockM + r;
-    ri.ok = ri.row < p.M;
+    ri.row = (long long)tc.m_blk * p.m_stride + r;
+    ri.ok = ri.row < p.M && r < p.m_stride;
   }
   return ri;
 }
@@ -462,22 +472,38 @@ L4P_DEVICE void epilogue_tile(const GemmKParams& p, const TileCoord& tc, const i
     uint16_t* const out_16_relu = p.out_16_relu;
     const int act_rt = p.act;
 
-    // residual of the 4-column group (n0 + c0 + 4*sub) of phase-B row `it`, summed in fp32
-    auto fetch_res = [&](const int c0, const int it) -> float4 {
+    // residual of the 4-column group (n0 + c0 + 4*sub) of phase-B row `it`. The loads stay RAW in registers (fp32 words /
+    // packed 16-bit pairs) until the chunk that consumes them: converting a 16-bit residual at fetch time puts a dependent
+    // instruction right behind every load and serialises the whole prefetch (measured: res_16 -> out_16 at M = 262144,
+    // N = 1408, K = 704 took 2054 us against 794 us with an fp32 residual of twice the bytes).
+    struct ResRaw { float4 f; uint2 h, h2; };
+    auto fetch_res = [&](const int c0, const int it) -> ResRaw {
       const int colg = c0 + sub * 4;
-      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+      ResRaw a;
+      a.f = make_float4(0.f, 0.f, 0.f, 0.f);
+      a.h = make_uint2(0u, 0u);   // +0.0 in both 16-bit formats
+      a.h2 = make_uint2(0u, 0u);
       if (colg < ncols && ((okm >> it) & 1u)) {
-        if (res32) a = *reinterpret_cast<const float4*>(res_f32 + ((long long)rrow[it] * ld_res + (n0 + colg)));
+        if (res32) a.f = *reinterpret_cast<const float4*>(res_f32 + ((long long)rrow[it] * ld_res + (n0 + colg)));
         if (res16) {
           const long long o = (long long)orow[it] * ld_res + (n0 + colg);
-          if (res_16 != nullptr) add_res16<BF16>(a, res_16 + o);
-          if (res2_16 != nullptr) add_res16<BF16>(a, res2_16 + o);
+          if (res_16 != nullptr) a.h = ldg_res16x4(res_16 + o);
+          if (res2_16 != nullptr) a.h2 = ldg_res16x4(res2_16 + o);
         }
       }
       return a;
     };
+    auto add_res = [&](float4& x, const ResRaw& a) {
+      if (res32) { x.x += a.f.x; x.y += a.f.y; x.z += a.f.z; x.w += a.f.w; }
+      if (res16) {
+        const float2 l0 = unpack2<BF16>(a.h.x), h0 = unpack2<BF16>(a.h.y);
+        const float2 l1 = unpack2<BF16>(a.h2.x), h1 = unpack2<BF16>(a.h2.y);
+        // same association as before: (res_16 + res2_16) is formed first, then added to the accumulator
+        x.x += l0.x + l1.x; x.y += l0.y + l1.y; x.z += h0.x + h1.x; x.w += h0.y + h1.y;
+      }
+    };
 
-    float4 rcur[8];
+    ResRaw rcur[8];
     int c0 = egrp * kEpiChunk;
     if (has_res && c0 < ncols) {  // in flight while the MMA warp finishes the tile
 #pragma unroll
@@ -603,7 +629,7 @@ L4P_DEVICE void epilogue_tile(const GemmKParams& p, const TileCoord& tc, const i
           apply_act2<epi_act(EPI)>(x.x, x.y); apply_act2<epi_act(EPI)>(x.z, x.w);
         }
         if (has_res) {
-          x.x += rcur[it].x; x.y += rcur[it].y; x.z += rcur[it].z; x.w += rcur[it].w;
+          add_res(x, rcur[it]);
           if (more) rcur[it] = fetch_res(cn, it);
         }
         if (cok && ((okm >> it) & 1u)) {
@@ -758,7 +784,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const TileCoord tc = decode_tile(p, tile / p.split_k);
         const int split = tile % p.split_k;
         const int kb0 = (int)((long long)split * p.num_kb / p.split_k), kb1 = (int)((long long)(split + 1) * p.num_kb / p.split_k);
-        const int n0 = tc.n_blk * p.block_n;
+        // grouped weights: this tile's group owns W rows [group * grp_b_rows, ...)
+        const int n0 = tc.n_blk * p.block_n +
+                       (p.grp_a_rows > 0 ? (int)(((long long)tc.m_blk * p.m_stride) / p.grp_a_rows) * p.grp_b_rows : 0);
         // filter-tap walk (cb fastest, then dw, dh, dt) kept as counters: no divisions in the single-thread hot loop
         int cb = 0, dw = -(p.kW / 2), dh = -(p.kH / 2), dt = -(p.kT / 2);
         if (p.a_mode == L4P_A_CONV3D && kb0 > 0) {
@@ -775,7 +803,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           const uint32_t sb = sa + kABytes;
           mbar_expect_tx(full, stage_bytes);
           if (p.a_mode == L4P_A_MATRIX) {
-            tma_load_2d(sa, &tmA, full, kb * kBlockK, tc.m_blk * kBlockM);
+            tma_load_2d(sa, &tmA, full, kb * kBlockK, tc.m_blk * p.m_stride);
           } else {
             tma_load_5d(sa, &tmA, full, cb * kBlockK, tc.w0 + dw, tc.h0 + dh, tc.t0 + dt, tc.b);
             if (++cb == p.cblocks) {

@@ -417,6 +417,113 @@ layernorm16_kernel(const uint16_t* __restrict__ x, const float* __restrict__ gam
   }
 }
 
+// Long rows (the 1408-channel per-query token stream of the two-way layers, 16-bit in and out): one warp owns R rows at a
+// time and keeps them as RAW packed words (CH x uint4 per lane and row instead of 8 x CH floats), so all R x CH 16-byte
+// loads of a lane are in flight at once: 11 KB per warp, ~135 KB per SM (R = 4, 12 warps per SM at <= 168 registers: with 128 registers the raw rows spill). The generic kernel above holds one unpacked row per
+// warp (2.8 KB in flight) and reached 3.1 TB/s on [262144, 1408]; the fp32-input LayerNorm of layernorm.cu, with twice the
+// bytes per row in flight, 6.2 TB/s.
+template <bool BF16, int CH, int R>  // cols <= 32 * 8 * CH
+__global__ void __launch_bounds__(128, 3)
+layernorm16_rows_kernel(const uint16_t* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                        uint16_t* __restrict__ y, long long rows, int cols, float eps, int gelu) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row0 = ((long long)blockIdx.x * (blockDim.x >> 5) + warp) * R;
+  const int nch = cols >> 3;
+  uint4 raw[R][CH];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const bool ok = row0 + r < rows;
+    const uint4* xr = reinterpret_cast<const uint4*>(x + (ok ? row0 + r : 0) * cols);
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+      const int j = lane + i * 32;
+      raw[r][i] = (ok && j < nch) ? xr[j] : make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+  float mean[R], rstd[R];
+  {
+    float s[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      float a = 0.f;
+#pragma unroll
+      for (int i = 0; i < CH; ++i) {  // chunks beyond the row are zero words: they add nothing
+        const uint32_t w[4] = {raw[r][i].x, raw[r][i].y, raw[r][i].z, raw[r][i].w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) { const float2 f = unpack2<BF16>(w[t]); a += f.x + f.y; }
+      }
+      s[r] = a;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int r = 0; r < R; ++r) s[r] += __shfl_xor_sync(0xffffffffu, s[r], o);
+#pragma unroll
+    for (int r = 0; r < R; ++r) mean[r] = s[r] / (float)cols;
+    // launder the raw words: without this the compiler keeps the UNPACKED values of the first pass alive for the next two
+    // (common-subexpression elimination), i.e. 8 x CH x R floats, and spills
+#define L4P_LN16_LAUNDER()                                                                                           \
+    _Pragma("unroll") for (int r = 0; r < R; ++r) _Pragma("unroll") for (int i = 0; i < CH; ++i)                       \
+        asm volatile("" : "+r"(raw[r][i].x), "+r"(raw[r][i].y), "+r"(raw[r][i].z), "+r"(raw[r][i].w))
+    L4P_LN16_LAUNDER();
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      float a = 0.f;
+#pragma unroll
+      for (int i = 0; i < CH; ++i) {
+        if (lane + i * 32 < nch) {
+          const uint32_t w[4] = {raw[r][i].x, raw[r][i].y, raw[r][i].z, raw[r][i].w};
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const float2 f = unpack2<BF16>(w[t]);
+            const float d0 = f.x - mean[r], d1 = f.y - mean[r];
+            a += d0 * d0 + d1 * d1;
+          }
+        }
+      }
+      s[r] = a;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int r = 0; r < R; ++r) s[r] += __shfl_xor_sync(0xffffffffu, s[r], o);
+#pragma unroll
+    for (int r = 0; r < R; ++r) rstd[r] = rsqrtf(s[r] / (float)cols + eps);
+    L4P_LN16_LAUNDER();
+#undef L4P_LN16_LAUNDER
+  }
+#pragma unroll
+  for (int i = 0; i < CH; ++i) {
+    const int j = lane + i * 32;
+    asm volatile("" ::: "memory");  // keep the gamma / beta loads of later chunks from being hoisted (they would spill the rows)
+    if (j < nch) {
+      const float4 g0 = reinterpret_cast<const float4*>(gamma)[2 * j], g1 = reinterpret_cast<const float4*>(gamma)[2 * j + 1];
+      const float4 b0 = reinterpret_cast<const float4*>(beta)[2 * j], b1 = reinterpret_cast<const float4*>(beta)[2 * j + 1];
+      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        if (row0 + r < rows) {
+          const uint32_t w[4] = {raw[r][i].x, raw[r][i].y, raw[r][i].z, raw[r][i].w};
+          float o[8];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const float2 f = unpack2<BF16>(w[t]);
+            o[2 * t] = (f.x - mean[r]) * rstd[r] * gg[2 * t] + bb[2 * t];
+            o[2 * t + 1] = (f.y - mean[r]) * rstd[r] * gg[2 * t + 1] + bb[2 * t + 1];
+          }
+          if (gelu) {
+#pragma unroll
+            for (int t = 0; t < 8; t += 2) gelu2(o[t], o[t + 1]);
+          }
+          reinterpret_cast<uint4*>(y + (row0 + r) * cols)[j] = make_uint4(pack2<BF16>(o[0], o[1]), pack2<BF16>(o[2], o[3]),
+                                                                          pack2<BF16>(o[4], o[5]), pack2<BF16>(o[6], o[7]));
+        }
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // masks fp32 [G, 3, T, h, w] (low-res logits) -> traj [G,2,T], vis [G,1,T], depth [G,1,T]. One block per (g,t).
 // Spatial bilinear upsample to (H,W) with align_corners=False; T is not resampled (T_in == T_out).
@@ -815,6 +922,10 @@ extern "C" int l4p_layernorm16(const void* x16, const float* gamma, const float*
     const unsigned grid = (unsigned)((rows + 31) / 32);
     if (bf16) layernorm16_kernel<true, 8, kLn16Iters><<<grid, 256, 0, st>>>(x, gamma, beta, y, rows, cols, eps, gelu);
     else layernorm16_kernel<false, 8, kLn16Iters><<<grid, 256, 0, st>>>(x, gamma, beta, y, rows, cols, eps, gelu);
+  } else if (cols <= 32 * 8 * 6 && rows >= 4096) {  // the 1408-channel token stream: 4 rows per warp kept as raw words
+    const unsigned grid = (unsigned)((rows + 15) / 16);
+    if (bf16) layernorm16_rows_kernel<true, 6, 4><<<grid, 128, 0, st>>>(x, gamma, beta, y, rows, cols, eps, gelu);
+    else layernorm16_rows_kernel<false, 6, 4><<<grid, 128, 0, st>>>(x, gamma, beta, y, rows, cols, eps, gelu);
   } else {
     const unsigned grid = (unsigned)((rows + 7) / 8);
     if (bf16) layernorm16_kernel<true, 32, kLn16Iters><<<grid, 256, 0, st>>>(x, gamma, beta, y, rows, cols, eps, gelu);

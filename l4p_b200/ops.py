@@ -129,14 +129,25 @@ def _epilogue(d: _l.GemmDesc, *, bias=None, act=_l.ACT_NONE, res_f32=None, res_1
 
 def linear(a: torch.Tensor, w: torch.Tensor, *, bias=None, act=_l.ACT_NONE, res_f32=None, res_16=None,
            out_f32=None, out_16=None, out_16_relu=None, block_n: int = 0, res_row_mod: int = 0,
-           cta_pair: int = 0, prof: Optional[torch.Tensor] = None) -> None:
-    """out[M,N] = act(a[M,K] @ w[N,K]^T + bias) (+ residual). Replaces F.linear/addmm call sites."""
+           cta_pair: int = 0, prof: Optional[torch.Tensor] = None, group_rows: int = 0, n_out: int = 0) -> None:
+    """out[M,N] = act(a[M,K] @ w[N,K]^T + bias) (+ residual). Replaces F.linear/addmm call sites.
+
+    group_rows > 0: grouped weights. Rows [g*group_rows, (g+1)*group_rows) of `a` multiply their own block
+    w[g*Nw:(g+1)*Nw] of a [groups*Nw, K] weight stack (Nw = w.shape[0] // groups); the output has n_out (default Nw) columns."""
     d = _base_desc(a, w)
     K = a.shape[-1]
     M = a.numel() // K
     N = w.shape[0]
     if w.shape[1] != K:
         raise _l.L4PError(f"linear: K mismatch {w.shape} vs {a.shape}")
+    if group_rows > 0:
+        groups = -(-M // group_rows)
+        if M % group_rows or N % groups:
+            raise _l.L4PError(f"linear(grouped): M={M} / group_rows={group_rows}, w rows {N} / groups {groups}")
+        d.grp_a_rows, d.grp_b_rows = group_rows, N // groups
+        d.m_stride = group_rows if group_rows < 128 else 0
+        N = n_out or N // groups
+        d.split_k = 1
     d.M, d.N, d.K = M, N, K
     d.lda, d.ldw = K, K
     d.a_mode = _l.A_MATRIX

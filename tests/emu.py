@@ -83,12 +83,19 @@ def layernorm(x, gamma, beta, eps, out16=None, out32=None) -> None:
 
 
 def linear(a, w, *, bias=None, act=ACT_NONE, res_f32=None, res_16=None, out_f32=None, out_16=None, out_16_relu=None,
-           block_n=0, res_row_mod=0, cta_pair=0, prof=None) -> None:
+           block_n=0, res_row_mod=0, cta_pair=0, prof=None, group_rows=0, n_out=0) -> None:
     _note("linear")
     assert _is16(a) and a.dtype == w.dtype and a.is_contiguous() and w.is_contiguous()
     K = a.shape[-1]
     assert w.shape[1] == K
-    acc = a.reshape(-1, K).float() @ w.float().t()
+    if group_rows > 0:   # grouped weights: every group of rows multiplies its own block of the weight stack
+        M = a.numel() // K
+        groups = M // group_rows
+        nw = w.shape[0] // groups
+        acc = torch.bmm(a.reshape(groups, group_rows, K).float(), w.reshape(groups, nw, K).float().transpose(1, 2))
+        acc = acc[..., :(n_out or nw)].reshape(M, -1)
+    else:
+        acc = a.reshape(-1, K).float() @ w.float().t()
     acc = _epilogue(acc, bias=bias, act=act, res_f32=res_f32, res_16=res_16, res_row_mod=res_row_mod)
     _store(acc, out_f32, out_16, out_16_relu)
 

@@ -350,3 +350,23 @@ def test_linear_16bit_residual_stream(dtype, M):
     ops.layernorm16(out2, g, be, 1e-5, y)
     torch.cuda.synchronize()
     _close(y, F.layer_norm(out2.float(), (N,), g, be, 1e-5), tol)
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("rows,gelu", [(4101, False), (4096 + 16 * 7 + 3, True)])
+def test_layernorm16_long_rows_ragged(dtype, rows, gelu):
+    """The 4-rows-per-warp 16-bit LayerNorm (1408-channel token stream, rows >= 4096) with a row count that is not a multiple
+    of the 16 rows of a block: the tail rows are written, nothing beyond them is."""
+    ops = _ops()
+    N = 1408
+    x = _rand((rows, N), dtype, 21, 1.7) + 0.3
+    g = 1.0 + 0.1 * _rand((N,), torch.float32, 22)
+    be = 0.02 * _rand((N,), torch.float32, 23)
+    y = torch.full((rows + 16, N), 7.0, device="cuda", dtype=dtype)
+    ops.layernorm16(x, g, be, 1e-5, y[:rows], gelu=gelu)
+    torch.cuda.synchronize()
+    ref = F.layer_norm(x.float(), (N,), g, be, 1e-5)
+    if gelu:
+        ref = F.gelu(ref)
+    _close(y[:rows], ref, 2 ** -7 if dtype == torch.bfloat16 else 2 ** -10)
+    assert bool((y[rows:] == 7.0).all())
