@@ -172,6 +172,19 @@ int l4p_image_attention_tc(const void* q16, const float* k, const float* v, void
  * (sam/mask_decoder.py:58-66,145-157). */
 int l4p_layernorm16(const void* x16, const float* gamma, const float* beta, void* y16, int64_t rows, int cols,
                     float eps, int gelu, int bf16, void* stream);
+/* Token -> video-token attention with the projections moved to the token side (sam/transformer.py:223-245, see
+ * csrc/track_t2i.cu): score = x . (W_k^T q) + q . (W_k pe + b_k), out = W_v (sum_n p_n x_n) + b_v.
+ * l4p_head_expand: q fp32 [G*nt, heads*hd] -> out16 [G*heads*nt, heads*hd], row (g, h, t) = q[g,t] * scale restricted to the
+ * columns of head h (zero elsewhere): the block-diagonal operand that turns per-head dot products into plain GEMMs. */
+int l4p_head_expand(const float* q, void* out16, int64_t G, int nt, int heads, int hd, float scale, int bf16, void* stream);
+/* Inverse bookkeeping: out fp32 [G*nt, heads*hd], out[(g,t), h*hd + d] = z[(g,h,t), h*hd + d] for z fp32 [G*heads*nt, heads*hd]. */
+int l4p_head_diag_gather(const float* z, float* out, int64_t G, int nt, int heads, int hd, void* stream);
+/* Row softmax of fp32 scores [rows, n] (already scaled) -> 16-bit probabilities; n multiple of 4, <= 2048. */
+int l4p_row_softmax16(const float* s, void* p16, int64_t rows, int n, int bf16, void* stream);
+/* y16[g] (J x C) = p16[g] (J x n) * x16[g] (n x C) for G groups: p16 [G*J, n], x16 [G*n, C], y16 [G*J, C]; fp32 accumulation,
+ * J <= 48, n multiple of 64, C multiple of 16. */
+int l4p_token_weighted_sum(const void* p16, const void* x16, void* y16, int64_t G, int J, int n, int C, int bf16, void* stream);
+
 /* masks fp32 [G,nch<=3,T,h,w] low-res logits -> bilinear (align_corners=False) to (H,W) fused with the
  * read-outs: traj[G,2,T] = soft-argmax of channel 0 at pixel centres (+0.5), vis[G,1,T] = mean of channel 1,
  * depth[G,1,T] = exp(mean of channel 2) (sparse_heads.py:140-160,574-589,645-647). */

@@ -171,6 +171,9 @@ class VideoMAETrack2DSamHead(nn.Module):
     # per-query video-token stream between the two-way layers: 16 bit (True, default: 5.2 instead of 10.4 GB of HBM traffic per
     # 128-query window, -0.63 ms, tracks equal to the fp32 stream within 6e-3 px) or fp32 (False); L4P_TRACK_STREAM16=0/1 overrides
     token_stream16 = __import__("os").environ.get("L4P_TRACK_STREAM16", "1") == "1"
+    # token -> video-token attention with the K / V projections folded onto the 6-token side (csrc/track_t2i.cu);
+    # L4P_TRACK_FOLD_T2I=0 restores the reference order (project all 2048 tokens of every query)
+    fold_t2i = __import__("os").environ.get("L4P_TRACK_FOLD_T2I", "1") == "1"
 
     def __init__(self, task_name: str = "track_2d", prompt_embed_dim: int = 1408,
                  image_size: Tuple[int, int, int] = (16, 224, 224), patch_size: Tuple[int, int, int] = (2, 14, 14),
@@ -239,6 +242,10 @@ class VideoMAETrack2DSamHead(nn.Module):
             # "+PE" folded: W(x + pe) + b = W x + (W pe + b); the table is added by the GEMM epilogue (row % P)
             if image_k:
                 d["k_pe"] = (pe @ a.k_proj.weight.detach().to(device).float().t() + f(a.k_proj.bias)).contiguous()
+                # operands of the folded token -> video-token attention (csrc/track_t2i.cu): W_k^T as a [C, inner] weight
+                # (Q' = Q_blockdiag W_k) and the 16-bit copy of the positional / bias table (scores' position term)
+                d["k_wT"] = w16(a.k_proj.weight.detach().t())
+                d["k_pe16"] = d["k_pe"].to(dt).contiguous()
             if image_q:
                 d["q_pe"] = (pe @ a.q_proj.weight.detach().to(device).float().t() + f(a.q_proj.bias)).contiguous()
             return d
@@ -334,7 +341,34 @@ class VideoMAETrack2DSamHead(nn.Module):
                 ops.linear(x16, l["w"], res_f32=table, res_row_mod=Pn, out_16=y)
             return y
 
+        def t2i_folded(a, queries, keys16):
+            """Per-query video tokens (keys16 [G*P, C]): K / V are never formed. score = x . (W_k^T q) + q . (W_k pe + b_k),
+            out = W_v (sum_n p_n x_n) + b_v (csrc/track_t2i.cu); 48 = heads x tokens score rows per query."""
+            H, hd = a["heads"], a["hd"]
+            D, J = H * hd, H * nt
+            q = self._lin32((queries + qpe).view(-1, C), a["q"])                       # [G*nt, D] fp32
+            qb = torch.empty(G * J, D, device=dev, dtype=dt)
+            ops.head_expand(q, qb, G, nt, H, hd, 1.0 / math.sqrt(hd))                  # block-diagonal, pre-scaled
+            qp = torch.empty(G * J, C, device=dev, dtype=dt)
+            ops.linear(qb, a["k_wT"], out_16=qp)                                       # Q' = W_k[h]^T q[g,t,h]
+            sc = torch.empty(G * J, Pn, device=dev, dtype=torch.float32)
+            ops.linear(qb, a["k_pe16"], out_f32=sc)                                    # q . (W_k pe_n + b_k)
+            ops.linear(qp, keys16, res_f32=sc, out_f32=sc, group_rows=J)               # + Q'_g X_g^T (grouped weights)
+            pr = torch.empty(G * J, Pn, device=dev, dtype=dt)
+            ops.row_softmax16(sc, pr)
+            y = torch.empty(G * J, C, device=dev, dtype=dt)
+            ops.token_weighted_sum(pr, keys16, y, G, J)                                # sum_n p_n x_n
+            z = torch.empty(G * J, D, device=dev, dtype=torch.float32)
+            ops.linear(y, a["v"]["w"], bias=a["v"]["b"], out_f32=z)
+            o = torch.empty(G * nt, D, device=dev, dtype=torch.float32)
+            ops.head_diag_gather(z, o, G, nt, H, hd)
+            return self._lin32(o, a["o"], res32=queries.view(-1, C).contiguous()).view(G, nt, C)
+
         def t2i(a, queries, keys16, shared_now):
+            # kernel limits of the folded path (l4p_token_weighted_sum / l4p_row_softmax16); other shapes keep the reference order
+            fits = a["heads"] * nt <= 48 and Pn % 64 == 0 and Pn <= 2048
+            if self.fold_t2i and not shared_now and (fits or not keys16.is_cuda):
+                return t2i_folded(a, queries, keys16)
             q = self._lin32((queries + qpe).view(-1, C), a["q"]).view(G, nt, -1)
             k16 = img_proj(keys16, a["k"], a["k_pe"])
             v16 = img_proj(keys16, a["v"], None)

@@ -418,6 +418,52 @@ def layernorm16(x16: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps:
     _count()
 
 
+def head_expand(q: torch.Tensor, out16: torch.Tensor, G: int, nt: int, heads: int, hd: int, scale: float) -> None:
+    """q fp32 [G*nt, heads*hd] -> out16 [G*heads*nt, heads*hd]: row (g,h,t) = scale * q[g,t] on head h's columns, 0 elsewhere."""
+    _dev_init(q)
+    _chk(q, "q", torch.float32); _chk(out16, "out16", sixteen=True)
+    if q.numel() != G * nt * heads * hd or out16.numel() != G * heads * nt * heads * hd:
+        raise _l.L4PError(f"head_expand: shapes {tuple(q.shape)} / {tuple(out16.shape)} vs G={G} nt={nt} heads={heads} hd={hd}")
+    _l.check(_l.load().l4p_head_expand(q.data_ptr(), out16.data_ptr(), G, nt, heads, hd, float(scale),
+                                       1 if out16.dtype == torch.bfloat16 else 0, _stream()), "l4p_head_expand")
+    _count()
+
+
+def head_diag_gather(z: torch.Tensor, out: torch.Tensor, G: int, nt: int, heads: int, hd: int) -> None:
+    """z fp32 [G*heads*nt, heads*hd] -> out fp32 [G*nt, heads*hd]: out[(g,t), h*hd+d] = z[(g,h,t), h*hd+d]."""
+    _dev_init(z)
+    _chk(z, "z", torch.float32); _chk(out, "out", torch.float32)
+    if out.numel() != G * nt * heads * hd or z.numel() != G * heads * nt * heads * hd:
+        raise _l.L4PError(f"head_diag_gather: shapes {tuple(z.shape)} / {tuple(out.shape)}")
+    _l.check(_l.load().l4p_head_diag_gather(z.data_ptr(), out.data_ptr(), G, nt, heads, hd, _stream()), "l4p_head_diag_gather")
+    _count()
+
+
+def row_softmax16(s: torch.Tensor, p16: torch.Tensor) -> None:
+    """fp32 scores [rows, n] (already scaled) -> 16-bit probabilities."""
+    _dev_init(s)
+    _chk(s, "s", torch.float32); _chk(p16, "p16", sixteen=True)
+    n = s.shape[-1]
+    if p16.shape != s.shape:
+        raise _l.L4PError(f"row_softmax16: {tuple(s.shape)} vs {tuple(p16.shape)}")
+    _l.check(_l.load().l4p_row_softmax16(s.data_ptr(), p16.data_ptr(), s.numel() // n, n,
+                                         1 if p16.dtype == torch.bfloat16 else 0, _stream()), "l4p_row_softmax16")
+    _count()
+
+
+def token_weighted_sum(p16: torch.Tensor, x16: torch.Tensor, y16: torch.Tensor, G: int, J: int) -> None:
+    """y16[g] = p16[g] @ x16[g]: p16 [G*J, n], x16 [G*n, C], y16 [G*J, C] (fp32 accumulation)."""
+    _dev_init(p16)
+    for nme, t in (("p16", p16), ("x16", x16), ("y16", y16)):
+        _chk(t, nme, sixteen=True)
+    n, Cc = p16.shape[-1], x16.shape[-1]
+    if p16.numel() != G * J * n or x16.numel() != G * n * Cc or y16.numel() != G * J * Cc or not (p16.dtype == x16.dtype == y16.dtype):
+        raise _l.L4PError(f"token_weighted_sum: shapes {tuple(p16.shape)} {tuple(x16.shape)} {tuple(y16.shape)} G={G} J={J}")
+    _l.check(_l.load().l4p_token_weighted_sum(p16.data_ptr(), x16.data_ptr(), y16.data_ptr(), G, J, n, Cc,
+                                              1 if p16.dtype == torch.bfloat16 else 0, _stream()), "l4p_token_weighted_sum")
+    _count()
+
+
 def track_readout(masks: torch.Tensor, image_hw: Tuple[int, int]):
     """K15: masks fp32 [G,nch,T,h,w] -> (traj [G,2,T], vis [G,1,T] | None, depth [G,1,T] | None)."""
     _dev_init(masks)

@@ -240,6 +240,34 @@ def layernorm16(x16, gamma, beta, eps, y16, gelu=False) -> None:
     y16.copy_(y.to(y16.dtype))
 
 
+def head_expand(q, out16, G, nt, heads, hd, scale) -> None:
+    _note("head_expand")
+    D = heads * hd
+    qq = (q.reshape(G, 1, nt, heads, hd).float() * scale).expand(G, heads, nt, heads, hd)
+    mask = torch.eye(heads, device=q.device).reshape(1, heads, 1, heads, 1)
+    out16.view(G, heads, nt, heads, hd).copy_((qq * mask).to(out16.dtype))
+
+
+def head_diag_gather(z, out, G, nt, heads, hd) -> None:
+    _note("head_diag_gather")
+    zz = z.reshape(G, heads, nt, heads, hd)
+    idx = torch.arange(heads, device=z.device)
+    out.view(G, nt, heads, hd).copy_(zz[:, idx, :, idx, :].permute(1, 2, 0, 3))   # [heads,G,nt,hd] -> [G,nt,heads,hd]
+
+
+def row_softmax16(s, p16) -> None:
+    _note("row_softmax16")
+    assert s.dtype == torch.float32 and _is16(p16)
+    p16.copy_(torch.softmax(s, dim=-1).to(p16.dtype))
+
+
+def token_weighted_sum(p16, x16, y16, G, J) -> None:
+    _note("token_weighted_sum")
+    n, C = p16.shape[-1], x16.shape[-1]
+    y = torch.bmm(p16.reshape(G, J, n).float(), x16.reshape(G, n, C).float())
+    y16.view(G, J, C).copy_(y.to(y16.dtype))
+
+
 def track_readout(masks, image_hw):
     """sparse_heads.py:149-160 read-outs of the trilinearly upsampled mask logits (align_corners=False)."""
     _note("track_readout")
@@ -319,7 +347,7 @@ def install(monkeypatch) -> None:
     CALLS.clear()
     for name in ("_dev_init", "layernorm", "linear", "linear_qkv", "conv3d", "conv_transpose3d", "conv_transpose3d_hyper",
                  "attention", "patchify", "cast16", "upsample3d", "im2col3", "token_attention", "image_attention",
-                 "layernorm16", "track_readout"):
+                 "layernorm16", "track_readout", "head_expand", "head_diag_gather", "row_softmax16", "token_weighted_sum"):
         assert hasattr(ops, name), f"l4p_b200.ops.{name} no longer exists: update tests/emu.py"
         monkeypatch.setattr(ops, name, globals()[name])
     monkeypatch.setattr(geometry_utils, "_pose_call", _pose_call)

@@ -1,5 +1,7 @@
-"""A/B of the track head's token stream (fp32 vs 16 bit, L4P_TRACK_STREAM16) at the bench size: time of one 128-query window
-and the difference of the two arms' tracks (each arm in its own subprocess writes its outputs, the parent compares)."""
+"""A/B of a track-head switch at the bench size (default L4P_TRACK_FOLD_T2I: reference-order K / V projections vs the folded
+token -> video-token attention; `python tools/track_ab.py L4P_TRACK_STREAM16` for the fp32 vs 16-bit token stream): time of
+one 128-query window and the difference of the two arms' tracks (each arm in its own subprocess writes its outputs, the
+parent compares)."""
 import os
 import subprocess
 import sys
@@ -7,10 +9,11 @@ import tempfile
 
 if os.environ.get("_TRK_ARM") is None:
     d = tempfile.mkdtemp()
+    var = sys.argv[1] if len(sys.argv) > 1 else "L4P_TRACK_FOLD_T2I"
     for arm in ("0", "1"):
-        r = subprocess.run([sys.executable, __file__], env=dict(os.environ, _TRK_ARM=arm, L4P_TRACK_STREAM16=arm, _TRK_OUT=d),
+        r = subprocess.run([sys.executable, __file__], env=dict(os.environ, _TRK_ARM=arm, _TRK_OUT=d, **{var: arm}),
                            capture_output=True, text=True, timeout=280)
-        print(f"--- L4P_TRACK_STREAM16={arm} (exit {r.returncode})\n{r.stdout}{r.stderr[-1500:]}")
+        print(f"--- {var}={arm} (exit {r.returncode})\n{r.stdout}{r.stderr[-1500:]}")
     import torch
 
     a, b = torch.load(os.path.join(d, "0.pt")), torch.load(os.path.join(d, "1.pt"))
