@@ -181,6 +181,9 @@ int l4p_head_expand(const float* q, void* out16, int64_t G, int nt, int heads, i
 int l4p_head_diag_gather(const float* z, float* out, int64_t G, int nt, int heads, int hd, void* stream);
 /* Row softmax of fp32 scores [rows, n] (already scaled) -> 16-bit probabilities; n multiple of 4, <= 2048. */
 int l4p_row_softmax16(const float* s, void* p16, int64_t rows, int n, int bf16, void* stream);
+/* Video-token -> token attention, folded form: s fp32 [G*heads*nt, n] (transposed scores, row (g,h,t)) -> softmax over the nt
+ * tokens of each head -> p16 [G*n, heads*nt] (the A operand of the per-query K = heads*nt output GEMM); nt <= 8. */
+int l4p_group_softmax_t16(const float* s, void* p16, int64_t G, int heads, int nt, int n, int bf16, void* stream);
 /* y16[g] (J x C) = p16[g] (J x n) * x16[g] (n x C) for G groups: p16 [G*J, n], x16 [G*n, C], y16 [G*J, C]; fp32 accumulation,
  * J <= 48, n multiple of 64, C multiple of 16. */
 int l4p_token_weighted_sum(const void* p16, const void* x16, void* y16, int64_t G, int J, int n, int C, int bf16, void* stream);

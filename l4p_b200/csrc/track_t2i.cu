@@ -102,6 +102,49 @@ row_softmax16_kernel(const float* __restrict__ s, uint16_t* __restrict__ p, long
   }
 }
 
+// Video-token -> token attention, folded form: scores arrive TRANSPOSED, s fp32 [G*heads*nt, n] (row (g,h,t), column = video
+// token), the softmax runs over the nt tokens of each head, and the probabilities leave as the A operand of the per-query
+// K = heads*nt output GEMM: p16 [G*n, heads*nt]. One thread per (g, video token): its reads are coalesced across the
+// warp (consecutive tokens of one score row), its heads*nt probabilities are contiguous in the output.
+template <bool BF16, int NT>
+__global__ void __launch_bounds__(256)
+group_softmax_t16_kernel(const float* __restrict__ s, uint16_t* __restrict__ p, long long total, int n, int heads) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int J = heads * NT;
+  const float L2E = 1.4426950408889634f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long g = i / n;
+    const int tok = (int)(i - g * n);
+    const float* src = s + (g * J) * n + tok;
+    uint16_t* dst = p + i * J;
+    for (int h = 0; h < heads; ++h) {
+      float v[NT];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+        v[t] = src[(long long)(h * NT + t) * n];
+        mx = fmaxf(mx, v[t]);
+      }
+      float sum = 0.f;
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+        v[t] = ex2((v[t] - mx) * L2E);
+        sum += v[t];
+      }
+      const float inv = 1.0f / sum;
+      if constexpr (NT % 2 == 0) {   // heads * NT * 2 bytes per output row: 4-byte aligned pairs
+#pragma unroll
+        for (int t = 0; t < NT; t += 2)
+          *reinterpret_cast<uint32_t*>(dst + h * NT + t) = pack2<BF16>(v[t] * inv, v[t + 1] * inv);
+      } else {
+#pragma unroll
+        for (int t = 0; t < NT; ++t) dst[h * NT + t] = pack1<BF16>(v[t] * inv);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // Y[g] (J x C) = P[g] (J x n) X[g] (n x C): one CTA per (query g, 128-channel slice). X tiles of 64 tokens x 128 channels
 // (two 128-byte-swizzled TMA boxes) and the matching 48 x 64 tile of P stream through a 4-deep mbarrier ring; 8 consumer
@@ -301,5 +344,23 @@ extern "C" int l4p_token_weighted_sum(const void* p16, const void* x16, void* y1
   L4P_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kWsSmem));
   L4P_CHECK_CUDA(launch_pdl(kfn, dim3((unsigned)(G * nslices)), dim3(kWsThreads), (size_t)kWsSmem, (cudaStream_t)stream, tmP, tmX,
                             (uint16_t*)y16, J, n, C, nslices));
+  return L4P_OK;
+}
+
+extern "C" int l4p_group_softmax_t16(const float* s, void* p16, int64_t G, int heads, int nt, int n, int bf16, void* stream) {
+  L4P_REQUIRE(s && p16, L4P_ERR_ARG, "l4p_group_softmax_t16: null pointer");
+  L4P_REQUIRE(G >= 0 && heads > 0 && n > 0 && nt >= 1 && nt <= 8, L4P_ERR_SHAPE, "l4p_group_softmax_t16: G=%lld heads=%d nt=%d n=%d (nt <= 8)",
+              (long long)G, heads, nt, n);
+  if (G == 0) return L4P_OK;
+  const long long total = (long long)G * n;
+  long long grid = (total + 255) / 256;
+  if (grid > 32ll * host_num_sms()) grid = 32ll * host_num_sms();
+  typedef void (*KFn)(const float*, uint16_t*, long long, int, int);
+  static const KFn table[2][8] = {
+      {group_softmax_t16_kernel<false, 1>, group_softmax_t16_kernel<false, 2>, group_softmax_t16_kernel<false, 3>, group_softmax_t16_kernel<false, 4>,
+       group_softmax_t16_kernel<false, 5>, group_softmax_t16_kernel<false, 6>, group_softmax_t16_kernel<false, 7>, group_softmax_t16_kernel<false, 8>},
+      {group_softmax_t16_kernel<true, 1>, group_softmax_t16_kernel<true, 2>, group_softmax_t16_kernel<true, 3>, group_softmax_t16_kernel<true, 4>,
+       group_softmax_t16_kernel<true, 5>, group_softmax_t16_kernel<true, 6>, group_softmax_t16_kernel<true, 7>, group_softmax_t16_kernel<true, 8>}};
+  L4P_CHECK_CUDA(launch_pdl(table[bf16 ? 1 : 0][nt - 1], dim3((unsigned)grid), dim3(256), 0, (cudaStream_t)stream, s, (uint16_t*)p16, total, n, heads));
   return L4P_OK;
 }

@@ -174,6 +174,8 @@ class VideoMAETrack2DSamHead(nn.Module):
     # token -> video-token attention with the K / V projections folded onto the 6-token side (csrc/track_t2i.cu);
     # L4P_TRACK_FOLD_T2I=0 restores the reference order (project all 2048 tokens of every query)
     fold_t2i = __import__("os").environ.get("L4P_TRACK_FOLD_T2I", "1") == "1"
+    # the same for the video-token -> token attention (Q projection + 6-key attention + output projection of the token stream)
+    fold_i2t = __import__("os").environ.get("L4P_TRACK_FOLD_I2T", "1") == "1"
 
     def __init__(self, task_name: str = "track_2d", prompt_embed_dim: int = 1408,
                  image_size: Tuple[int, int, int] = (16, 224, 224), patch_size: Tuple[int, int, int] = (2, 14, 14),
@@ -248,6 +250,8 @@ class VideoMAETrack2DSamHead(nn.Module):
                 d["k_pe16"] = d["k_pe"].to(dt).contiguous()
             if image_q:
                 d["q_pe"] = (pe @ a.q_proj.weight.detach().to(device).float().t() + f(a.q_proj.bias)).contiguous()
+                d["q_wT"] = w16(a.q_proj.weight.detach().t())     # folded video-token -> token attention (see i2t_folded)
+                d["q_pe16"] = d["q_pe"].to(dt).contiguous()
             return d
 
         tr = self.mask_decoder.transformer
@@ -396,6 +400,43 @@ class VideoMAETrack2DSamHead(nn.Module):
             queries = self._ln32(m.view(G, nt, C), w["n3"])
             # (4) video tokens attend to the prompt tokens -> per-query video tokens
             a = w["i2t"]
+            fits = a["heads"] * nt <= 48 and a["heads"] * nt % 8 == 0 and Pn <= 2048
+            if self.fold_i2t and self.token_stream16 and (fits or not keys16.is_cuda):
+                # Folded form (csrc/track_t2i.cu): the Q projection of the 2048 video tokens of every query, the 6-key attention
+                # and the output projection collapse into   S^T = (W_q^T k) X^T + k . (W_q pe + b_q)   (48 score rows per query),
+                # a softmax over the 6 tokens of each head, and   new = P (W_o v) + b_o + residual   with a K = 48 GEMM per
+                # query: the 704-wide Q and attention-output copies of the token stream are never formed.
+                H, hd = a["heads"], a["hd"]
+                D, J = H * hd, H * nt
+                kk = self._lin32((queries + qpe).view(-1, C), a["k"])                   # [G*nt, D] fp32
+                vv = self._lin32(queries.view(-1, C), a["v"])
+                kb = torch.empty(G * J, D, device=dev, dtype=dt)
+                ops.head_expand(kk, kb, G, nt, H, hd, 1.0 / math.sqrt(hd))
+                kp = torch.empty(G * J, C, device=dev, dtype=dt)
+                ops.linear(kb, a["q_wT"], out_16=kp)                                    # K' = W_q[h]^T k[g,t,h]
+                sc = torch.empty(G * J, Pn, device=dev, dtype=torch.float32)
+                ops.linear(kb, a["q_pe16"], out_f32=sc)                                 # k . (W_q pe_n + b_q)
+                if shared:
+                    ops.linear(kp, keys16, res_f32=sc, out_f32=sc)                      # all queries still share the video tokens
+                else:
+                    ops.linear(kp, keys16, res_f32=sc, out_f32=sc, group_rows=J)
+                p2 = torch.empty(G * Pn, J, device=dev, dtype=dt)
+                ops.group_softmax_t16(sc, p2, G, H, nt)                                 # softmax over the tokens of a head, [G*P, J]
+                vb = torch.empty(G * J, D, device=dev, dtype=dt)
+                ops.head_expand(vv, vb, G, nt, H, hd, 1.0)
+                vp = torch.empty(G * J, C, device=dev, dtype=dt)
+                ops.linear(vb, a["o"]["w"], out_16=vp)                                  # V' = W_o[:, head h] v[g,t,h]
+                vpt = vp.view(G, J, C).transpose(1, 2).contiguous().view(G * C, J)      # per-query [C, J] weight block
+                new16 = torch.empty(G * Pn, C, device=dev, dtype=dt)
+                if keys32 is not None:
+                    ops.linear(p2, vpt, bias=a["o"]["b"], res_f32=keys32, res_row_mod=Pn if shared else 0, out_16=new16, group_rows=Pn)
+                else:
+                    ops.linear(p2, vpt, bias=a["o"]["b"], res_16=keys16, out_16=new16, group_rows=Pn)
+                keys16 = torch.empty(G * Pn, C, device=dev, dtype=dt)
+                ops.layernorm16(new16, w["n4"][0], w["n4"][1], w["n4"][2], keys16)
+                keys32 = None
+                shared = False
+                continue
             q16 = img_proj(keys16, a["q"], a["q_pe"])                                   # [rows, 704]
             k = self._lin32((queries + qpe).view(-1, C), a["k"]).view(G, nt, -1)
             v = self._lin32(queries.view(-1, C), a["v"]).view(G, nt, -1)

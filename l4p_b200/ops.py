@@ -451,6 +451,18 @@ def row_softmax16(s: torch.Tensor, p16: torch.Tensor) -> None:
     _count()
 
 
+def group_softmax_t16(s: torch.Tensor, p16: torch.Tensor, G: int, heads: int, nt: int) -> None:
+    """s fp32 [G*heads*nt, n] (transposed scores) -> p16 [G*n, heads*nt]: softmax over the nt tokens of each head."""
+    _dev_init(s)
+    _chk(s, "s", torch.float32); _chk(p16, "p16", sixteen=True)
+    n = s.shape[-1]
+    if s.numel() != G * heads * nt * n or p16.numel() != s.numel():
+        raise _l.L4PError(f"group_softmax_t16: shapes {tuple(s.shape)} / {tuple(p16.shape)} vs G={G} heads={heads} nt={nt}")
+    _l.check(_l.load().l4p_group_softmax_t16(s.data_ptr(), p16.data_ptr(), G, heads, nt, n,
+                                             1 if p16.dtype == torch.bfloat16 else 0, _stream()), "l4p_group_softmax_t16")
+    _count()
+
+
 def token_weighted_sum(p16: torch.Tensor, x16: torch.Tensor, y16: torch.Tensor, G: int, J: int) -> None:
     """y16[g] = p16[g] @ x16[g]: p16 [G*J, n], x16 [G*n, C], y16 [G*J, C] (fp32 accumulation)."""
     _dev_init(p16)

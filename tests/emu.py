@@ -261,6 +261,13 @@ def row_softmax16(s, p16) -> None:
     p16.copy_(torch.softmax(s, dim=-1).to(p16.dtype))
 
 
+def group_softmax_t16(s, p16, G, heads, nt) -> None:
+    _note("group_softmax_t16")
+    n = s.shape[-1]
+    pr = torch.softmax(s.reshape(G, heads, nt, n), dim=2)             # over the tokens of a head
+    p16.view(G, n, heads * nt).copy_(pr.reshape(G, heads * nt, n).transpose(1, 2).to(p16.dtype))
+
+
 def token_weighted_sum(p16, x16, y16, G, J) -> None:
     _note("token_weighted_sum")
     n, C = p16.shape[-1], x16.shape[-1]
@@ -347,7 +354,7 @@ def install(monkeypatch) -> None:
     CALLS.clear()
     for name in ("_dev_init", "layernorm", "linear", "linear_qkv", "conv3d", "conv_transpose3d", "conv_transpose3d_hyper",
                  "attention", "patchify", "cast16", "upsample3d", "im2col3", "token_attention", "image_attention",
-                 "layernorm16", "track_readout", "head_expand", "head_diag_gather", "row_softmax16", "token_weighted_sum"):
+                 "layernorm16", "track_readout", "head_expand", "head_diag_gather", "row_softmax16", "token_weighted_sum", "group_softmax_t16"):
         assert hasattr(ops, name), f"l4p_b200.ops.{name} no longer exists: update tests/emu.py"
         monkeypatch.setattr(ops, name, globals()[name])
     monkeypatch.setattr(geometry_utils, "_pose_call", _pose_call)

@@ -113,6 +113,19 @@ def test_token_weighted_sum(dtype, G, J, n, C):
     assert bool((y[G * J:] == 5.0).all())
 
 
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("G,H,nt,n", [(3, 8, 6, 2048), (2, 2, 5, 100), (1, 4, 1, 64)])
+def test_group_softmax_t16(dtype, G, H, nt, n):
+    ops = _ops()
+    s = _rand((G * H * nt, n), torch.float32, 12, 3.0)
+    p = torch.empty(G * n, H * nt, device="cuda", dtype=dtype)
+    ops.group_softmax_t16(s, p, G, H, nt)
+    ref = torch.empty_like(p)
+    emu.group_softmax_t16(s, ref, G, H, nt)
+    torch.cuda.synchronize()
+    assert (p.float() - ref.float()).abs().max().item() <= (2 ** -8 if dtype == torch.bfloat16 else 2 ** -11) * 1.01
+
+
 def test_folded_head_equals_reference_order():
     """The whole track head at the bench's size class (full token size, 16 queries, per-query tokens after the first layer)
     with the folded token -> video-token attention against the same head projecting K / V of all video tokens."""
@@ -129,13 +142,15 @@ def test_folded_head_equals_reference_order():
     lab = torch.ones(1, q.shape[1], device="cuda")
     feats = [None] * 40 + [feat]
     outs = {}
-    for fold in (False, True):
-        h.fold_t2i = fold
+    for fold in ((False, False), (True, False), (False, True), (True, True)):
+        h.fold_t2i, h.fold_i2t = fold
         with torch.no_grad():
             outs[fold] = {k: v.float().clone() for k, v in h.forward_windowed([feats], q, lab, time_strides=torch.tensor([0])).items()}
     torch.cuda.synchronize()
-    a, b = outs[False], outs[True]
-    assert (a["track_2d_traj_est_bn2t"] - b["track_2d_traj_est_bn2t"]).abs().max().item() < 0.05      # pixels
-    assert (a["track_2d_vis_est_bn1t"] - b["track_2d_vis_est_bn1t"]).abs().max().item() < 5e-3
-    d = (a["track_2d_depth_est_bn1t"] - b["track_2d_depth_est_bn1t"]).abs() / a["track_2d_depth_est_bn1t"].abs()
-    assert d.max().item() < 5e-3
+    a = outs[(False, False)]
+    for fold in ((True, False), (False, True), (True, True)):
+        b = outs[fold]
+        assert (a["track_2d_traj_est_bn2t"] - b["track_2d_traj_est_bn2t"]).abs().max().item() < 0.05, fold      # pixels
+        assert (a["track_2d_vis_est_bn1t"] - b["track_2d_vis_est_bn1t"]).abs().max().item() < 5e-3, fold
+        d = (a["track_2d_depth_est_bn1t"] - b["track_2d_depth_est_bn1t"]).abs() / a["track_2d_depth_est_bn1t"].abs()
+        assert d.max().item() < 5e-3, fold
