@@ -141,6 +141,9 @@ int l4p_preprocess_rgb(const void* frames_u8, float* out, int T0, int H0, int W0
                        int To, int Hc, int Wc, const float* mean3, const float* std3, void* stream);
 /* fp32 -> 16-bit cast, n a multiple of 4. */
 int l4p_cast16(const float* x, void* y16, int64_t n, int bf16, void* stream);
+/* The same with an optional fp32 addend of the same length (y = round16(x + add); add may be NULL): the "+ positional
+ * embedding" of the SAM attention inputs (sam/transformer.py:168-170,178-180) folded into the operand cast. */
+int l4p_cast16_add(const float* x, const float* add, void* y16, int64_t n, int bf16, void* stream);
 /* Trilinear resampling of channels-last 16-bit [B,Ti,Hi,Wi,C] -> [B,To,Ho,Wo,C] (y16 and/or its ReLU y16_relu).
  * Replaces F.interpolate(mode="trilinear") (dpt_block.py:231-236, dpt_head.py:79-83: align_corners=1;
  * sparse_heads.py:645-647: align_corners=0). */

@@ -31,10 +31,18 @@ __global__ void patchify_kernel(const float* __restrict__ rgb, uint16_t* __restr
   }
 }
 
+// y = round16(x (+ add)): the fp32 -> operand-type cast in front of a GEMM, optionally with the "+ positional embedding" of
+// the SAM attention inputs (sam/transformer.py:168-170,178-180) folded in. PDL: its launch overlaps the producer's tail.
 template <bool BF16>
-__global__ void cast16_kernel(const float4* __restrict__ x, uint2* __restrict__ y, long long n4) {
+__global__ void cast16_kernel(const float4* __restrict__ x, const float4* __restrict__ add, uint2* __restrict__ y, long long n4) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-    const float4 v = x[i];
+    float4 v = x[i];
+    if (add != nullptr) {
+      const float4 a = add[i];
+      v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+    }
     y[i] = make_uint2(pack2<BF16>(v.x, v.y), pack2<BF16>(v.z, v.w));
   }
 }
@@ -230,17 +238,20 @@ extern "C" int l4p_patchify(const float* rgb, void* out16, int B, int C, int T, 
   return L4P_OK;
 }
 
-extern "C" int l4p_cast16(const float* x, void* y16, int64_t n, int bf16, void* stream) {
+extern "C" int l4p_cast16_add(const float* x, const float* add, void* y16, int64_t n, int bf16, void* stream) {
   L4P_REQUIRE(x && y16, L4P_ERR_ARG, "l4p_cast16: null pointer");
   L4P_REQUIRE(n >= 0 && n % 4 == 0, L4P_ERR_SHAPE, "l4p_cast16: n=%lld must be a multiple of 4", (long long)n);
   if (n == 0) return L4P_OK;
   const unsigned grid = grid_for(n / 4, 256);
   if (bf16)
-    cast16_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>((const float4*)x, (uint2*)y16, n / 4);
+    L4P_CHECK_CUDA(launch_pdl(cast16_kernel<true>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const float4*)x, (const float4*)add, (uint2*)y16, (long long)(n / 4)));
   else
-    cast16_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>((const float4*)x, (uint2*)y16, n / 4);
-  L4P_CHECK_CUDA(cudaGetLastError());
+    L4P_CHECK_CUDA(launch_pdl(cast16_kernel<false>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const float4*)x, (const float4*)add, (uint2*)y16, (long long)(n / 4)));
   return L4P_OK;
+}
+
+extern "C" int l4p_cast16(const float* x, void* y16, int64_t n, int bf16, void* stream) {
+  return l4p_cast16_add(x, nullptr, y16, n, bf16, stream);
 }
 
 extern "C" int l4p_upsample3d(const void* x16, void* y16, void* y16_relu, int B, int Ti, int Hi, int Wi, int To, int Ho,

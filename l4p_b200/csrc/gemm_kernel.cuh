@@ -215,6 +215,30 @@ L4P_DEVICE void apply_act2_rt(float& a, float& b, int act) {
   else if (act == L4P_ACT_RELU) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
 }
 
+// split-K: bias / activation / residuals / stores of four finished columns of one output row (run-time options: the
+// split-K problems are the small low-resolution ones, their finalisation is latency-, not issue-bound)
+template <bool BF16>
+L4P_DEVICE void splitk_finalize4(const GemmKParams& p, const long long row, const int col, float4 x) {
+  if (p.bias != nullptr) {
+    const float4 b4 = *reinterpret_cast<const float4*>(p.bias + col);
+    x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
+  }
+  apply_act2_rt(x.x, x.y, p.act);
+  apply_act2_rt(x.z, x.w, p.act);
+  if (p.res_f32 != nullptr) {
+    const long long rrow = p.res_row_mod > 0 ? row % p.res_row_mod : row;
+    const float4 r4 = *reinterpret_cast<const float4*>(p.res_f32 + rrow * p.ld_res + col);
+    x.x += r4.x; x.y += r4.y; x.z += r4.z; x.w += r4.w;
+  }
+  if (p.res_16 != nullptr) add_res16<BF16>(x, p.res_16 + row * p.ld_res + col);
+  if (p.res2_16 != nullptr) add_res16<BF16>(x, p.res2_16 + row * p.ld_res + col);
+  const long long o = row * p.ld_out + col;
+  if (p.out_f32 != nullptr) *reinterpret_cast<float4*>(p.out_f32 + o) = x;
+  if (p.out_16 != nullptr) store4_16<BF16>(p.out_16 + o, x);
+  if (p.out_16_relu != nullptr)
+    store4_16<BF16>(p.out_16_relu + o, make_float4(fmaxf(x.x, 0.f), fmaxf(x.y, 0.f), fmaxf(x.z, 0.f), fmaxf(x.w, 0.f)));
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // Fused-dot modes (HEAD1X1 / HYPER): shared state between the epilogue warps and the HELPER warp (4th pipeline warp).
 // A single epilogue warp pays a full L1/L2 round trip for every global access it makes, so everything that touches
@@ -606,10 +630,8 @@ L4P_DEVICE void epilogue_tile(const GemmKParams& p, const TileCoord& tc, const i
         for (int it = 0; it < 8; ++it) {
           const uint32_t rl = (uint32_t)(it * 4 + rgrp);
           const float4 x = lds128(rbase + (uint32_t)it * 512u + ((((uint32_t)sub) ^ (rl & 7u)) << 4));
-          if (cok && ((okm >> it) & 1u)) {
-            float* dst = p.splitk_ws + ((long long)orow[it] * p.N + col);
-            atomicAdd(dst, x.x); atomicAdd(dst + 1, x.y); atomicAdd(dst + 2, x.z); atomicAdd(dst + 3, x.w);
-          }
+          if (cok && ((okm >> it) & 1u))  // one 16-byte reduction (red.global.add.v4.f32, sm_90+) instead of four scalar ones
+            atomicAdd(reinterpret_cast<float4*>(p.splitk_ws + ((long long)orow[it] * p.N + col)), x);
         }
         continue;
       }
@@ -1084,7 +1106,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   }
 }
 
-// split-K finalisation: out = epilogue(workspace), workspace re-zeroed for the next split-K launch (4 columns per thread)
+// split-K finalisation: out = epilogue(workspace), workspace re-zeroed for the next split-K launch (4 columns per thread).
+// A fused form (the CTA that delivers the last K slice of a tile finalises it, per-tile arrival counters) was measured in
+// round 2 and removed: one CTA finalising a 128 x 256 tile sits on the critical path for longer than this all-SM kernel
+// takes including its (PDL-overlapped) launch: 1.94 vs 1.74 ms for the 59 low-resolution convolutions of a step.
 template <bool BF16>
 __global__ void __launch_bounds__(256)
 splitk_finalize_kernel(const GemmKParams p) {
@@ -1095,26 +1120,9 @@ splitk_finalize_kernel(const GemmKParams p) {
     const long long row = i / n4;
     const int col = (int)(i - row * n4) * 4;
     float4* w = reinterpret_cast<float4*>(p.splitk_ws + row * p.N + col);
-    float4 x = *w;
+    const float4 x = *w;
     *w = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (p.bias != nullptr) {
-      const float4 b4 = *reinterpret_cast<const float4*>(p.bias + col);
-      x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
-    }
-    apply_act2_rt(x.x, x.y, p.act);
-    apply_act2_rt(x.z, x.w, p.act);
-    if (p.res_f32 != nullptr) {
-      const long long rrow = p.res_row_mod > 0 ? row % p.res_row_mod : row;
-      const float4 r4 = *reinterpret_cast<const float4*>(p.res_f32 + rrow * p.ld_res + col);
-      x.x += r4.x; x.y += r4.y; x.z += r4.z; x.w += r4.w;
-    }
-    if (p.res_16 != nullptr) add_res16<BF16>(x, p.res_16 + row * p.ld_res + col);
-    if (p.res2_16 != nullptr) add_res16<BF16>(x, p.res2_16 + row * p.ld_res + col);
-    const long long o = row * p.ld_out + col;
-    if (p.out_f32 != nullptr) *reinterpret_cast<float4*>(p.out_f32 + o) = x;
-    if (p.out_16 != nullptr) store4_16<BF16>(p.out_16 + o, x);
-    if (p.out_16_relu != nullptr)
-      store4_16<BF16>(p.out_16_relu + o, make_float4(fmaxf(x.x, 0.f), fmaxf(x.y, 0.f), fmaxf(x.z, 0.f), fmaxf(x.w, 0.f)));
+    splitk_finalize4<BF16>(p, row, col, x);
   }
 }
 

@@ -419,9 +419,11 @@ layernorm16_kernel(const uint16_t* __restrict__ x, const float* __restrict__ gam
 
 // Long rows (the 1408-channel per-query token stream of the two-way layers, 16-bit in and out): one warp owns R rows at a
 // time and keeps them as RAW packed words (CH x uint4 per lane and row instead of 8 x CH floats), so all R x CH 16-byte
-// loads of a lane are in flight at once: 11 KB per warp, ~135 KB per SM (R = 4, 12 warps per SM at <= 168 registers: with 128 registers the raw rows spill). The generic kernel above holds one unpacked row per
-// warp (2.8 KB in flight) and reached 3.1 TB/s on [262144, 1408]; the fp32-input LayerNorm of layernorm.cu, with twice the
-// bytes per row in flight, 6.2 TB/s.
+// loads of a lane are in flight at once: 11 KB per warp, ~135 KB per SM (R = 4, 12 warps per SM at <= 168 registers). The
+// generic kernel above holds one unpacked row per warp (2.8 KB in flight) and reached 3.1 TB/s on [262144, 1408].
+// With the rows in flight the kernel is INSTRUCTION-bound (16-bit input doubles the elements per byte): statistics in ONE
+// pass as shifted moments (shift = the row's first element, so E[(x-s)^2] - E[x-s]^2 does not cancel) and all arithmetic
+// on the packed f32x2 pipe: ~5.5 instead of ~9.5 instructions per element.
 template <bool BF16, int CH, int R>  // cols <= 32 * 8 * CH
 __global__ void __launch_bounds__(128, 3)
 layernorm16_rows_kernel(const uint16_t* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -442,33 +444,13 @@ layernorm16_rows_kernel(const uint16_t* __restrict__ x, const float* __restrict_
   }
   float mean[R], rstd[R];
   {
-    float s[R];
+    uint64_t s1[R], s2[R];
+    float shift[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      float a = 0.f;
-#pragma unroll
-      for (int i = 0; i < CH; ++i) {  // chunks beyond the row are zero words: they add nothing
-        const uint32_t w[4] = {raw[r][i].x, raw[r][i].y, raw[r][i].z, raw[r][i].w};
-#pragma unroll
-        for (int t = 0; t < 4; ++t) { const float2 f = unpack2<BF16>(w[t]); a += f.x + f.y; }
-      }
-      s[r] = a;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-      for (int r = 0; r < R; ++r) s[r] += __shfl_xor_sync(0xffffffffu, s[r], o);
-#pragma unroll
-    for (int r = 0; r < R; ++r) mean[r] = s[r] / (float)cols;
-    // launder the raw words: without this the compiler keeps the UNPACKED values of the first pass alive for the next two
-    // (common-subexpression elimination), i.e. 8 x CH x R floats, and spills
-#define L4P_LN16_LAUNDER()                                                                                           \
-    _Pragma("unroll") for (int r = 0; r < R; ++r) _Pragma("unroll") for (int i = 0; i < CH; ++i)                       \
-        asm volatile("" : "+r"(raw[r][i].x), "+r"(raw[r][i].y), "+r"(raw[r][i].z), "+r"(raw[r][i].w))
-    L4P_LN16_LAUNDER();
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      float a = 0.f;
+      shift[r] = __shfl_sync(0xffffffffu, unpack2<BF16>(raw[r][0].x).x, 0);   // the row's first element
+      const uint64_t ns2 = pk2(-shift[r], -shift[r]);
+      uint64_t a1 = pk2(0.f, 0.f), a2 = pk2(0.f, 0.f);
 #pragma unroll
       for (int i = 0; i < CH; ++i) {
         if (lane + i * 32 < nch) {
@@ -476,21 +458,36 @@ layernorm16_rows_kernel(const uint16_t* __restrict__ x, const float* __restrict_
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
             const float2 f = unpack2<BF16>(w[t]);
-            const float d0 = f.x - mean[r], d1 = f.y - mean[r];
-            a += d0 * d0 + d1 * d1;
+            const uint64_t d = add2(pk2(f.x, f.y), ns2);
+            a1 = add2(a1, d);
+            a2 = fma2(d, d, a2);
           }
         }
       }
-      s[r] = a;
+      s1[r] = a1; s2[r] = a2;
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
+    for (int r = 0; r < R; ++r) {
+      float u0, u1, q0, q1;
+      upk2(s1[r], u0, u1);
+      upk2(s2[r], q0, q1);
+      float u = u0 + u1, q = q0 + q1;
 #pragma unroll
-      for (int r = 0; r < R; ++r) s[r] += __shfl_xor_sync(0xffffffffu, s[r], o);
+      for (int o = 16; o > 0; o >>= 1) {
+        u += __shfl_xor_sync(0xffffffffu, u, o);
+        q += __shfl_xor_sync(0xffffffffu, q, o);
+      }
+      const float m = u / (float)cols;
+      mean[r] = shift[r] + m;
+      rstd[r] = rsqrtf(fmaxf(q / (float)cols - m * m, 0.f) + eps);
+    }
+    // launder the raw words: without this the compiler keeps the UNPACKED values of the statistics pass alive for the
+    // output pass (common-subexpression elimination), i.e. 8 x CH x R floats, and spills
 #pragma unroll
-    for (int r = 0; r < R; ++r) rstd[r] = rsqrtf(s[r] / (float)cols + eps);
-    L4P_LN16_LAUNDER();
-#undef L4P_LN16_LAUNDER
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int i = 0; i < CH; ++i)
+        asm volatile("" : "+r"(raw[r][i].x), "+r"(raw[r][i].y), "+r"(raw[r][i].z), "+r"(raw[r][i].w));
   }
 #pragma unroll
   for (int i = 0; i < CH; ++i) {
@@ -499,18 +496,20 @@ layernorm16_rows_kernel(const uint16_t* __restrict__ x, const float* __restrict_
     if (j < nch) {
       const float4 g0 = reinterpret_cast<const float4*>(gamma)[2 * j], g1 = reinterpret_cast<const float4*>(gamma)[2 * j + 1];
       const float4 b0 = reinterpret_cast<const float4*>(beta)[2 * j], b1 = reinterpret_cast<const float4*>(beta)[2 * j + 1];
-      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      const uint64_t gg[4] = {pk2(g0.x, g0.y), pk2(g0.z, g0.w), pk2(g1.x, g1.y), pk2(g1.z, g1.w)};
+      const uint64_t bb[4] = {pk2(b0.x, b0.y), pk2(b0.z, b0.w), pk2(b1.x, b1.y), pk2(b1.z, b1.w)};
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         if (row0 + r < rows) {
           const uint32_t w[4] = {raw[r][i].x, raw[r][i].y, raw[r][i].z, raw[r][i].w};
+          const uint64_t rs2 = pk2(rstd[r], rstd[r]), nm2 = pk2(-mean[r], -mean[r]);
           float o[8];
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
             const float2 f = unpack2<BF16>(w[t]);
-            o[2 * t] = (f.x - mean[r]) * rstd[r] * gg[2 * t] + bb[2 * t];
-            o[2 * t + 1] = (f.y - mean[r]) * rstd[r] * gg[2 * t + 1] + bb[2 * t + 1];
+            // ((x - mean) * rstd) * gamma + beta, the association of the other LayerNorm kernels
+            const uint64_t v = fma2(mul2(add2(pk2(f.x, f.y), nm2), rs2), gg[t], bb[t]);
+            upk2(v, o[2 * t], o[2 * t + 1]);
           }
           if (gelu) {
 #pragma unroll

@@ -64,6 +64,7 @@ _SIGNATURES = {
     "l4p_patchify": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 9 + [C.c_void_p]),
     "l4p_preprocess_rgb": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 11 + [C.c_void_p, C.c_void_p, C.c_void_p]),
     "l4p_cast16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
+    "l4p_cast16_add": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     "l4p_upsample3d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 10 + [C.c_void_p]),
     "l4p_im2col3": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 8 + [C.c_void_p]),
     "l4p_pose_from_rays": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 7 + [C.c_float, C.c_int] + [C.c_void_p] * 6),

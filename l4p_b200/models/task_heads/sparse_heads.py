@@ -285,18 +285,27 @@ class VideoMAETrack2DSamHead(nn.Module):
         return pk
 
     # ------------------------------------------------------------------ small helpers (token side)
-    def _lin32(self, x32: torch.Tensor, l, act=_l.ACT_NONE, res32=None, out16=False):
-        """Linear on fp32 rows through the tcgen05 GEMM: cast -> GEMM(+bias, act, +residual)."""
-        dt = self.compute_dtype
+    def _tok16(self, x32: torch.Tensor, add32: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """16-bit GEMM operand of fp32 rows, optionally of (x32 + add32) (the "+ positional embedding" of the attention inputs,
+        one kernel instead of an add and a cast)."""
         rows = x32.numel() // x32.shape[-1]
-        x16 = torch.empty(rows, x32.shape[-1], device=x32.device, dtype=dt)
-        ops.cast16(x32.contiguous(), x16)
+        x16 = torch.empty(rows, x32.shape[-1], device=x32.device, dtype=self.compute_dtype)
+        ops.cast16(x32.contiguous(), x16, add=None if add32 is None else add32.contiguous())
+        return x16
+
+    def _lin32(self, x32: Optional[torch.Tensor], l, act=_l.ACT_NONE, res32=None, out16=False, x16: Optional[torch.Tensor] = None):
+        """Linear on fp32 rows through the tcgen05 GEMM: cast -> GEMM(+bias, act, +residual). A caller that feeds the same rows
+        to several projections passes their 16-bit copy `x16` (from _tok16) instead of x32."""
+        dt = self.compute_dtype
+        if x16 is None:
+            x16 = self._tok16(x32)
+        rows, dev = x16.shape[0], x16.device
         N = l["w"].shape[0]
         if out16:
-            y = torch.empty(rows, N, device=x32.device, dtype=dt)
+            y = torch.empty(rows, N, device=dev, dtype=dt)
             ops.linear(x16, l["w"], bias=l["b"], act=act, out_16=y)
         else:
-            y = torch.empty(rows, N, device=x32.device, dtype=torch.float32)
+            y = torch.empty(rows, N, device=dev, dtype=torch.float32)
             ops.linear(x16, l["w"], bias=l["b"], act=act, res_f32=res32, out_f32=y)
         return y
 
@@ -305,12 +314,12 @@ class VideoMAETrack2DSamHead(nn.Module):
         ops.layernorm(x32.contiguous(), n[0], n[1], n[2], out32=y)
         return y
 
-    def _token_attn(self, a, q_in, k_in, v_in, G):
-        """Attention among the prompt tokens themselves (6 keys), sam/transformer.py:157-161."""
-        C = q_in.shape[-1]
-        q = self._lin32(q_in, a["q"]).view(G, -1, a["q"]["w"].shape[0])
-        k16 = self._lin32(k_in, a["k"], out16=True)
-        v16 = self._lin32(v_in, a["v"], out16=True)
+    def _token_attn(self, a, qk16, v16_in, G):
+        """Attention among the prompt tokens themselves (6 keys), sam/transformer.py:157-161. qk16 / v16_in: 16-bit operand
+        copies of the q = k input (queries + pe) and of the v input (queries)."""
+        q = self._lin32(None, a["q"], x16=qk16).view(G, -1, a["q"]["w"].shape[0])
+        k16 = self._lin32(None, a["k"], out16=True, x16=qk16)
+        v16 = self._lin32(None, a["v"], out16=True, x16=v16_in)
         o = torch.empty_like(q)
         ops.token_attention(q, k16, v16, o, a["heads"], shared_kv=False, scale=1.0 / math.sqrt(a["hd"]))
         return o
@@ -350,7 +359,7 @@ class VideoMAETrack2DSamHead(nn.Module):
             out = W_v (sum_n p_n x_n) + b_v (csrc/track_t2i.cu); 48 = heads x tokens score rows per query."""
             H, hd = a["heads"], a["hd"]
             D, J = H * hd, H * nt
-            q = self._lin32((queries + qpe).view(-1, C), a["q"])                       # [G*nt, D] fp32
+            q = self._lin32(None, a["q"], x16=self._tok16(queries, qpe))               # [G*nt, D] fp32
             qb = torch.empty(G * J, D, device=dev, dtype=dt)
             ops.head_expand(q, qb, G, nt, H, hd, 1.0 / math.sqrt(hd))                  # block-diagonal, pre-scaled
             qp = torch.empty(G * J, C, device=dev, dtype=dt)
@@ -373,7 +382,7 @@ class VideoMAETrack2DSamHead(nn.Module):
             fits = a["heads"] * nt <= 48 and Pn % 64 == 0 and Pn <= 2048
             if self.fold_t2i and not shared_now and (fits or not keys16.is_cuda):
                 return t2i_folded(a, queries, keys16)
-            q = self._lin32((queries + qpe).view(-1, C), a["q"]).view(G, nt, -1)
+            q = self._lin32(None, a["q"], x16=self._tok16(queries, qpe)).view(G, nt, -1)
             k16 = img_proj(keys16, a["k"], a["k_pe"])
             v16 = img_proj(keys16, a["v"], None)
             o = torch.empty_like(q)
@@ -384,11 +393,11 @@ class VideoMAETrack2DSamHead(nn.Module):
         for li, w in enumerate(pk["layers"]):
             # (1) token self attention
             if w["skip_pe"]:
-                o = self._token_attn(w["sa"], queries.view(-1, C), queries.view(-1, C), queries.view(-1, C), G)
+                t16 = self._tok16(queries)
+                o = self._token_attn(w["sa"], t16, t16, G)
                 queries = self._lin32(o.view(-1, C), w["sa"]["o"]).view(G, nt, C)
             else:
-                qq = (queries + qpe).view(-1, C)
-                o = self._token_attn(w["sa"], qq, qq, queries.view(-1, C), G)
+                o = self._token_attn(w["sa"], self._tok16(queries, qpe), self._tok16(queries), G)
                 queries = self._lin32(o.view(-1, C), w["sa"]["o"], res32=queries.view(-1, C).contiguous()).view(G, nt, C)
             queries = self._ln32(queries, w["n1"])
             # (2) tokens attend to the video tokens
@@ -408,7 +417,7 @@ class VideoMAETrack2DSamHead(nn.Module):
                 # query: the 704-wide Q and attention-output copies of the token stream are never formed.
                 H, hd = a["heads"], a["hd"]
                 D, J = H * hd, H * nt
-                kk = self._lin32((queries + qpe).view(-1, C), a["k"])                   # [G*nt, D] fp32
+                kk = self._lin32(None, a["k"], x16=self._tok16(queries, qpe))           # [G*nt, D] fp32
                 vv = self._lin32(queries.view(-1, C), a["v"])
                 kb = torch.empty(G * J, D, device=dev, dtype=dt)
                 ops.head_expand(kk, kb, G, nt, H, hd, 1.0 / math.sqrt(hd))
@@ -438,7 +447,7 @@ class VideoMAETrack2DSamHead(nn.Module):
                 shared = False
                 continue
             q16 = img_proj(keys16, a["q"], a["q_pe"])                                   # [rows, 704]
-            k = self._lin32((queries + qpe).view(-1, C), a["k"]).view(G, nt, -1)
+            k = self._lin32(None, a["k"], x16=self._tok16(queries, qpe)).view(G, nt, -1)
             v = self._lin32(queries.view(-1, C), a["v"]).view(G, nt, -1)
             if shared:  # first use of per-query state: the attention output differs per query
                 q16 = q16.unsqueeze(0).expand(G, -1, -1).reshape(G * Pn, -1)

@@ -302,13 +302,14 @@ def patchify(rgb: torch.Tensor, out16: torch.Tensor, tubelet: Tuple[int, int, in
     _count()
 
 
-def cast16(x: torch.Tensor, y16: torch.Tensor) -> None:
+def cast16(x: torch.Tensor, y16: torch.Tensor, add: Optional[torch.Tensor] = None) -> None:
+    """y16 = round16(x (+ add)); x, add fp32 of the same size."""
     _dev_init(x)
-    _chk(x, "x", torch.float32); _chk(y16, "y16", sixteen=True)
-    if x.numel() != y16.numel():
+    _chk(x, "x", torch.float32); _chk(y16, "y16", sixteen=True); _chk(add, "add", torch.float32)
+    if x.numel() != y16.numel() or (add is not None and add.numel() != x.numel()):
         raise _l.L4PError("cast16: size mismatch")
-    _l.check(_l.load().l4p_cast16(x.data_ptr(), y16.data_ptr(), x.numel(), 1 if y16.dtype == torch.bfloat16 else 0,
-                                  _stream()), "l4p_cast16")
+    _l.check(_l.load().l4p_cast16_add(x.data_ptr(), _ptr(add), y16.data_ptr(), x.numel(),
+                                      1 if y16.dtype == torch.bfloat16 else 0, _stream()), "l4p_cast16")
     _count()
 
 

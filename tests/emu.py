@@ -180,10 +180,10 @@ def patchify(rgb, out16, tubelet) -> None:
     out16.copy_(x.reshape(out16.shape).to(out16.dtype))
 
 
-def cast16(x, y16) -> None:
+def cast16(x, y16, add=None) -> None:
     _note("cast16")
     assert x.dtype == torch.float32 and _is16(y16)
-    y16.view(x.shape).copy_(x.to(y16.dtype))
+    y16.view(x.shape).copy_((x if add is None else x + add.view(x.shape)).to(y16.dtype))
 
 
 def upsample3d(x, out_size, *, align_corners, y=None, y_relu=None) -> None:
