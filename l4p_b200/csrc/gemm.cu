@@ -1,5 +1,7 @@
 // Host side of the tcgen05 GEMM / implicit-GEMM conv kernels (gemm_kernel.cuh): descriptor validation, TMA tensor maps,
 // tile / stage selection, 1-CTA vs CTA-pair choice and the lookup of the compile-time epilogue instance.
+#include <cstdlib>
+
 #include "gemm_kernel.cuh"
 
 namespace l4p {
@@ -315,10 +317,32 @@ extern "C" int l4p_gemm(const l4p_gemm_desc* d, void* stream_) {
     const uint32_t box[2] = {kBlockK, (uint32_t)(p.block_n / 2)};
     rc = t_plan ? L4P_OK : host_make_tmap_16b(&tmB, d->w, 2, dims, strides, box, 128);
     if (rc != L4P_OK) return rc;
-    const uint32_t sb2 = kABytes + (uint32_t)(p.block_n / 2) * 128u;
+    // Line-halo stages (gemm_kernel.cuh, gemm2_kernel producer): the three in-plane row taps share one A box with bH + 2
+    // lines. A 256 x 128 pair tile otherwise needs 16 + 8 KiB per CTA and k-block = 96 B/clk through the 64 B/clk L2 -> SM
+    // port (measured 927 -> 1519 TFLOP/s on the 224^2 head convolution); 256 x 256 tiles sit exactly at 64 B/clk.
+    // L4P_CONV_HALO=0 restores one box per tap (tuning / A-B).
+    static int halo_env = -1;
+    if (halo_env < 0) {
+      const char* e = getenv("L4P_CONV_HALO");
+      halo_env = (e && atoi(e) == 0) ? 0 : 1;
+    }
+    const uint32_t halo_a = (uint32_t)((d->bH + 2) * d->bW) * 128u;
+    const bool halo = halo_env && d->a_mode == L4P_A_CONV3D && d->kH == 3 && d->kW == 3 && d->bT == 1 && d->bH >= 2 && d->bW % 8 == 0 &&
+                      2u * (halo_a + 3u * (uint32_t)(p.block_n / 2) * 128u) <= kRingBudget;
+    if (halo) {
+      p.a_halo = 1;
+      const uint64_t C = (uint64_t)d->cCin;
+      const uint64_t dimsA[5] = {C, (uint64_t)d->cW, (uint64_t)d->cH, (uint64_t)d->cT, (uint64_t)d->cB};
+      const uint64_t stridesA[4] = {C * 2, C * 2 * d->cW, C * 2 * d->cW * d->cH, C * 2 * d->cW * d->cH * d->cT};
+      const uint32_t boxA[5] = {kBlockK, (uint32_t)d->bW, (uint32_t)(d->bH + 2), 1, 1};
+      rc = t_plan ? L4P_OK : host_make_tmap_16b(&tmA, d->a, 5, dimsA, stridesA, boxA, 128);
+      if (rc != L4P_OK) return rc;
+    }
+    const uint32_t sb2 = halo ? halo_a + 3u * (uint32_t)(p.block_n / 2) * 128u : kABytes + (uint32_t)(p.block_n / 2) * 128u;
+    const int nst2 = halo ? d->kT * 3 * p.cblocks : p.num_kb;   // ring iterations per tile
     int st2 = (int)(kRingBudget / sb2);
     if (st2 > kMaxStages) st2 = kMaxStages;
-    if (st2 > p.num_kb) st2 = p.num_kb < 2 ? 2 : p.num_kb;
+    if (st2 > nst2) st2 = nst2 < 2 ? 2 : nst2;
     if (st2 > kMaxStages) st2 = kMaxStages;
     p.stages = st2;
     const size_t smem2 = (size_t)st2 * sb2 + 1024 + epi_bytes;

@@ -110,6 +110,7 @@ struct GemmKParams {
   FastDiv fd_bW, fd_bH;                 // HEAD1X1 finalisation: row in tile -> (tl,hl,wl)
   int split_k;               // >1: work unit = (tile, k-range); partial sums are atomically added to splitk_ws [M,N] fp32
   float* splitk_ws;
+  int a_halo;                // 2-CTA conv mode, 3x3 in-plane filter: one A box with bH+2 lines per (dt, dw, channel block) serves the 3 dh taps
   int m_stride;              // matrix mode: rows between consecutive M tiles = rows stored per tile (128 unless grouped)
   int grp_a_rows, grp_b_rows;  // grouped weights: tile rows / grp_a_rows = group, its W block starts at row group * grp_b_rows
   long long* prof;           // optional [3][512] clock64 timeline of CTA 0
@@ -956,7 +957,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t half_n = (uint32_t)p.block_n / 2;
   const uint32_t b_bytes = half_n * 128u;
-  const uint32_t stage_bytes = kABytes + b_bytes;
+  const uint32_t stage_bytes = p.a_halo ? (uint32_t)((p.bH + 2) * p.bW) * 128u + 3u * b_bytes : kABytes + b_bytes;
   const int tiles_m2 = (p.tiles_m + 1) / 2;
   const int num_tiles = tiles_m2 * p.tiles_n;
   const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
@@ -1002,6 +1003,30 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const int n_blk = tile % p.tiles_n;
         const TileCoord tc = decode_block(p, (tile / p.tiles_n) * 2 + (int)rank, n_blk);
         const int n0 = n_blk * p.block_n + (int)(rank * half_n);
+        if (p.a_halo) {
+          // Line-halo stages: A = the tile's voxel box grown by one line above and below (bH + 2 lines, shifted by dw in W and dt
+          // in T), B = the weights of the three taps (dt, -1..1, dw) of one 64-channel block. The three dh taps read the SAME
+          // A box at line offsets 0 / 1 / 2, so every activation byte crosses the 64 B/clk L2 -> SM port once per dw shift
+          // instead of once per tap (9 instead of 27 times): 24 + 3 x 8 KiB per 768 cycles of UMMA instead of 3 x (16 + 8).
+          const uint32_t a_bytes = (uint32_t)((p.bH + 2) * p.bW) * 128u;
+          for (int dti = 0; dti < p.kT; ++dti)
+            for (int dwi = 0; dwi < 3; ++dwi)
+              for (int cb = 0; cb < p.cblocks; ++cb) {
+                mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
+                const uint32_t full_leader = mapa_shared(smem_u32(&bar_full[stage]), 0);
+                const uint32_t sa = smem_base + stage * stage_bytes;
+                if (is_leader) mbar_expect_tx(smem_u32(&bar_full[stage]), 2 * stage_bytes);
+                tma2_load_5d(sa, &tmA, full_leader, cb * kBlockK, tc.w0 + dwi - 1, tc.h0 - 1, tc.t0 + dti - p.kT / 2, tc.b);
+#pragma unroll
+                for (int dhi = 0; dhi < 3; ++dhi) {
+                  const int kb = ((dti * 3 + dhi) * 3 + dwi) * p.cblocks + cb;
+                  tma2_load_2d(sa + a_bytes + (uint32_t)dhi * b_bytes, &tmB, full_leader, kb * kBlockK, n0);
+                }
+                GEMM_STAMP(0, pg); ++pg;
+                if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+              }
+          continue;
+        }
         int cb = 0, dw = -(p.kW / 2), dh = -(p.kH / 2), dt = -(p.kT / 2);
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
@@ -1044,6 +1069,35 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         mbar_wait(smem_u32(&bar_tempty[acc]), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * kAccCols;
+        if (p.a_halo) {
+          // one stage = 3 k-blocks: tap dh reads the A box from line dh on (a whole number of 1024-byte swizzle periods: bW is
+          // a multiple of 8) and its own weight tile behind the box
+          const uint32_t a_units = (uint32_t)((p.bH + 2) * p.bW) * 8u, line_units = (uint32_t)p.bW * 8u, b_units = b_bytes >> 4;
+          const int nst = p.kT * 3 * p.cblocks;
+          for (int st = 0; st < nst; ++st) {
+            mbar_wait(smem_u32(&bar_full[stage]), phase);
+            tc_fence_after();
+            if (leader_lane) {
+              GEMM_STAMP(1, mg);
+              const uint32_t s_lo = a_lo0 + (uint32_t)stage * stage_step;
+#pragma unroll
+              for (int dhi = 0; dhi < 3; ++dhi) {
+                const uint32_t a_lo = s_lo + (uint32_t)dhi * line_units, b_lo = s_lo + a_units + (uint32_t)dhi * b_units;
+#pragma unroll
+                for (int k = 0; k < kBlockK / 16; ++k)
+                  umma2_ss(d_tmem, umma_desc_make(a_lo + 2 * k, hi128), umma_desc_make(b_lo + 2 * k, hi128), idesc,
+                           (st | dhi | k) != 0 ? 1u : 0u);
+              }
+              umma2_commit_mc(smem_u32(&bar_empty[stage]), 3);
+              if (st == nst - 1) umma2_commit_mc(smem_u32(&bar_tfull[acc]), 3);
+            }
+            __syncwarp();
+            ++mg;
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+          }
+          if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+          continue;
+        }
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(smem_u32(&bar_full[stage]), phase);
           tc_fence_after();

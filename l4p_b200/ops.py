@@ -222,6 +222,10 @@ def conv3d(x: torch.Tensor, w: torch.Tensor, *, ksize: Tuple[int, int, int], bia
     d.cB, d.cT, d.cH, d.cW, d.cCin = B, T, H, W, Cin
     d.kT, d.kH, d.kW = kT, kH, kW
     d.bT, d.bH, d.bW = pick_box(T, H, W)
+    if kH == 3 and kW == 3 and H % 4 == 0 and W % 32 == 0:
+        # a 4-line box lets the 2-CTA kernel's line-halo stages serve the three row taps from one 6-line A box (l4p_gemm,
+        # gemm2_kernel); the wide single- or two-line boxes pick_box prefers at W = 128 / 64 have little or no row reuse
+        d.bT, d.bH, d.bW = 1, 4, 32
     d.block_n = block_n
     d.cta_pair = cta_pair
     d.prof = _ptr(prof)

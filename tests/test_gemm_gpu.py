@@ -370,3 +370,54 @@ def test_layernorm16_long_rows_ragged(dtype, rows, gelu):
         ref = F.gelu(ref)
     _close(y[:rows], ref, 2 ** -7 if dtype == torch.bfloat16 else 2 ** -10)
     assert bool((y[rows:] == 7.0).all())
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("shape", [(1, 4, 64, 64, 128, 128), (1, 3, 20, 32, 64, 128), (2, 2, 12, 96, 256, 64),
+                                   (1, 1, 8, 32, 64, 16)])
+def test_conv3d_line_halo_pair(dtype, shape):
+    """Narrow 3x3x3 convolutions through the 2-CTA kernel's line-halo stages (one 6-line A box per (dt, dw, channel block)
+    serves the three row taps): whole volumes, an odd tile count (padding block of the last pair), several channel blocks,
+    a single frame (the dt = +-1 boxes lie entirely outside the volume: TMA zero fill)."""
+    ops = _ops()
+    B, T, H, W, Cin, Cout = shape
+    x = _rand((B, T, H, W, Cin), dtype, 31)
+    w = _rand((Cout, 27 * Cin), dtype, 32, (27 * Cin) ** -0.5)
+    b = _rand((Cout,), torch.float32, 33)
+    out = torch.empty(B, T, H, W, Cout, device="cuda", dtype=torch.float32)
+    ops.conv3d(x, w, ksize=(3, 3, 3), bias=b, out_f32=out, cta_pair=1)
+    torch.cuda.synchronize()
+    _close(out, _conv_ref(x, w, (3, 3, 3), b), 3e-5)
+
+
+@pytest.mark.parametrize("dtype", DT)
+def test_conv3d_head1x1_line_halo_pair(dtype):
+    """The DPT head convolution (3x3x3 128 -> 128 + ReLU + 1x1x1, fused-dot epilogue) at a size that takes the 2-CTA kernel."""
+    ops = _ops()
+    B, T, H, W, Cc, C2 = 1, 2, 56, 64, 128, 2
+    x = _rand((B, T, H, W, Cc), dtype, 34)
+    w = _rand((Cc, 27 * Cc), dtype, 35, (27 * Cc) ** -0.5)
+    b = _rand((Cc,), torch.float32, 36)
+    w2 = _rand((C2, Cc), torch.float32, 37, Cc ** -0.5)
+    b2 = _rand((C2,), torch.float32, 38)
+    out = torch.empty(B, C2, T, H, W, device="cuda", dtype=torch.float32)
+    ops.conv3d(x, w, ksize=(3, 3, 3), bias=b, head_w2=w2, head_b2=b2, head_exp=False, out_f32=out, cta_pair=1)
+    torch.cuda.synchronize()
+    hid = _conv_ref(x, w, (3, 3, 3), b).clamp_min(0)
+    ref = (hid @ w2.t() + b2).permute(0, 4, 1, 2, 3)
+    _close(out, ref, 5e-5)
+
+
+@pytest.mark.parametrize("dtype", DT)
+def test_conv3d_line_halo_wide(dtype):
+    """Line-halo stages with 256-wide tiles (two 72 KiB stages in the ring): the 64^2 RefineNet convolution shape class."""
+    ops = _ops()
+    B, T, H, W, Cin, Cout = 1, 3, 32, 64, 128, 256
+    x = _rand((B, T, H, W, Cin), dtype, 41)
+    w = _rand((Cout, 27 * Cin), dtype, 42, (27 * Cin) ** -0.5)
+    b = _rand((Cout,), torch.float32, 43)
+    r1 = _rand((B, T, H, W, Cout), dtype, 44)
+    o = torch.empty(B, T, H, W, Cout, device="cuda", dtype=dtype)
+    ops.conv3d(x, w, ksize=(3, 3, 3), bias=b, res_16=r1, out_16=o, cta_pair=1)
+    torch.cuda.synchronize()
+    _close(o, _conv_ref(x, w, (3, 3, 3), b) + r1.float(), 2 ** -8 if dtype == torch.bfloat16 else 2 ** -10)
