@@ -800,10 +800,32 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (warp == kWarpProducer) {
     // ------------------------------------------------------------------ TMA producer
     if constexpr (kRepartition) asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
-    if (lane == 0) {
-      int stage = 0, pg = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    // Short-K problems with a 16-bit residual (the track head's per-query K = 48 output GEMM: 0.74 GB of residual per launch)
+    // are bound by the epilogue's residual loads: one chunk of prefetch distance keeps 16 KB per SM in flight, 1.5 TB/s at
+    // HBM latency. The otherwise idle lanes of this warp pull the residual tile of the CTA's tile after next into L2 while
+    // lane 0 produces the current one (paced by the __syncwarp at the end of each tile), so the epilogue's loads hit L2.
+    const bool res_pf = p.a_mode == L4P_A_MATRIX && p.store_mode == L4P_STORE_ROWMAJOR && p.res_16 != nullptr && p.split_k == 1 &&
+                        p.num_kb <= 4;
+    int stage = 0, pg = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      if (res_pf) {
+        const int nxt = tile + 2 * (int)gridDim.x;
+        if (nxt < num_tiles) {
+          const int mb = nxt / p.tiles_n, nb = nxt - mb * p.tiles_n;
+          const int c0 = nb * p.block_n;
+          const int nbytes = min(p.block_n, p.N - c0) * 2;
+          for (int r = lane; r < p.m_stride; r += 32) {
+            const long long row = (long long)mb * p.m_stride + r;
+            if (row < p.M) {
+              const char* src = reinterpret_cast<const char*>(p.res_16 + row * p.ld_res + c0);
+              for (int b = 0; b < nbytes; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + b));
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(src + nbytes - 1));   // the row segment may end in one more line
+            }
+          }
+        }
+      }
+      if (lane == 0) {
         const TileCoord tc = decode_tile(p, tile / p.split_k);
         const int split = tile % p.split_k;
         const int kb0 = (int)((long long)split * p.num_kb / p.split_k), kb1 = (int)((long long)(split + 1) * p.num_kb / p.split_k);
@@ -842,6 +864,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
       }
+      __syncwarp();
     }
   } else if (warp == kWarpMma) {
     // ------------------------------------------------------------------ UMMA issuer

@@ -435,14 +435,19 @@ class VideoMAETrack2DSamHead(nn.Module):
                 ops.head_expand(vv, vb, G, nt, H, hd, 1.0)
                 vp = torch.empty(G * J, C, device=dev, dtype=dt)
                 ops.linear(vb, a["o"]["w"], out_16=vp)                                  # V' = W_o[:, head h] v[g,t,h]
+                # new = P (W_o v) + b_o + residual through the grouped K = 48 GEMM, then the 16-bit LayerNorm. (A single kernel
+                # doing both with mma.sync - whole rows per warp and two passes over the columns, or column slices per warp
+                # with the row moments merged through shared memory - was measured in round 2: correct, but 8.7 / 9.1 ms per
+                # window against 8.1-8.3 ms for these two kernels; removed.)
                 vpt = vp.view(G, J, C).transpose(1, 2).contiguous().view(G * C, J)      # per-query [C, J] weight block
                 new16 = torch.empty(G * Pn, C, device=dev, dtype=dt)
                 if keys32 is not None:
                     ops.linear(p2, vpt, bias=a["o"]["b"], res_f32=keys32, res_row_mod=Pn if shared else 0, out_16=new16, group_rows=Pn)
                 else:
                     ops.linear(p2, vpt, bias=a["o"]["b"], res_16=keys16, out_16=new16, group_rows=Pn)
-                keys16 = torch.empty(G * Pn, C, device=dev, dtype=dt)
-                ops.layernorm16(new16, w["n4"][0], w["n4"][1], w["n4"][2], keys16)
+                nk16 = torch.empty(G * Pn, C, device=dev, dtype=dt)
+                ops.layernorm16(new16, w["n4"][0], w["n4"][1], w["n4"][2], nk16)
+                keys16 = nk16
                 keys32 = None
                 shared = False
                 continue

@@ -34,7 +34,8 @@ batch = {k: v.to(dev) for k, v in bench.synth_batch(1).items()}
 
 ORIG = {n: getattr(ops, n) for n in ("layernorm", "linear", "linear_qkv", "attention", "conv3d", "conv_transpose3d", "upsample3d",
                                      "conv_transpose3d_hyper", "token_attention", "image_attention", "layernorm16", "track_readout",
-                                     "cast16", "im2col3", "patchify")}
+                                     "cast16", "im2col3", "patchify", "token_weighted_sum", "row_softmax16", "group_softmax_t16",
+                                     "head_expand", "head_diag_gather")}
 
 
 def rows(t):
@@ -60,6 +61,13 @@ ABL = {
     "trk.layernorm(262144x1408)": ("layernorm", lambda x, *a, **k: rows(x) == 262144),
     "trk.kvq(262144,704,1408)": ("linear", lin(lambda M, N, K: (M, N, K) == (262144, 704, 1408))),
     "trk.outproj(262144,1408,704)": ("linear", lin(lambda M, N, K: (M, N, K) == (262144, 1408, 704))),
+    "trk.fold.scores(6144,2048,1408)": ("linear", lin(lambda M, N, K: M == 6144 and K == 1408 and N in (2048, 128 * 2048))),
+    "trk.fold.small_linear(M=6144)": ("linear", lin(lambda M, N, K: M == 6144 and not (K == 1408 and N in (2048, 128 * 2048)))),
+    "trk.fold.out(262144,1408,48)": ("linear", lin(lambda M, N, K: M == 262144 and K == 48)),
+    "trk.fold.token_weighted_sum": ("token_weighted_sum", lambda *a, **k: True),
+    "trk.fold.softmaxes": ("row_softmax16", lambda *a, **k: True),
+    "trk.fold.group_softmax": ("group_softmax_t16", lambda *a, **k: True),
+    "trk.fold.expand+gather": ("head_expand", lambda *a, **k: True),
     "trk.other_linear(M<=768)": ("linear", lin(lambda M, N, K: M <= 768)),
     "trk.token_attention": ("token_attention", lambda *a, **k: True),
     "trk.image_attention": ("image_attention", lambda *a, **k: True),
@@ -73,7 +81,7 @@ ABL = {
     "dpt.upsample3d": ("upsample3d", lambda *a, **k: True),
     "dpt.convT": ("conv_transpose3d", lambda x, w, *a, **k: x.shape[-1] != 1408),
     "dpt.linear(2048 rows, heads' 1x1)": ("linear", lin(lambda M, N, K: M == 2048 and N <= 1024)),
-    "dpt.linear(other)": ("linear", lin(lambda M, N, K: M not in (2048, 262144) and M > 768)),
+    "dpt.linear(other)": ("linear", lin(lambda M, N, K: M not in (2048, 262144, 6144) and M > 768)),
 }
 
 
