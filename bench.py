@@ -36,6 +36,7 @@ sys.path.insert(0, str(ROOT))
 TASKS = ["flow_2d_backward", "track_2d", "depth", "dyn_mask", "camray"]
 NQ = 128
 ATT_FLOPS_PER_BLOCK_WINDOW = 4 * 2048 * 2048 * 88 * 16  # 23 622 320 128 (unpadded d=88)
+STEP_GFLOP = 23316.6   # one all-heads window in the reference's order of operations (cfg 2, 128 track queries)
 WORKLOAD = ("single 16x224x224 clip per GPU, all heads (flow, depth, dyn-mask, camray pose, 128-query 2D/3D tracks), "
             "shipped config (windowed + joint alignment), BASELINE.json configs[1]")
 REF_ARM_FILES = [Path("/tmp/l4p_reference_arm.json"), ROOT / "gpurun_out" / "reference_arm_last.json"]
@@ -434,6 +435,11 @@ def main():
                             "(double-buffered pinned memory, copy stream); the all-gathered buffer stays on the device"},
             "gpu_launches": m["launches"],
             "clocks": m["clocks"],
+            # the whole step against the tensor roofline: FLOPs of the REFERENCE's order of operations for this workload
+            # (cfg 2: 23 316.6 GF per window; the folded track-head attention executes fewer)
+            "step_roofline": {"reference_algorithmic_gflop": STEP_GFLOP * clips,
+                              "tflops": STEP_GFLOP * clips / m["ms"], "peak": pk["tflops"],
+                              "frac": STEP_GFLOP * clips / m["ms"] / pk["tflops"]},
             "roofline": {"kernel": "attention_kernel (fused QK^T+softmax+PV, tcgen05)", "bound": "tensor", "achieved": ach,
                          "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"],
                          # dram__bytes_read + write per launch of the shipped kernel, from the committed ncu --set full capture

@@ -24,8 +24,9 @@ static GemmKernelFn find_kernel(int epi, bool bf16, bool pair) {
   return nullptr;
 }
 
-// exact compile-time instance for this descriptor, else the run-time-flag instance of its store mode
-static GemmKernelFn select_kernel(const l4p_gemm_desc* d, bool pair) {
+// exact compile-time instance for this descriptor, else the run-time-flag instance of its store mode. `wide` asks for the
+// three-epilogue-warpgroup instance of the same configuration (short-K problems); *epi_out = the configuration found.
+static GemmKernelFn select_kernel(const l4p_gemm_desc* d, bool pair, bool wide = false, int* epi_out = nullptr) {
   int flags = 0, act = d->act;
   if (d->store_mode == L4P_STORE_ROWMAJOR) {
     if (d->res_f32) flags |= EPI_RES32;
@@ -35,8 +36,15 @@ static GemmKernelFn select_kernel(const l4p_gemm_desc* d, bool pair) {
     if (d->out_16_relu) flags |= EPI_OUT16R;
   }
   if (d->store_mode == L4P_STORE_QKV) act = L4P_ACT_NONE;
-  GemmKernelFn fn = find_kernel(epi_make(d->store_mode, act, flags), d->bf16 != 0, pair);
-  if (fn == nullptr) fn = find_kernel(epi_make(d->store_mode, 0, EPI_GENERIC), d->bf16 != 0, pair);
+  int epi = epi_make(d->store_mode, act, flags);
+  GemmKernelFn fn = nullptr;
+  if (wide) {
+    fn = find_kernel(epi | EPI_WIDE3, d->bf16 != 0, pair);
+    if (fn != nullptr) epi |= EPI_WIDE3;
+  }
+  if (fn == nullptr) fn = find_kernel(epi, d->bf16 != 0, pair);
+  if (fn == nullptr) { epi = epi_make(d->store_mode, 0, EPI_GENERIC); fn = find_kernel(epi, d->bf16 != 0, pair); }
+  if (epi_out != nullptr) *epi_out = epi;
   return fn;
 }
 
@@ -355,11 +363,19 @@ extern "C" int l4p_gemm(const l4p_gemm_desc* d, void* stream_) {
     return L4P_OK;
   }
 
-  GemmKernelFn kfn = select_kernel(d, false);
+  // short-K problems (one or two k-blocks per tile: the per-query K = 48 output GEMM of the track head) spend their time in the
+  // epilogue: take the instance with three epilogue warpgroups when this configuration has one
+  int epi_sel = 0;
+  const bool wide = d->store_mode == L4P_STORE_ROWMAJOR && p.num_kb <= 2 && num_tiles >= 4 * grid;
+  GemmKernelFn kfn = select_kernel(d, false, wide, &epi_sel);
   L4P_REQUIRE(kfn != nullptr, L4P_ERR_ARG, "l4p_gemm: no kernel instance for store_mode=%d", d->store_mode);
-  if (t_plan) { *t_plan = GemmPlanOut{p.block_n, 1, 0, p.stages, grid, threads}; return L4P_OK; }
-  L4P_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kRingBudget + 1024 + epi_bytes)));
-  L4P_CHECK_CUDA(launch_pdl(kfn, dim3(grid), dim3(threads), smem, stream, tmA, tmB, p));
+  const int threads1 = gemm_threads(epi_sel);
+  const uint32_t epi_bytes1 = fused_dot ? 0u : (uint32_t)epi_smem_bytes(epi_groups(epi_sel));
+  const size_t smem1 = (size_t)p.stages * stage_bytes + 1024 + epi_bytes1;
+  if (t_plan) { *t_plan = GemmPlanOut{p.block_n, 1, 0, p.stages, grid, threads1}; return L4P_OK; }
+  const size_t attr1 = (epi_sel & EPI_WIDE3) ? smem1 : (size_t)(kRingBudget + 1024 + epi_bytes1);
+  L4P_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attr1));
+  L4P_CHECK_CUDA(launch_pdl(kfn, dim3(grid), dim3(threads1), smem1, stream, tmA, tmB, p));
   return L4P_OK;
 }
 

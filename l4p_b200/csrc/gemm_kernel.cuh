@@ -47,13 +47,17 @@ constexpr int EPI_OUT32 = 1 << 7;
 constexpr int EPI_OUT16 = 1 << 8;
 constexpr int EPI_OUT16R = 1 << 9;   // second 16-bit output = relu(out)
 constexpr int EPI_GENERIC = 1 << 10; // activation and ROWMAJOR options decided at run time (slow, always correct)
+constexpr int EPI_WIDE3 = 1 << 11;   // THREE epilogue warpgroups (512 threads, 128 registers each): for short-K problems, whose time is
+                                     // the epilogue's (tools/outk48_prof.py: ~6 k cycles per 128 x 176 tile with two warpgroups)
 constexpr int kStoreSplitK = 5;      // internal store mode: fp32 atomic accumulation of a K-slice into the split-K workspace
 constexpr int epi_make(int store, int act, int flags) { return store | (act << 3) | flags; }
 constexpr int epi_store(int e) { return e & 7; }
 // Epilogue warpgroups (group g handles column chunks c with c % groups == g). The fused-dot modes are bound by the
 // instruction throughput of their epilogue (GELU + per-row dot products) and need few registers: four groups (640
 // threads); the store modes keep two groups with 200 registers each for the transposed sub-tile and its residuals.
-constexpr int epi_groups(int e) { return (epi_store(e) == L4P_STORE_HEAD1X1 || epi_store(e) == L4P_STORE_HYPER) ? 4 : 2; }
+constexpr int epi_groups(int e) {
+  return (epi_store(e) == L4P_STORE_HEAD1X1 || epi_store(e) == L4P_STORE_HYPER) ? 4 : ((e & EPI_WIDE3) ? 3 : 2);
+}
 constexpr int gemm_threads(int e) { return 128 + 128 * epi_groups(e); }
 constexpr int epi_act(int e) { return (e >> 3) & 3; }
 
@@ -800,31 +804,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (warp == kWarpProducer) {
     // ------------------------------------------------------------------ TMA producer
     if constexpr (kRepartition) asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
-    // Short-K problems with a 16-bit residual (the track head's per-query K = 48 output GEMM: 0.74 GB of residual per launch)
-    // are bound by the epilogue's residual loads: one chunk of prefetch distance keeps 16 KB per SM in flight, 1.5 TB/s at
-    // HBM latency. The otherwise idle lanes of this warp pull the residual tile of the CTA's tile after next into L2 while
-    // lane 0 produces the current one (paced by the __syncwarp at the end of each tile), so the epilogue's loads hit L2.
-    const bool res_pf = p.a_mode == L4P_A_MATRIX && p.store_mode == L4P_STORE_ROWMAJOR && p.res_16 != nullptr && p.split_k == 1 &&
-                        p.num_kb <= 4;
     int stage = 0, pg = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      if (res_pf) {
-        const int nxt = tile + 2 * (int)gridDim.x;
-        if (nxt < num_tiles) {
-          const int mb = nxt / p.tiles_n, nb = nxt - mb * p.tiles_n;
-          const int c0 = nb * p.block_n;
-          const int nbytes = min(p.block_n, p.N - c0) * 2;
-          for (int r = lane; r < p.m_stride; r += 32) {
-            const long long row = (long long)mb * p.m_stride + r;
-            if (row < p.M) {
-              const char* src = reinterpret_cast<const char*>(p.res_16 + row * p.ld_res + c0);
-              for (int b = 0; b < nbytes; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + b));
-              asm volatile("prefetch.global.L2 [%0];" ::"l"(src + nbytes - 1));   // the row segment may end in one more line
-            }
-          }
-        }
-      }
       if (lane == 0) {
         const TileCoord tc = decode_tile(p, tile / p.split_k);
         const int split = tile % p.split_k;

@@ -10,4 +10,6 @@ TAILN=2 T=900 run bench_ref python bench.py --impl reference --steps 20 --warmup
 TAILN=2 T=900 run bench_n1 python bench.py --steps 20 --warmup 5
 T=900 run ncu_launches ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file "$OUT/launches_r2.csv" python bench.py --steps 1 --warmup 3 --no-cpu-baseline --ncu-range --no-graph --skip-configs
 T=400 run ncu_att ncu --set full --clock-control none --import-source on --profile-from-start off -o "$OUT/att_r2" -f python tools/att_ncu.py
+T=400 run ncu_new ncu --set full --clock-control none --import-source on --profile-from-start off -o "$OUT/newk_r2" -f python tools/newkernels_ncu.py
+T=300 run ablate python tools/ablate_step.py
 python -c "import __graft_entry__ as g; g.smoke()" > "$OUT/smoke.log" 2>&1; echo "smoke exit $?"; tail -2 "$OUT/smoke.log"
