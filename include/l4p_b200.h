@@ -114,6 +114,10 @@ typedef struct l4p_gemm_desc {
    * (q W_k^T) x instead of q (W_k x)). */
   int64_t grp_a_rows, grp_b_rows;
   int m_stride;
+  /* A_CONV3D with grouped weights (ROWMAJOR store): the batch axis holds conv_grp_b entries per group (cB = groups *
+   * conv_grp_b); group g convolves with W rows [g*N, (g+1)*N) of a [groups*N, K] weight stack and adds bias[g*N ...]:
+   * the identical layers of several decoder heads (DPT flow / depth / motion-mask heads, dpt_block.py) in ONE launch. */
+  int conv_grp_b;
 } l4p_gemm_desc;
 
 /* Replaces F.linear/addmm (modeling_finetune.py:62-69,171-177,188), the 1x1x1/3x3x3 Conv3d and k==s

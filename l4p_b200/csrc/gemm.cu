@@ -102,6 +102,14 @@ extern "C" int l4p_gemm(const l4p_gemm_desc* d, void* stream_) {
                 d->cCin, d->kT, d->kH, d->kW);
   }
 
+  // grouped convolution (several heads' identical layers in one launch): batch entries per group
+  const bool conv_grouped = d->conv_grp_b > 0;
+  if (conv_grouped) {
+    L4P_REQUIRE(d->a_mode == L4P_A_CONV3D && d->store_mode == L4P_STORE_ROWMAJOR && d->grp_a_rows == 0, L4P_ERR_ARG,
+                "l4p_gemm(grouped conv): conv mode with row-major store only");
+    L4P_REQUIRE(d->cB % d->conv_grp_b == 0 && (int64_t)(d->cB / d->conv_grp_b) * d->N < (1ll << 31), L4P_ERR_SHAPE,
+                "l4p_gemm(grouped conv): cB=%d must be a multiple of conv_grp_b=%d", d->cB, d->conv_grp_b);
+  }
   // grouped weights / tile row stride (see l4p_b200.h): matrix mode, row-major store, 1-CTA kernel, no split-K
   const bool grouped = d->grp_a_rows > 0;
   const int m_stride = d->m_stride > 0 ? d->m_stride : kBlockM;
@@ -122,7 +130,8 @@ extern "C" int l4p_gemm(const l4p_gemm_desc* d, void* stream_) {
   p.N = (int)d->N;
   p.m_stride = m_stride;
   p.grp_a_rows = (int)d->grp_a_rows;
-  p.grp_b_rows = (int)d->grp_b_rows;
+  p.grp_b_rows = conv_grouped ? (int)d->N : (int)d->grp_b_rows;
+  p.conv_grp_b = d->conv_grp_b;
   const long long tm_all = d->a_mode == L4P_A_CONV3D
                                ? (long long)d->cB * ((d->cT + d->bT - 1) / d->bT) * ((d->cH + d->bH - 1) / d->bH) * ((d->cW + d->bW - 1) / d->bW)
                                : (d->M + m_stride - 1) / m_stride;
@@ -198,7 +207,8 @@ extern "C" int l4p_gemm(const l4p_gemm_desc* d, void* stream_) {
   }
   {
     // grouped: W holds one [grp_b_rows, ldw] block per group of A rows
-    const uint64_t w_rows = grouped ? (uint64_t)((d->M + d->grp_a_rows - 1) / d->grp_a_rows) * (uint64_t)d->grp_b_rows : (uint64_t)d->N;
+    const uint64_t w_rows = grouped ? (uint64_t)((d->M + d->grp_a_rows - 1) / d->grp_a_rows) * (uint64_t)d->grp_b_rows
+                            : conv_grouped ? (uint64_t)(d->cB / d->conv_grp_b) * (uint64_t)d->N : (uint64_t)d->N;
     const uint64_t dims[2] = {(uint64_t)d->K, w_rows};
     const uint64_t strides[1] = {(uint64_t)d->ldw * 2};
     const uint32_t box[2] = {kBlockK, (uint32_t)p.block_n};
@@ -316,11 +326,16 @@ extern "C" int l4p_gemm(const l4p_gemm_desc* d, void* stream_) {
   // the pair kernel halves the B traffic per SM: worth it even when it leaves a few pairs idle (M=2048, N=1408: 64 pair
   // tiles on 74 pairs beat 128 single tiles on 148 SMs by 6 % at K=6144, equal at K=1408)
   if (grouped || m_stride != kBlockM) use_pair = -1;
+  // grouped conv: the two 128-row blocks of a pair tile share ONE weight tile, so a pair must not straddle two groups
+  if (conv_grouped && ((long long)d->conv_grp_b * p.ntT * p.ntH * p.ntW) % 2 != 0) {
+    L4P_REQUIRE(use_pair != 1, L4P_ERR_SHAPE, "l4p_gemm(grouped conv): odd tile count per group, the 2-CTA kernel cannot be forced");
+    use_pair = -1;
+  }
   if (use_pair == 0) use_pair = (pair_tiles * 5 >= pairs * 4 && p.block_n >= 64 && p.tiles_m >= 2) ? 1 : -1;
   if (use_pair == 1) {
     L4P_REQUIRE(p.block_n % 32 == 0 || p.block_n % 16 == 0, L4P_ERR_SHAPE, "l4p_gemm(pair): block_n=%d", p.block_n);
     // B tensor map with the half-tile box
-    const uint64_t dims[2] = {(uint64_t)d->K, (uint64_t)d->N};
+    const uint64_t dims[2] = {(uint64_t)d->K, conv_grouped ? (uint64_t)(d->cB / d->conv_grp_b) * (uint64_t)d->N : (uint64_t)d->N};
     const uint64_t strides[1] = {(uint64_t)d->ldw * 2};
     const uint32_t box[2] = {kBlockK, (uint32_t)(p.block_n / 2)};
     rc = t_plan ? L4P_OK : host_make_tmap_16b(&tmB, d->w, 2, dims, strides, box, 128);

@@ -115,6 +115,8 @@ struct GemmKParams {
   int split_k;               // >1: work unit = (tile, k-range); partial sums are atomically added to splitk_ws [M,N] fp32
   float* splitk_ws;
   int a_halo;                // 2-CTA conv mode, 3x3 in-plane filter: one A box with bH+2 lines per (dt, dw, channel block) serves the 3 dh taps
+  int conv_grp_b;            // conv mode, grouped weights: batch entries per group (0 = one shared W); group = b / conv_grp_b owns W rows
+                             // [group * grp_b_rows, ...) and bias [group * N, ...): several heads' identical layers in one launch
   int m_stride;              // matrix mode: rows between consecutive M tiles = rows stored per tile (128 unless grouped)
   int grp_a_rows, grp_b_rows;  // grouped weights: tile rows / grp_a_rows = group, its W block starts at row group * grp_b_rows
   long long* prof;           // optional [3][512] clock64 timeline of CTA 0
@@ -225,7 +227,12 @@ L4P_DEVICE void apply_act2_rt(float& a, float& b, int act) {
 template <bool BF16>
 L4P_DEVICE void splitk_finalize4(const GemmKParams& p, const long long row, const int col, float4 x) {
   if (p.bias != nullptr) {
-    const float4 b4 = *reinterpret_cast<const float4*>(p.bias + col);
+    int bg = 0;
+    if (p.conv_grp_b > 0) {   // grouped conv: the row's batch entry selects the bias vector
+      const long long vox = (long long)p.cT * p.cH * p.cW;
+      bg = (int)((row / vox) / p.conv_grp_b) * p.N;
+    }
+    const float4 b4 = *reinterpret_cast<const float4*>(p.bias + bg + col);
     x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
   }
   apply_act2_rt(x.x, x.y, p.act);
@@ -258,6 +265,16 @@ struct DotShared {
   float part[kMaxEpiGroups][8][128];       // partial dot products [warpgroup][channel][row] (conflict-free both ways)
 };
 struct DotSharedNone { int unused; };
+
+// grouped weights: index of the weight block / bias vector this tile uses
+L4P_DEVICE int tile_group(const GemmKParams& p, const TileCoord& tc) {
+  if (p.a_mode == L4P_A_CONV3D) {
+    if (p.conv_grp_b <= 0) return 0;
+    const int g = tc.b / p.conv_grp_b, gmax = (p.cB - 1) / p.conv_grp_b;   // the padding block of an odd tile count lies beyond cB
+    return g < gmax ? g : gmax;
+  }
+  return p.grp_a_rows > 0 ? (int)(((long long)tc.m_blk * p.m_stride) / p.grp_a_rows) : 0;
+}
 
 struct RowInfo {
   long long row;  // logical output row
@@ -491,6 +508,7 @@ L4P_DEVICE void epilogue_tile(const GemmKParams& p, const TileCoord& tc, const i
       okm |= (__shfl_sync(0xffffffffu, row_ok ? 1u : 0u, src) & 1u) << it;
     }
     const int ncols = min(p.block_n, p.N - n0);  // valid columns of this tile
+    const int bias_grp = p.conv_grp_b > 0 ? tile_group(p, tc) * p.N : 0;   // grouped conv: one bias vector per group
     const int D = p.heads * p.head_dim;
     const int ld_out = p.ld_out, ld_res = p.ld_res;
     const float* const res_f32 = p.res_f32;
@@ -603,7 +621,7 @@ L4P_DEVICE void epilogue_tile(const GemmKParams& p, const TileCoord& tc, const i
       const bool cok = colg < ncols;
       const int col = n0 + colg;
       float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (p.bias != nullptr && cok) b4 = *reinterpret_cast<const float4*>(p.bias + col);
+      if (p.bias != nullptr && cok) b4 = *reinterpret_cast<const float4*>(p.bias + bias_grp + col);
 
       // per-lane column decode of the scatter modes (the 4-column group never straddles a head / tap: both are
       // multiples of 8 wide)
@@ -812,8 +830,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int split = tile % p.split_k;
         const int kb0 = (int)((long long)split * p.num_kb / p.split_k), kb1 = (int)((long long)(split + 1) * p.num_kb / p.split_k);
         // grouped weights: this tile's group owns W rows [group * grp_b_rows, ...)
-        const int n0 = tc.n_blk * p.block_n +
-                       (p.grp_a_rows > 0 ? (int)(((long long)tc.m_blk * p.m_stride) / p.grp_a_rows) * p.grp_b_rows : 0);
+        const int n0 = tc.n_blk * p.block_n + tile_group(p, tc) * p.grp_b_rows;
         // filter-tap walk (cb fastest, then dw, dh, dt) kept as counters: no divisions in the single-thread hot loop
         int cb = 0, dw = -(p.kW / 2), dh = -(p.kH / 2), dt = -(p.kT / 2);
         if (p.a_mode == L4P_A_CONV3D && kb0 > 0) {
@@ -1007,7 +1024,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
         const int n_blk = tile % p.tiles_n;
         const TileCoord tc = decode_block(p, (tile / p.tiles_n) * 2 + (int)rank, n_blk);
-        const int n0 = n_blk * p.block_n + (int)(rank * half_n);
+        const int n0 = n_blk * p.block_n + (int)(rank * half_n) + tile_group(p, tc) * p.grp_b_rows;
         if (p.a_halo) {
           // Line-halo stages: A = the tile's voxel box grown by one line above and below (bH + 2 lines, shifted by dw in W and dt
           // in T), B = the weights of the three taps (dt, -1..1, dw) of one 64-channel block. The three dh taps read the SAME

@@ -47,7 +47,7 @@ class GemmDesc(C.Structure):
         ("cta_pair", C.c_int),
         ("prof", C.c_void_p),
         ("splitk_ws", C.c_void_p), ("splitk_ws_bytes", C.c_int64), ("split_k", C.c_int),
-        ("grp_a_rows", C.c_int64), ("grp_b_rows", C.c_int64), ("m_stride", C.c_int),
+        ("grp_a_rows", C.c_int64), ("grp_b_rows", C.c_int64), ("m_stride", C.c_int), ("conv_grp_b", C.c_int),
     ]
 
 

@@ -114,6 +114,25 @@ class L4P_VideoMAE(torch.nn.Module):
             per_window.append([None if f is None else f[sl] for f in batched])
         return batched, per_window
 
+    group_dense_heads = __import__("os").environ.get("L4P_DPT_GROUP", "1") == "1"
+
+    def _dense_group(self, tasks, batched, shard):
+        """Heads of `tasks` whose DPT decoders can run as one group on the batched encoder result (>= 2 of them), else []."""
+        if not self.group_dense_heads or batched is None or shard is not None:
+            return []
+        from .task_heads.dense_heads import VideoMAEFlowDPTHead
+        rows = next(f for f in batched if f is not None).shape[0]
+        if self.max_windows_per_pass and rows > self.max_windows_per_pass:
+            return []
+        by_sig = {}
+        for t in tasks:
+            h = self.task_heads[t] if t in self.task_heads else None
+            if isinstance(h, VideoMAEFlowDPTHead) and type(h)._run_dpt is VideoMAEFlowDPTHead._run_dpt and hasattr(h.task_head, "dpt"):
+                sig = (h.task_head.dpt.group_signature(), tuple(h.hooks_idx), h.compute_dtype)
+                by_sig.setdefault(sig, []).append(h)
+        best = max(by_sig.values(), key=len, default=[])
+        return best if len(best) >= 2 else []
+
     def _run_jobs(self, jobs, device):
         if not self.parallel_heads or len(jobs) < 2 or device.type != "cuda":
             return [j() for j in jobs]
@@ -193,6 +212,27 @@ class L4P_VideoMAE(torch.nn.Module):
             return {k: torch.cat([o[k] for o in per_clip], dim=0) for k in per_clip[0]}
 
         jobs = []
+        # Dense heads whose DPT decoders share one architecture and read the same taps (flow / depth / motion mask in the shipped
+        # config) run their decoders as ONE grouped launch sequence (dpt.forward_grouped) in a job of its own, enqueued first;
+        # the heads' own jobs pick the result up behind a CUDA event (VideoMAEFlowDPTHead._run_dpt). Only when the whole batch
+        # of windows is decoded in a single pass (no window sharding, rows <= max_windows_per_pass).
+        group = self._dense_group(tasks, batched, shard)
+        if group:
+            def dense_group_job(group=group):
+                from .task_heads.dense_heads import _taps16
+                from .task_heads.dpt import forward_grouped
+                h0 = group[0]
+                img_info = tuple(self.window_size)
+                taps, rows = _taps16(batched, h0.hooks_idx, h0.compute_dtype)
+                outs = forward_grouped([h.task_head.dpt for h in group], taps, rows, img_info, exp_outs=[h._exp_out for h in group])
+                evt = None
+                if outs[0].is_cuda:       # (the CPU stand-in of the host tests runs the jobs in order on one thread)
+                    evt = torch.cuda.Event()
+                    evt.record()
+                for h, o in zip(group, outs):
+                    h._dpt_pre = (id(batched), o, evt, img_info)
+                return {}
+            jobs.append(dense_group_job)
         joint_alignment_possible = "depth" in tasks and "camray" in tasks
         if self.joint_alignment and joint_alignment_possible:
             for task in ["track_2d", "dyn_mask", "flow_2d_backward"]:
@@ -204,6 +244,10 @@ class L4P_VideoMAE(torch.nn.Module):
                 print("Joint alignment is not possible as depth or camray tasks are not present")
             for task in tasks:
                 jobs.append(lambda task=task: head_job(task))
-        for res in self._run_jobs(jobs, data["rgb_b3thw"].device):
-            out.update(res)
+        try:
+            for res in self._run_jobs(jobs, data["rgb_b3thw"].device):
+                out.update(res)
+        finally:
+            for h in group:
+                h._dpt_pre = None
         return out

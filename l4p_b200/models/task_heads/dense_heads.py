@@ -84,7 +84,19 @@ class VideoMAEFlowDPTHead(nn.Module):
     # hook for subclasses: function fused into the last conv epilogue
     _exp_out = False
 
+    # set by L4P_VideoMAE.forward when this head's DPT ran as part of a group of identical decoders (dpt.forward_grouped):
+    # (id of the feature list it was computed from, output, CUDA event recorded behind it on the group's stream)
+    _dpt_pre = None
+
     def _run_dpt(self, enc_features_bpc_list, img_info) -> torch.Tensor:
+        pre = self._dpt_pre
+        if pre is not None and pre[0] == id(enc_features_bpc_list) and pre[3] == tuple(img_info):
+            if pre[2] is not None:
+                cur = torch.cuda.current_stream(pre[1].device)
+                cur.wait_event(pre[2])
+                if not torch.cuda.is_current_stream_capturing():
+                    pre[1].record_stream(cur)
+            return pre[1]
         taps, B = _taps16(enc_features_bpc_list, self.hooks_idx, self.compute_dtype)
         return self.task_head.dpt(taps, B, tuple(img_info), exp_out=self._exp_out)
 
@@ -165,6 +177,7 @@ class VideoMAEDepthDPTHead(VideoMAEFlowDPTHead):
                          overlap_aligner_type=LstSqAffineAligner if align_type == "affine" else LinearAligner,
                          aligner_kwargs=dict(pre_post_fn=align_window_overlap_fn), device=device)
         self.depth_fn = depth_fn
+        self._exp_out = depth_fn == "exp"   # fused into the last conv's epilogue (also read by the grouped DPT job)
 
     def forward(self, enc_features_bpc_list, img_info: Tuple[int, int, int] = (16, 224, 224), **kwargs):
         self._exp_out = self.depth_fn == "exp"  # fused into the conv epilogue

@@ -156,26 +156,29 @@ class DPTOutputAdapter_fix(nn.Module):
         return pk
 
     # ------------------------------------------------------------------ compute
-    def _rcu(self, w, x, x_relu, extra_res=None, want_relu=True):
+    def _rcu(self, w, x, x_relu, extra_res=None, want_relu=True, groups=1):
         """RCU(x) (+ extra_res): conv2(relu(conv1(relu(x)))) + x. Returns (out, relu(out) or None)."""
         mid = torch.empty_like(x)
-        ops.conv3d(x_relu, w["w1"], ksize=(3, 3, 3), bias=w["b1"], act=_l.ACT_RELU, out_16=mid)
+        ops.conv3d(x_relu, w["w1"], ksize=(3, 3, 3), bias=w["b1"], act=_l.ACT_RELU, out_16=mid, groups=groups)
         out = torch.empty_like(x)
         out_relu = torch.empty_like(x) if want_relu else None
         ops.conv3d(mid, w["w2"], ksize=(3, 3, 3), bias=w["b2"], res_16=x, res2_16=extra_res, out_16=out,
-                   out_16_relu=out_relu)
+                   out_16_relu=out_relu, groups=groups)
         return out, out_relu
 
-    def _fuse(self, w, x0, x0_relu, x1=None, x1_relu=None, crop=None):
+    def _fuse(self, w, x0, x0_relu, x1=None, x1_relu=None, crop=None, groups=1):
         """FeatureFusionBlock_custom.forward (dpt_block.py:210-238) with out_conv commuted before the upsample."""
         if x1 is not None:
-            s, s_relu = self._rcu(w["resConfUnit1"], x1, x1_relu, extra_res=x0)  # s = x0 + RCU1(x1)
+            s, s_relu = self._rcu(w["resConfUnit1"], x1, x1_relu, extra_res=x0, groups=groups)  # s = x0 + RCU1(x1)
         else:
             s, s_relu = x0, x0_relu
-        y, _ = self._rcu(w["resConfUnit2"], s, s_relu, want_relu=False)
+        y, _ = self._rcu(w["resConfUnit2"], s, s_relu, want_relu=False, groups=groups)
         B, T, H, W, C = y.shape
         z = torch.empty_like(y)
-        ops.linear(y.view(-1, C), w["ow"], bias=w["ob"], out_16=z.view(-1, C))
+        if groups > 1:   # per-head 1x1x1 weights and biases: the conv path carries the group of every tile
+            ops.conv3d(y, w["ow"], ksize=(1, 1, 1), bias=w["ob"], out_16=z, groups=groups)
+        else:
+            ops.linear(y.view(-1, C), w["ow"], bias=w["ob"], out_16=z.view(-1, C))
         st, sh, sw = w["scale"]
         osz = (T * st, H * sh, W * sw)
         if osz == (T, H, W):
@@ -191,13 +194,62 @@ class DPTOutputAdapter_fix(nn.Module):
     def forward(self, taps16: Sequence[torch.Tensor], batch: int, image_size: Tuple[int, int, int], *,
                 exp_out: bool = False) -> torch.Tensor:
         """taps16: the four hooked token tensors [B*tokens, C] 16-bit (hook order). Returns fp32 [B,Cout,T',H',W']."""
-        dev, dt = taps16[0].device, taps16[0].dtype
-        pk = self.prepare(dev, dt)
-        T, H, W = image_size
-        nt, nh, nw = T // self.patch_size[0], H // self.patch_size[1], W // self.patch_size[2]
-        B = batch
-        layers, layers_relu = [], []
-        for i in range(4):
+        return forward_grouped([self], taps16, batch, image_size, exp_outs=[exp_out])[0]
+
+    # ------------------------------------------------------------------ several adapters of identical architecture at once
+    def group_signature(self):
+        """Adapters with equal signatures can run as one group (forward_grouped): everything but the output channel count."""
+        return (tuple(self.hooks), tuple(self.layer_dims), self.feature_dim, self.last_dim, self.patch_size,
+                self.actpost_scale_factors, self.fusion_scale_factors, self.output_size,
+                tuple(getattr(self.act_postprocess[i], "0").in_channels for i in range(4)))
+
+
+def _stack_packed(pks):
+    """Weights of the group's adapters stacked along the output-row axis (one block per adapter), biases concatenated, for
+    the layers that run as ONE grouped launch: layer_rn, the four fusion blocks, head1."""
+    cat = lambda key_fn: torch.cat([key_fn(pk) for pk in pks], dim=0).contiguous()
+    g = {"rn": [cat(lambda pk, i=i: pk["act"][i]["rn"]) for i in range(4)], "fusion": []}
+    for j in range(4):
+        d = dict(scale=pks[0]["fusion"][j]["scale"], ow=cat(lambda pk: pk["fusion"][j]["ow"]), ob=cat(lambda pk: pk["fusion"][j]["ob"]))
+        for r in ("resConfUnit1", "resConfUnit2"):
+            d[r] = {k: cat(lambda pk, k=k: pk["fusion"][j][r][k]) for k in ("w1", "b1", "w2", "b2")}
+        g["fusion"].append(d)
+    g["h1w"], g["h1b"] = cat(lambda pk: pk["h1w"]), cat(lambda pk: pk["h1b"])
+    return g
+
+
+@torch.no_grad()
+def forward_grouped(adapters: Sequence[DPTOutputAdapter_fix], taps16: Sequence[torch.Tensor], batch: int,
+                    image_size: Tuple[int, int, int], *, exp_outs: Sequence[bool]):
+    """The DPT decoders of several heads that read the SAME taps and share one architecture (the flow, depth and motion-mask
+    heads of the shipped config: dense_heads.py:20-217) as one launch sequence: every layer between the per-head token
+    projections and the per-head final convolution runs ONCE on the heads' activations stacked along the batch axis, with
+    grouped weights (`ops.conv3d(..., groups=G)`: the tile's batch entry selects the head's weight block and bias). Three heads
+    cost 3 x 38 launches one by one; grouped 38 + 2 x 10, and the low-resolution pyramid levels (2048-16384 voxels per head,
+    split-K territory) become three times larger problems. A single adapter (`forward`) is the G = 1 case of the same code.
+    Returns one fp32 [B, Cout_g, T', H', W'] tensor per adapter."""
+    G = len(adapters)
+    a0 = adapters[0]
+    assert all(a.group_signature() == a0.group_signature() for a in adapters), "forward_grouped: different DPT architectures"
+    dev, dt = taps16[0].device, taps16[0].dtype
+    pks = [a.prepare(dev, dt) for a in adapters]
+    if G == 1:
+        pg = dict(rn=[pks[0]["act"][i]["rn"] for i in range(4)], fusion=pks[0]["fusion"], h1w=pks[0]["h1w"], h1b=pks[0]["h1b"])
+    else:
+        key = tuple(id(pk) for pk in pks)
+        cache = a0.__dict__.setdefault("_group_packed", {})
+        if key not in cache:
+            cache.clear()
+            cache[key] = _stack_packed(pks)
+        pg = cache[key]
+    T, H, W = image_size
+    nt, nh, nw = T // a0.patch_size[0], H // a0.patch_size[1], W // a0.patch_size[2]
+    B = batch
+    GB = G * B
+    layers, layers_relu = [], []
+    for i in range(4):
+        z_all = None
+        for g, pk in enumerate(pks):          # per-head token projection + reassemble op, written into the head's batch slice
             a = pk["act"][i]
             tok = taps16[i]
             c1 = a["w1"].shape[0]
@@ -206,42 +258,55 @@ class DPTOutputAdapter_fix(nn.Module):
             y = y.view(B, nt, nh, nw, c1)
             if a["kind"] == "convT":
                 st, sh, sw = a["stride"]
-                z = torch.empty(B, nt * st, nh * sh, nw * sw, c1, device=dev, dtype=dt)
-                ops.conv_transpose3d(y, a["w2"], a["b2"], a["stride"], z)
+                shape = (nt * st, nh * sh, nw * sw)
             elif a["kind"] == "conv_s":
                 st, sh, sw = a["stride"]
-                To, Ho, Wo = (nt - 1) // st + 1, (nh - 1) // sh + 1, (nw - 1) // sw + 1
-                col = torch.empty(B * To * Ho * Wo, 27 * c1, device=dev, dtype=dt)
+                shape = ((nt - 1) // st + 1, (nh - 1) // sh + 1, (nw - 1) // sw + 1)
+            else:
+                shape = (nt, nh, nw)
+            if a["kind"] == "id" and G == 1:
+                z_all = y
+                continue
+            if z_all is None:
+                z_all = torch.empty(GB, *shape, c1, device=dev, dtype=dt)
+            z = z_all[g * B:(g + 1) * B]
+            if a["kind"] == "convT":
+                ops.conv_transpose3d(y, a["w2"], a["b2"], a["stride"], z)
+            elif a["kind"] == "conv_s":
+                col = torch.empty(B * shape[0] * shape[1] * shape[2], 27 * c1, device=dev, dtype=dt)
                 ops.im2col3(y, col, a["stride"])
-                z = torch.empty(B, To, Ho, Wo, c1, device=dev, dtype=dt)
                 ops.linear(col, a["w2"], bias=a["b2"], out_16=z.view(-1, c1))
             else:
-                z = y
-            l = torch.empty(*z.shape[:4], self.feature_dim, device=dev, dtype=dt)
-            lr = torch.empty_like(l)
-            ops.conv3d(z, a["rn"], ksize=(3, 3, 3), out_16=l, out_16_relu=lr)
-            layers.append(l)
-            layers_relu.append(lr)
-        f1, f2, f3, f4 = pk["fusion"]
-        p4 = self._fuse(f4, layers[3], layers_relu[3], crop=(layers[2].shape[1], layers[2].shape[2]))
-        p3 = self._fuse(f3, p4, None, layers[2], layers_relu[2])
-        p2 = self._fuse(f2, p3, None, layers[1], layers_relu[1])
-        p1 = self._fuse(f1, p2, None, layers[0], layers_relu[0])
-        h1 = torch.empty(*p1.shape[:4], self.feature_dim // 2, device=dev, dtype=dt)
-        ops.conv3d(p1, pk["h1w"], ksize=(3, 3, 3), bias=pk["h1b"], out_16=h1)
-        if self.debug is not None:
-            cf = lambda t: t.float().permute(0, 4, 1, 2, 3)
-            self.debug.update(l0=cf(layers[0]), l1=cf(layers[1]), l2=cf(layers[2]), l3=cf(layers[3]), p4=cf(p4), p3=cf(p3),
-                              p2=cf(p2), p1=cf(p1), h1=cf(h1))
-        osz = tuple(image_size) if self.output_size is None else self.output_size
-        if tuple(h1.shape[1:4]) != osz:
-            r = torch.empty(B, *osz, h1.shape[-1], device=dev, dtype=dt)
-            ops.upsample3d(h1, osz, align_corners=True, y=r)
-            h1 = r
-        out = torch.empty(B, self.num_channels, *osz, device=dev, dtype=torch.float32)
-        ops.conv3d(h1, pk["h2w"], ksize=(3, 3, 3), bias=pk["h2b"], head_w2=pk["h3w"], head_b2=pk["h3b"],
-                   head_exp=exp_out, out_f32=out)
-        return out
+                z.copy_(y)
+        l = torch.empty(*z_all.shape[:4], a0.feature_dim, device=dev, dtype=dt)
+        lr = torch.empty_like(l)
+        ops.conv3d(z_all, pg["rn"][i], ksize=(3, 3, 3), out_16=l, out_16_relu=lr, groups=G)
+        layers.append(l)
+        layers_relu.append(lr)
+    f1, f2, f3, f4 = pg["fusion"]
+    p4 = a0._fuse(f4, layers[3], layers_relu[3], crop=(layers[2].shape[1], layers[2].shape[2]), groups=G)
+    p3 = a0._fuse(f3, p4, None, layers[2], layers_relu[2], groups=G)
+    p2 = a0._fuse(f2, p3, None, layers[1], layers_relu[1], groups=G)
+    p1 = a0._fuse(f1, p2, None, layers[0], layers_relu[0], groups=G)
+    h1 = torch.empty(*p1.shape[:4], a0.feature_dim // 2, device=dev, dtype=dt)
+    ops.conv3d(p1, pg["h1w"], ksize=(3, 3, 3), bias=pg["h1b"], out_16=h1, groups=G)
+    for g, ad in enumerate(adapters):
+        if ad.debug is not None:
+            cf = lambda t: t[g * B:(g + 1) * B].float().permute(0, 4, 1, 2, 3)
+            ad.debug.update(l0=cf(layers[0]), l1=cf(layers[1]), l2=cf(layers[2]), l3=cf(layers[3]), p4=cf(p4), p3=cf(p3),
+                            p2=cf(p2), p1=cf(p1), h1=cf(h1))
+    osz = tuple(image_size) if a0.output_size is None else a0.output_size
+    if tuple(h1.shape[1:4]) != osz:
+        r = torch.empty(GB, *osz, h1.shape[-1], device=dev, dtype=dt)
+        ops.upsample3d(h1, osz, align_corners=True, y=r)
+        h1 = r
+    outs = []
+    for g, (ad, pk) in enumerate(zip(adapters, pks)):   # per-head final convolution: fused ReLU + 1x1x1 (+exp) epilogue
+        out = torch.empty(B, ad.num_channels, *osz, device=dev, dtype=torch.float32)
+        ops.conv3d(h1[g * B:(g + 1) * B], pk["h2w"], ksize=(3, 3, 3), bias=pk["h2b"], head_w2=pk["h3w"], head_b2=pk["h3b"],
+                   head_exp=bool(exp_outs[g]), out_f32=out)
+        outs.append(out)
+    return outs
 
 
 class PixelwiseTaskWithDPT(nn.Module):

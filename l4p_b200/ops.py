@@ -205,15 +205,22 @@ def pick_box(T: int, H: int, W: int) -> Tuple[int, int, int]:
 def conv3d(x: torch.Tensor, w: torch.Tensor, *, ksize: Tuple[int, int, int], bias=None, act=_l.ACT_NONE,
            res_16=None, res2_16=None, out_16=None, out_16_relu=None, out_f32=None,
            head_w2=None, head_b2=None, head_exp=False, block_n: int = 0, cta_pair: int = 0,
-           prof: Optional[torch.Tensor] = None) -> None:
+           prof: Optional[torch.Tensor] = None, groups: int = 1) -> None:
     """K8: stride-1 'same' Conv3d as implicit GEMM.
 
     x channels-last [B,T,H,W,Cin] (16-bit); w [Cout, kT*kH*kW*Cin] with the K axis ordered (kt,kh,kw,cin).
-    With head_w2/head_b2 the epilogue is ReLU -> 1x1x1 conv (+exp) -> out_f32 [B,C2,T,H,W]."""
+    With head_w2/head_b2 the epilogue is ReLU -> 1x1x1 conv (+exp) -> out_f32 [B,C2,T,H,W].
+    groups > 1: the batch axis holds `groups` equal blocks, block g convolves with w[g*Cout:(g+1)*Cout] (w [groups*Cout, K],
+    bias [groups*Cout]): the identical layers of several heads in one launch."""
     d = _base_desc(x, w)
     B, T, H, W, Cin = x.shape
     kT, kH, kW = ksize
     Cout = w.shape[0]
+    if groups > 1:
+        if B % groups or Cout % groups or head_w2 is not None:
+            raise _l.L4PError(f"conv3d(groups={groups}): batch {B} / weight rows {Cout} not divisible, or fused head epilogue")
+        Cout //= groups
+        d.conv_grp_b = B // groups
     if w.shape[1] != kT * kH * kW * Cin:
         raise _l.L4PError(f"conv3d: weight {tuple(w.shape)} vs taps*Cin={kT * kH * kW * Cin}")
     d.M, d.N, d.K = B * T * H * W, Cout, kT * kH * kW * Cin

@@ -119,12 +119,22 @@ def _conv_weight(w_k, ksize, cin):
 
 
 def conv3d(x, w, *, ksize, bias=None, act=ACT_NONE, res_16=None, res2_16=None, out_16=None, out_16_relu=None,
-           out_f32=None, head_w2=None, head_b2=None, head_exp=False, block_n=0, cta_pair=0, prof=None) -> None:
+           out_f32=None, head_w2=None, head_b2=None, head_exp=False, block_n=0, cta_pair=0, prof=None, groups=1) -> None:
     _note("conv3d")
     assert _is16(x) and x.dtype == w.dtype and x.is_contiguous()
     B, T, H, W, Cin = x.shape
     kT, kH, kW = ksize
     assert w.shape[1] == kT * kH * kW * Cin
+    if groups > 1:   # several heads' identical layers in one call: block g of the batch axis with its own weights / bias
+        assert head_w2 is None and B % groups == 0 and w.shape[0] % groups == 0
+        bg, co = B // groups, w.shape[0] // groups
+        sl = lambda t, g, n: None if t is None else t.reshape(groups, -1)[g].reshape(n)
+        for g in range(groups):
+            part = lambda t: None if t is None else t.reshape(groups, bg, *t.shape[1:])[g]
+            conv3d(x[g * bg:(g + 1) * bg].contiguous(), w[g * co:(g + 1) * co].contiguous(), ksize=ksize,
+                   bias=None if bias is None else bias[g * co:(g + 1) * co], act=act, res_16=part(res_16), res2_16=part(res2_16),
+                   out_16=part(out_16), out_16_relu=part(out_16_relu), out_f32=part(out_f32))
+        return
     y = F.conv3d(x.float().permute(0, 4, 1, 2, 3), _conv_weight(w, ksize, Cin), None,
                  padding=(kT // 2, kH // 2, kW // 2)).permute(0, 2, 3, 4, 1)
     acc = y.reshape(-1, w.shape[0])

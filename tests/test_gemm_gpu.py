@@ -421,3 +421,37 @@ def test_conv3d_line_halo_wide(dtype):
     ops.conv3d(x, w, ksize=(3, 3, 3), bias=b, res_16=r1, out_16=o, cta_pair=1)
     torch.cuda.synchronize()
     _close(o, _conv_ref(x, w, (3, 3, 3), b) + r1.float(), 2 ** -8 if dtype == torch.bfloat16 else 2 ** -10)
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("shape,pair", [((2, 2, 16, 32, 64, 64), 0), ((1, 4, 64, 64, 128, 128), 1), ((2, 1, 8, 8, 256, 256), 0),
+                                        ((1, 3, 20, 32, 64, 32), -1)])
+def test_conv3d_grouped_weights(dtype, shape, pair):
+    """Grouped convolution (several heads' identical layers in one launch): G = 3 blocks of the batch axis, each with its own
+    weight block, bias and residual; 1-CTA, 2-CTA (line-halo) and split-K paths."""
+    ops = _ops()
+    G = 3
+    Bg, T, H, W, Cin, Cout = shape
+    x = _rand((G * Bg, T, H, W, Cin), dtype, 51)
+    w = _rand((G * Cout, 27 * Cin), dtype, 52, (27 * Cin) ** -0.5)
+    b = _rand((G * Cout,), torch.float32, 53)
+    r = _rand((G * Bg, T, H, W, Cout), dtype, 54)
+    o = torch.empty(G * Bg, T, H, W, Cout, device="cuda", dtype=dtype)
+    orl = torch.empty_like(o)
+    ops.conv3d(x, w, ksize=(3, 3, 3), bias=b, res_16=r, out_16=o, out_16_relu=orl, groups=G, cta_pair=pair)
+    torch.cuda.synchronize()
+    tol = 2 ** -7 if dtype == torch.bfloat16 else 2 ** -10
+    for g in range(G):
+        sl = slice(g * Bg, (g + 1) * Bg)
+        ref = _conv_ref(x[sl], w[g * Cout:(g + 1) * Cout], (3, 3, 3), b[g * Cout:(g + 1) * Cout]) + r[sl].float()
+        _close(o[sl], ref, tol)
+        _close(orl[sl], ref.clamp_min(0), tol)
+    # 1x1x1 grouped conv (the fusion blocks' out_conv)
+    w1 = _rand((G * Cout, Cin), dtype, 55, Cin ** -0.5)
+    o1 = torch.empty(G * Bg, T, H, W, Cout, device="cuda", dtype=dtype)
+    ops.conv3d(x, w1, ksize=(1, 1, 1), bias=b, out_16=o1, groups=G)
+    torch.cuda.synchronize()
+    for g in range(G):
+        sl = slice(g * Bg, (g + 1) * Bg)
+        ref = x[sl].float() @ w1[g * Cout:(g + 1) * Cout].float().t() + b[g * Cout:(g + 1) * Cout]
+        _close(o1[sl], ref, tol)
