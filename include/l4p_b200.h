@@ -169,12 +169,6 @@ int l4p_token_attention(const float* q, const void* k16, const void* v16, float*
 int l4p_image_attention(const void* q16, const float* k, const float* v, void* out16, int G, int Np, int nk,
                         int H, int d, float scale, int bf16, void* stream);
 
-/* EXPERIMENTAL tensor-core variant of l4p_image_attention (same contract; not yet validated on hardware, opt-in through
- * L4P_IMGATT_TC=1 in the Python layer): per (128 rows, head) S = Q K^T and O = P V run as tcgen05 UMMAs. `ws` is a caller
- * provided device workspace of l4p_image_attention_tc_workspace_bytes(G, H) bytes (padded 16-bit K / V^T operands). */
-int64_t l4p_image_attention_tc_workspace_bytes(int G, int H);
-int l4p_image_attention_tc(const void* q16, const float* k, const float* v, void* out16, void* ws, int64_t ws_bytes, int G,
-                           int Np, int nk, int H, int d, float scale, int bf16, void* stream);
 /* LayerNorm over the channels of 16-bit rows (+GELU): LayerNorm3d + activation of MaskDecoder.output_upscaling
  * (sam/mask_decoder.py:58-66,145-157). */
 int l4p_layernorm16(const void* x16, const float* gamma, const float* beta, void* y16, int64_t rows, int cols,

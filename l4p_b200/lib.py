@@ -73,8 +73,6 @@ _SIGNATURES = {
     "l4p_affine_align_apply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p]),
     "l4p_token_attention": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 5 + [C.c_int64, C.c_float, C.c_int, C.c_void_p]),
     "l4p_image_attention": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 5 + [C.c_float, C.c_int, C.c_void_p]),
-    "l4p_image_attention_tc_workspace_bytes": (C.c_int64, [C.c_int, C.c_int]),
-    "l4p_image_attention_tc": (C.c_int, [C.c_void_p] * 5 + [C.c_int64] + [C.c_int] * 5 + [C.c_float, C.c_int, C.c_void_p]),
     "l4p_layernorm16": (C.c_int, [C.c_void_p] * 4 + [C.c_int64, C.c_int, C.c_float, C.c_int, C.c_int, C.c_void_p]),
     "l4p_head_expand": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p]),
     "l4p_head_diag_gather": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p]),

@@ -85,8 +85,6 @@ SPLITK_WS_BYTES = 8 << 20   # covers M*N*4 of every low-resolution pyramid level
 SPLITK = True
 
 
-IMGATT_TC = __import__("os").environ.get("L4P_IMGATT_TC", "0") == "1"
-_IMGATT_WS: Dict[Tuple[int, int], torch.Tensor] = {}
 
 
 def _splitk_ws(dev: torch.device) -> torch.Tensor:
@@ -400,19 +398,6 @@ def image_attention(q16: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out16: 
     _chk(q16, "q16", sixteen=True); _chk(out16, "out16", sixteen=True); _chk(k, "k", torch.float32); _chk(v, "v", torch.float32)
     Np = q16.shape[0] // G
     Cc = q16.shape[1]
-    if IMGATT_TC:  # experimental tcgen05 formulation (csrc/track_tc.cu), opt-in until validated on hardware
-        L = _l.load()
-        need = int(L.l4p_image_attention_tc_workspace_bytes(G, heads))
-        key = (q16.device.index, _stream() or 0)
-        ws = _IMGATT_WS.get(key)
-        if ws is None or ws.numel() < need:
-            ws = torch.empty(need, device=q16.device, dtype=torch.uint8)
-            _IMGATT_WS[key] = ws
-        _l.check(L.l4p_image_attention_tc(q16.data_ptr(), k.data_ptr(), v.data_ptr(), out16.data_ptr(), ws.data_ptr(), need, G, Np,
-                                          k.shape[1], heads, Cc // heads, float(scale), 1 if q16.dtype == torch.bfloat16 else 0,
-                                          _stream()), "l4p_image_attention_tc")
-        _count(2)
-        return
     _l.check(_l.load().l4p_image_attention(q16.data_ptr(), k.data_ptr(), v.data_ptr(), out16.data_ptr(), G, Np, k.shape[1],
                                            heads, Cc // heads, float(scale), 1 if q16.dtype == torch.bfloat16 else 0,
                                            _stream()), "l4p_image_attention")
