@@ -372,7 +372,11 @@ def main():
             for T in (264, 512):
                 hostv = {k: v.pin_memory() for k, v in synth_batch(1, T, queries=False).items()}
                 step_video = step_video_eager
-                if use_graph and world == 1:   # sharded runs exchange window metadata on the host: eager there
+                # window-sharded runs are captured too when every rank holds at least one window (the exchange is then ONE NCCL
+                # all-gather with no host-side metadata round, l4p_b200/parallel.py); L4P_CFG4_GRAPH=0 keeps them eager
+                nW_ = (T - 16) // 8 + 1
+                graph_ok = world == 1 or (nW_ >= world and -(-nW_ // world) * (world - 1) < nW_ and os.environ.get("L4P_CFG4_GRAPH", "1") != "0")
+                if use_graph and graph_ok:
                     vg = StepGraph(lambda b: {"packed": pack_outputs(model.forward(b, tasks4), keys4, 1)}, hostv, dev, warmup=1)
                     step_video = lambda b, vg=vg: vg(b)["packed"]
                 mv = measure(step_video, hostv, steps=2, warmup=1)

@@ -70,7 +70,11 @@ def gather_window_outputs(local: Sequence[Sequence[torch.Tensor]], shard: Window
     meta = [None]
     if ref is not None:
         meta = [[(tuple(t.shape), t.dtype) for t in ref]]
-    if ref is None or world > 1:
+    # every rank computes the same partition: when ALL ranks hold at least one window, each knows the per-window shapes from
+    # its own outputs and the host-side object exchange (a blocking, pickled collective, not capturable in a CUDA graph) is
+    # skipped; it is only needed when some rank has no window at all (more ranks than windows)
+    all_have = all(cnt > 0 for _, cnt in contiguous_partition(shard.n_windows, world))
+    if world > 1 and not all_have:
         metas = [None] * world
         dist.all_gather_object(metas, meta[0], group=shard.group)
         meta0 = next(m for m in metas if m is not None)
