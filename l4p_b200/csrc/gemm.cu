@@ -137,19 +137,22 @@ extern "C" int l4p_gemm(const l4p_gemm_desc* d, void* stream_) {
                                : (d->M + m_stride - 1) / m_stride;
   p.block_n = d->block_n > 0 ? d->block_n : pick_block_n(d->N, tm_all);
   if (d->block_n <= 0 && d->store_mode == L4P_STORE_HYPER) p.block_n = d->ctCout;  // one tap per tile
-  // Few rows and a short K loop (the track head's token-side GEMMs: M = 128 queries x 6 tokens = 768 rows, K <= 2048): one wave
+  // Few rows and a short K loop (the track head's token-side GEMMs: M = 128 queries x 6 tokens = 768 rows, K <= 2048; the DPT
+  // heads' token projections: M = 2048, N <= 1024): one wave
   // of NARROW tiles - the smallest N tile that still gives every tile its own SM - beats wide tiles cut along K (split-K +
   // finalize kernel): 10.4 vs 17.4 us for 768 x 1408 x 1408, 11.3 vs 21.4 us for 768 x 2048 x 1408 inside a dependent chain
   // (tools/small_gemm_sweep.py). Long-K problems (the low-resolution convolutions, K = 6912+) keep split-K: narrow tiles would
   // re-read A once per N tile.
   bool narrow = false;
   if (d->block_n <= 0 && d->a_mode == L4P_A_MATRIX && d->store_mode == L4P_STORE_ROWMAJOR && !grouped && m_stride == kBlockM &&
-      tm_all <= 12 && (d->K + kBlockK - 1) / kBlockK <= 32 && d->N >= 64) {
+      tm_all <= 16 && (d->K + kBlockK - 1) / kBlockK <= 32 && d->N >= 64) {
     const long long sms = host_num_sms();
     int bn = 32;
     while (bn < 256 && tm_all * ((d->N + bn - 1) / bn) > sms) bn += 16;
-    p.block_n = bn;
-    narrow = true;
+    if (bn <= 128) {   // wider one-wave tiles (M = 2048 with N >= 1408: the encoder GEMMs) are better served by the 2-CTA kernel
+      p.block_n = bn;
+      narrow = true;
+    }
   }
   // split-K decision (needs the tile and k-block counts up front)
   int split_k = 1;

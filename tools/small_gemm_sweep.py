@@ -27,7 +27,8 @@ def timeit(f, n=40):
 
 
 for (M, N, K) in [(768, 1408, 1408), (768, 704, 1408), (768, 1408, 704), (768, 2048, 1408), (768, 1408, 2048), (128, 1408, 1408),
-                  (6144, 1408, 704), (6144, 2048, 704), (6144, 704, 1408)]:
+                  (6144, 1408, 704), (6144, 2048, 704), (6144, 704, 1408),
+                  (2048, 256, 1408), (2048, 512, 1408), (2048, 1024, 1408), (2048, 704, 1408), (4096, 256, 256), (16384, 256, 256)]:
     x = torch.randn(M, K, device=dev).to(dt); w = (torch.randn(N, K, device=dev) * 0.03).to(dt)
     b = torch.zeros(N, device=dev); y = torch.empty(M, N, device=dev)
     row = [f"M={M} N={N} K={K}:"]
