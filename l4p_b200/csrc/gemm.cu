@@ -154,6 +154,17 @@ extern "C" int l4p_gemm(const l4p_gemm_desc* d, void* stream_) {
       narrow = true;
     }
   }
+  // Mid-size 3x3 convolutions (the grouped 8x16x16 / 16x16x16 RefineNet levels: 32..128 row tiles, N = 256): two 128-wide N
+  // tiles through the 2-CTA kernel with line-halo stages beat one 256-wide tile cut along K with a finalize kernel
+  // (tools/small_conv_sweep.py: 8x16x16 256 -> 256 x3: 22.1 vs 32.6 us; 16x16x16: 37.1 vs 42.8 us; 1024 -> 256: 69.9 vs 76.3 us).
+  bool halo_pair_pref = false;
+  if (d->block_n <= 0 && d->cta_pair == 0 && d->a_mode == L4P_A_CONV3D && d->store_mode == L4P_STORE_ROWMAJOR && d->kH == 3 &&
+      d->kW == 3 && d->bT == 1 && d->bH >= 2 && d->bW % 8 == 0 && tm_all >= 32 && tm_all <= 128 && tm_all % 2 == 0 &&
+      d->N >= 256 && d->N % 128 == 0 &&
+      (!conv_grouped || ((long long)d->conv_grp_b * ((d->cT + d->bT - 1) / d->bT) * ((d->cH + d->bH - 1) / d->bH) * ((d->cW + d->bW - 1) / d->bW)) % 2 == 0)) {
+    p.block_n = 128;
+    halo_pair_pref = true;
+  }
   // split-K decision (needs the tile and k-block counts up front)
   int split_k = 1;
   {
@@ -161,7 +172,7 @@ extern "C" int l4p_gemm(const l4p_gemm_desc* d, void* stream_) {
     const long long tiles = tm * ((d->N + p.block_n - 1) / p.block_n);
     const long long nkb = d->a_mode == L4P_A_CONV3D ? (long long)d->kT * d->kH * d->kW * (d->cCin / kBlockK) : (d->K + kBlockK - 1) / kBlockK;
     const bool can = d->store_mode == L4P_STORE_ROWMAJOR && d->splitk_ws != nullptr && d->splitk_ws_bytes >= d->M * d->N * 4 &&
-                     d->split_k != 1 && d->block_n <= 0 && !grouped && m_stride == kBlockM && !narrow;
+                     d->split_k != 1 && d->block_n <= 0 && !grouped && m_stride == kBlockM && !narrow && !halo_pair_pref;
     if (can) {
       if (d->split_k > 1) {
         split_k = d->split_k;
@@ -174,7 +185,7 @@ extern "C" int l4p_gemm(const l4p_gemm_desc* d, void* stream_) {
       if (split_k < 1) split_k = 1;
     }
   }
-  if (d->block_n <= 0 && d->store_mode != L4P_STORE_HEAD1X1 && split_k == 1 && !narrow) {
+  if (d->block_n <= 0 && d->store_mode != L4P_STORE_HEAD1X1 && split_k == 1 && !narrow && !halo_pair_pref) {
     // few output tiles (low-resolution pyramid levels, token-side GEMMs): trade tile width for CTAs so that more
     // than a handful of SMs work on the (long) K loop
     const long long tm = tm_all;
@@ -343,6 +354,7 @@ extern "C" int l4p_gemm(const l4p_gemm_desc* d, void* stream_) {
   // the pair kernel halves the B traffic per SM: worth it even when it leaves a few pairs idle (M=2048, N=1408: 64 pair
   // tiles on 74 pairs beat 128 single tiles on 148 SMs by 6 % at K=6144, equal at K=1408)
   if (grouped || m_stride != kBlockM) use_pair = -1;
+  if (halo_pair_pref) use_pair = 1;
   // grouped conv: the two 128-row blocks of a pair tile share ONE weight tile, so a pair must not straddle two groups
   if (conv_grouped && ((long long)d->conv_grp_b * p.ntT * p.ntH * p.ntW) % 2 != 0) {
     L4P_REQUIRE(use_pair != 1, L4P_ERR_SHAPE, "l4p_gemm(grouped conv): odd tile count per group, the 2-CTA kernel cannot be forced");

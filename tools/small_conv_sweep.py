@@ -38,4 +38,10 @@ for (T, H, W, Cin, Cout) in [(4, 8, 8, 256, 256), (4, 8, 8, 1024, 256), (8, 16, 
     for bn in (0, 64, 128, 256):
         t = timeit(lambda: ops.conv3d(x, w, ksize=(3, 3, 3), bias=b, out_16=y, groups=G, **(dict(block_n=bn) if bn else {})))
         row.append(f"bn={bn or 'auto'} {t:.1f}us ({fl / t / 1e6:.0f} TF/s)")
+    for bn in (128, 256):   # the 2-CTA kernel forced (line-halo stages) where the tile count allows it
+        try:
+            t = timeit(lambda: ops.conv3d(x, w, ksize=(3, 3, 3), bias=b, out_16=y, groups=G, block_n=bn, cta_pair=1))
+            row.append(f"pair bn={bn} {t:.1f}us")
+        except Exception:  # noqa: BLE001
+            row.append(f"pair bn={bn} n/a")
     print("  ".join(row))
