@@ -829,8 +829,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const TileCoord tc = decode_tile(p, tile / p.split_k);
         const int split = tile % p.split_k;
         const int kb0 = (int)((long long)split * p.num_kb / p.split_k), kb1 = (int)((long long)(split + 1) * p.num_kb / p.split_k);
-        // grouped weights: this tile's group owns W rows [group * grp_b_rows, ...)
-        const int n0 = tc.n_blk * p.block_n + tile_group(p, tc) * p.grp_b_rows;
         // filter-tap walk (cb fastest, then dw, dh, dt) kept as counters: no divisions in the single-thread hot loop
         int cb = 0, dw = -(p.kW / 2), dh = -(p.kH / 2), dt = -(p.kT / 2);
         if (p.a_mode == L4P_A_CONV3D && kb0 > 0) {
@@ -844,8 +842,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
           const uint32_t full = smem_u32(&bar_full[stage]);
           const uint32_t sa = smem_base + stage * stage_bytes;
-          const uint32_t sb = sa + kABytes;
-          mbar_expect_tx(full, stage_bytes);
+          mbar_expect_tx(full, stage_bytes);   // the bytes of BOTH operands (the B warp's load may even land first)
           if (p.a_mode == L4P_A_MATRIX) {
             tma_load_2d(sa, &tmA, full, kb * kBlockK, tc.m_blk * p.m_stride);
           } else {
@@ -858,13 +855,35 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               }
             }
           }
-          tma_load_2d(sb, &tmB, full, kb * kBlockK, n0);
           GEMM_STAMP(0, pg); ++pg;
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
       }
       __syncwarp();
     }
+  } else if (warp == kWarpAlloc) {
+    // ------------------------------------------------------------------ TMA producer of the B (weight) operand
+    // One thread needs ~250 cycles per ring iteration for wait + expect_tx + one TMA issue and ~490 with two loads and the tap walk
+    // (tools/ubench/tma_issue_bench.cu, tools/pair_n_sweep.py: every tile width from 64 to 256 took 494 cycles per k-block), which
+    // capped all tiles narrower than 256 columns; the two operands are therefore issued by two warps. Both wait on the same
+    // empty barrier; the A warp arms the full barrier with the bytes of both loads.
+    if constexpr (kRepartition) asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const TileCoord tc = decode_tile(p, tile / p.split_k);
+        const int split = tile % p.split_k;
+        const int kb0 = (int)((long long)split * p.num_kb / p.split_k), kb1 = (int)((long long)(split + 1) * p.num_kb / p.split_k);
+        const int n0 = tc.n_blk * p.block_n + tile_group(p, tc) * p.grp_b_rows;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
+          tma_load_2d(smem_base + stage * stage_bytes + kABytes, &tmB, smem_u32(&bar_full[stage]), kb * kBlockK, n0);
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
   } else if (warp == kWarpMma) {
     // ------------------------------------------------------------------ UMMA issuer
     // whole warp walks the pipeline (warp-uniform control flow), one elected lane issues
@@ -1024,13 +1043,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
         const int n_blk = tile % p.tiles_n;
         const TileCoord tc = decode_block(p, (tile / p.tiles_n) * 2 + (int)rank, n_blk);
-        const int n0 = n_blk * p.block_n + (int)(rank * half_n) + tile_group(p, tc) * p.grp_b_rows;
         if (p.a_halo) {
           // Line-halo stages: A = the tile's voxel box grown by one line above and below (bH + 2 lines, shifted by dw in W and dt
           // in T), B = the weights of the three taps (dt, -1..1, dw) of one 64-channel block. The three dh taps read the SAME
           // A box at line offsets 0 / 1 / 2, so every activation byte crosses the 64 B/clk L2 -> SM port once per dw shift
           // instead of once per tap (9 instead of 27 times): 24 + 3 x 8 KiB per 768 cycles of UMMA instead of 3 x (16 + 8).
-          const uint32_t a_bytes = (uint32_t)((p.bH + 2) * p.bW) * 128u;
           for (int dti = 0; dti < p.kT; ++dti)
             for (int dwi = 0; dwi < 3; ++dwi)
               for (int cb = 0; cb < p.cblocks; ++cb) {
@@ -1039,11 +1056,6 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 const uint32_t sa = smem_base + stage * stage_bytes;
                 if (is_leader) mbar_expect_tx(smem_u32(&bar_full[stage]), 2 * stage_bytes);
                 tma2_load_5d(sa, &tmA, full_leader, cb * kBlockK, tc.w0 + dwi - 1, tc.h0 - 1, tc.t0 + dti - p.kT / 2, tc.b);
-#pragma unroll
-                for (int dhi = 0; dhi < 3; ++dhi) {
-                  const int kb = ((dti * 3 + dhi) * 3 + dwi) * p.cblocks + cb;
-                  tma2_load_2d(sa + a_bytes + (uint32_t)dhi * b_bytes, &tmB, full_leader, kb * kBlockK, n0);
-                }
                 GEMM_STAMP(0, pg); ++pg;
                 if (++stage == p.stages) { stage = 0; phase ^= 1u; }
               }
@@ -1054,7 +1066,6 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
           const uint32_t full_leader = mapa_shared(smem_u32(&bar_full[stage]), 0);
           const uint32_t sa = smem_base + stage * stage_bytes;
-          const uint32_t sb = sa + kABytes;
           if (is_leader) mbar_expect_tx(smem_u32(&bar_full[stage]), 2 * stage_bytes);
           if (p.a_mode == L4P_A_MATRIX) {
             tma2_load_2d(sa, &tmA, full_leader, kb * kBlockK, tc.m_blk * kBlockM);
@@ -1068,12 +1079,46 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               }
             }
           }
-          tma2_load_2d(sb, &tmB, full_leader, kb * kBlockK, n0);
           GEMM_STAMP(0, pg); ++pg;
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
       }
     }
+  } else if (warp == kWarpAlloc) {
+    // ------------------------------------------------------------------ TMA producer of the B operand (both CTAs; see gemm_kernel)
+    if constexpr (kRepartition) asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t a_bytes = p.a_halo ? (uint32_t)((p.bH + 2) * p.bW) * 128u : kABytes;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const int n_blk = tile % p.tiles_n;
+        const TileCoord tc = decode_block(p, (tile / p.tiles_n) * 2 + (int)rank, n_blk);
+        const int n0 = n_blk * p.block_n + (int)(rank * half_n) + tile_group(p, tc) * p.grp_b_rows;
+        if (p.a_halo) {
+          for (int dti = 0; dti < p.kT; ++dti)
+            for (int dwi = 0; dwi < 3; ++dwi)
+              for (int cb = 0; cb < p.cblocks; ++cb) {
+                mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
+                const uint32_t full_leader = mapa_shared(smem_u32(&bar_full[stage]), 0);
+                const uint32_t sb = smem_base + stage * stage_bytes + a_bytes;
+#pragma unroll
+                for (int dhi = 0; dhi < 3; ++dhi) {
+                  const int kb = ((dti * 3 + dhi) * 3 + dwi) * p.cblocks + cb;
+                  tma2_load_2d(sb + (uint32_t)dhi * b_bytes, &tmB, full_leader, kb * kBlockK, n0);
+                }
+                if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+              }
+          continue;
+        }
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
+          tma2_load_2d(smem_base + stage * stage_bytes + a_bytes, &tmB, mapa_shared(smem_u32(&bar_full[stage]), 0), kb * kBlockK, n0);
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
   } else if (warp == kWarpMma) {
     // ------------------------------------------------------------------ UMMA issuer (leader CTA only)
     if constexpr (kRepartition) asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
