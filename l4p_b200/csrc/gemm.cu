@@ -48,31 +48,56 @@ static GemmKernelFn select_kernel(const l4p_gemm_desc* d, bool pair, bool wide =
   return fn;
 }
 
-// N-tile width from a measured cost model (tools/ubench/umma_bench.cu, tools/blockn_sweep.py): one UMMA of width bn costs
-// ~43 + bn/2 cycles (the 128 x 16 A operand is fetched before B streams), a tile costs that per k-step, and the kernel
-// needs ceil(tiles / slots) rounds of tiles (slots = CTA pairs when the problem is large enough for the 2-CTA kernel,
-// else SMs). A ragged last N tile (TMA zero fill + column masking) is fine: 704 = 3 x 240 beats 4 x 176 by 8 %,
-// 4224 = 17 x 256 beats 22 x 192 by 18 %.
-static int pick_block_n(long long N, long long tiles_m) {
+// Matrix mode with K % 64 == 0: ring stages of TWO 64-wide k-blocks per operand. The operand is viewed as [K / 64][rows][64]
+// (the k-block index is the slowest TMA dimension, 128 bytes apart), one 3-D box {64, rows, 2} per operand and stage lands
+// slab-major in shared memory: [rows x 128 B of k-block kb][rows x 128 B of k-block kb + 1]. A box that reaches past the last
+// k-block is zero-filled (odd k-block counts: the issuer skips the second slab). L4P_GEMM_K128=0 disables (A / B runs).
+static bool k128_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("L4P_GEMM_K128");
+    v = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return v != 0;
+}
+static int make_tmap_k128(CUtensorMap* m, const void* base, uint64_t K, uint64_t rows, uint64_t ld_elems, uint32_t box_rows) {
+  const uint64_t dims[3] = {(uint64_t)kBlockK, rows, K / kBlockK};
+  const uint64_t strides[2] = {ld_elems * 2, (uint64_t)kBlockK * 2};
+  const uint32_t box[3] = {kBlockK, box_rows, 2};
+  return host_make_tmap_16b(m, base, 3, dims, strides, box, 128);
+}
+
+// N-tile width from a measured cost model (tools/pair_n_sweep.py, tools/blockn_sweep2.py). With the operands issued by two warps and
+// 128-wide K stages the 2-CTA kernel is tensor-bound down to 96-column tiles: one k-block of a 256 x bn pair tile costs ~2 bn cycles,
+// a tile a fixed ~2300 cycles more (pipeline drain, epilogue hand-over), and the kernel needs ceil(tiles / CTA pairs) rounds of tiles.
+// The 1-CTA kernel (128-row tiles) is L2 -> SM bound: ~480 + 0.4 bn cycles per k-block whatever the width, so it wants the fewest,
+// widest tiles. A ragged last N tile (TMA zero fill + column masking) is fine. Examples at M = 2048: N = 1408 -> 9 x 160 (72 pair
+// tiles on 74 pairs, one round; 8 x 176 costs 10 % more per k-block), N = 6144 -> 26 x 240 (3 rounds like 24 x 256, 6 % cheaper),
+// N = 4224 -> 17 x 256 (2 rounds; 22 x 192 needs 3).
+static int pick_block_n(long long N, long long tiles_m, long long num_kb) {
   if (N <= 128) return (int)((N + 15) / 16 * 16);
   const int sms = host_num_sms();
   const int cands[] = {256, 240, 224, 208, 192, 176, 160, 144, 128};
   int dflt = 256;  // the widest tile that divides N ...
   for (int c : cands)
     if (N % c == 0) { dflt = c; break; }
+  auto is_pair = [&](int c) {
+    const long long pair_tiles = ((tiles_m + 1) / 2) * ((N + c - 1) / c);
+    return pair_tiles * 5 >= (sms / 2) * 4 && tiles_m >= 2;   // same rule as the kernel choice below
+  };
   auto cost = [&](int c) {
     const long long tn = (N + c - 1) / c;
     const long long pair_tiles = ((tiles_m + 1) / 2) * tn;
-    const bool pair = pair_tiles * 5 >= (sms / 2) * 4 && tiles_m >= 2;   // same rule as the kernel choice below
-    const long long rounds = pair ? (pair_tiles + sms / 2 - 1) / (sms / 2) : (tiles_m * tn + sms - 1) / sms;
-    return (double)rounds * (43.0 + 0.5 * c);
+    const bool pair = is_pair(c);
+    if (pair) return (double)((pair_tiles + sms / 2 - 1) / (sms / 2)) * (2.0 * c * (double)num_kb + 2300.0);
+    return (double)((tiles_m * tn + sms - 1) / sms) * ((480.0 + 0.4 * c) * (double)num_kb + 2300.0);
   };
-  // ... unless a WIDER (ragged) tiling is predicted >= 3 % cheaper. Narrower alternatives are not considered: 9 x 160 for
-  // N = 1408 is predicted 6 % faster than 8 x 176 and measured 30 % slower.
+  // ... unless another (ragged) tiling is predicted >= 3 % cheaper (narrower tiles only for the 2-CTA kernel: small problems on
+  // the 1-CTA kernel keep their tile count, which the split-K and narrow-tile rules below are tuned on)
   int best = dflt;
   double best_cost = cost(dflt) * 0.97;
   for (int c : cands) {
-    if (c <= dflt) break;
+    if (c == dflt || (c < dflt && !is_pair(c))) continue;
     const double k = cost(c);
     if (k < best_cost) { best_cost = k; best = c; }
   }
@@ -135,7 +160,7 @@ extern "C" int l4p_gemm(const l4p_gemm_desc* d, void* stream_) {
   const long long tm_all = d->a_mode == L4P_A_CONV3D
                                ? (long long)d->cB * ((d->cT + d->bT - 1) / d->bT) * ((d->cH + d->bH - 1) / d->bH) * ((d->cW + d->bW - 1) / d->bW)
                                : (d->M + m_stride - 1) / m_stride;
-  p.block_n = d->block_n > 0 ? d->block_n : pick_block_n(d->N, tm_all);
+  p.block_n = d->block_n > 0 ? d->block_n : pick_block_n(d->N, tm_all, (d->K + kBlockK - 1) / kBlockK);
   if (d->block_n <= 0 && d->store_mode == L4P_STORE_HYPER) p.block_n = d->ctCout;  // one tap per tile
   // Few rows and a short K loop (the track head's token-side GEMMs: M = 128 queries x 6 tokens = 768 rows, K <= 2048; the DPT
   // heads' token projections: M = 2048, N <= 1024): one wave
@@ -390,8 +415,21 @@ extern "C" int l4p_gemm(const l4p_gemm_desc* d, void* stream_) {
       rc = t_plan ? L4P_OK : host_make_tmap_16b(&tmA, d->a, 5, dimsA, stridesA, boxA, 128);
       if (rc != L4P_OK) return rc;
     }
-    const uint32_t sb2 = halo ? halo_a + 3u * (uint32_t)(p.block_n / 2) * 128u : kABytes + (uint32_t)(p.block_n / 2) * 128u;
-    const int nst2 = halo ? d->kT * 3 * p.cblocks : p.num_kb;   // ring iterations per tile
+    uint32_t sb2 = halo ? halo_a + 3u * (uint32_t)(p.block_n / 2) * 128u : kABytes + (uint32_t)(p.block_n / 2) * 128u;
+    int nst2 = halo ? d->kT * 3 * p.cblocks : p.num_kb;   // ring iterations per tile
+    // two k-blocks per stage when three such stages fit (tiles up to 256 x 208): the producer / issuer threads then keep up with
+    // tiles narrower than 256 columns (fc2 / proj at N = 176: 407 -> 352 cycles per k-block)
+    if (k128_enabled() && d->a_mode == L4P_A_MATRIX && d->K % kBlockK == 0 && p.num_kb >= 4 && 3u * 2u * sb2 <= kRingBudget) {
+      p.k128 = 1;
+      sb2 *= 2;
+      nst2 = (p.num_kb + 1) / 2;
+      if (!t_plan) {
+        rc = make_tmap_k128(&tmA, d->a, (uint64_t)d->K, (uint64_t)d->M, (uint64_t)d->lda, kBlockM);
+        if (rc != L4P_OK) return rc;
+        rc = make_tmap_k128(&tmB, d->w, (uint64_t)d->K, (uint64_t)d->N, (uint64_t)d->ldw, (uint32_t)(p.block_n / 2));
+        if (rc != L4P_OK) return rc;
+      }
+    }
     int st2 = (int)(kRingBudget / sb2);
     if (st2 > kMaxStages) st2 = kMaxStages;
     if (st2 > nst2) st2 = nst2 < 2 ? 2 : nst2;
@@ -409,13 +447,30 @@ extern "C" int l4p_gemm(const l4p_gemm_desc* d, void* stream_) {
 
   // short-K problems (one or two k-blocks per tile: the per-query K = 48 output GEMM of the track head) spend their time in the
   // epilogue: take the instance with three epilogue warpgroups when this configuration has one
+  uint32_t stage_bytes1 = stage_bytes;
+  if (k128_enabled() && d->a_mode == L4P_A_MATRIX && d->K % kBlockK == 0 && p.num_kb >= 4 && 3u * 2u * stage_bytes <= kRingBudget) {
+    p.k128 = 1;
+    stage_bytes1 = 2 * stage_bytes;
+    int st = (int)(kRingBudget / stage_bytes1);
+    const int nst = (p.num_kb + 1) / 2;
+    if (st > kMaxStages) st = kMaxStages;
+    if (st > nst) st = nst;
+    p.stages = st;
+    if (!t_plan) {
+      const uint64_t w_rows = grouped ? (uint64_t)((d->M + d->grp_a_rows - 1) / d->grp_a_rows) * (uint64_t)d->grp_b_rows : (uint64_t)d->N;
+      rc = make_tmap_k128(&tmA, d->a, (uint64_t)d->K, (uint64_t)d->M, (uint64_t)d->lda, kBlockM);
+      if (rc != L4P_OK) return rc;
+      rc = make_tmap_k128(&tmB, d->w, (uint64_t)d->K, w_rows, (uint64_t)d->ldw, (uint32_t)p.block_n);
+      if (rc != L4P_OK) return rc;
+    }
+  }
   int epi_sel = 0;
   const bool wide = d->store_mode == L4P_STORE_ROWMAJOR && p.num_kb <= 2 && num_tiles >= 4 * grid;
   GemmKernelFn kfn = select_kernel(d, false, wide, &epi_sel);
   L4P_REQUIRE(kfn != nullptr, L4P_ERR_ARG, "l4p_gemm: no kernel instance for store_mode=%d", d->store_mode);
   const int threads1 = gemm_threads(epi_sel);
   const uint32_t epi_bytes1 = fused_dot ? 0u : (uint32_t)epi_smem_bytes(epi_groups(epi_sel));
-  const size_t smem1 = (size_t)p.stages * stage_bytes + 1024 + epi_bytes1;
+  const size_t smem1 = (size_t)p.stages * stage_bytes1 + 1024 + epi_bytes1;
   if (t_plan) { *t_plan = GemmPlanOut{p.block_n, 1, 0, p.stages, grid, threads1}; return L4P_OK; }
   const size_t attr1 = (epi_sel & EPI_WIDE3) ? smem1 : (size_t)(kRingBudget + 1024 + epi_bytes1);
   L4P_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attr1));

@@ -114,6 +114,8 @@ struct GemmKParams {
   FastDiv fd_bW, fd_bH;                 // HEAD1X1 finalisation: row in tile -> (tl,hl,wl)
   int split_k;               // >1: work unit = (tile, k-range); partial sums are atomically added to splitk_ws [M,N] fp32
   float* splitk_ws;
+  int k128;                  // matrix mode: one ring stage holds TWO 64-wide k-blocks per operand (one 3-D TMA box each, slab-major): halves the
+                             // per-k-block cost of the single-thread producer / issuer loops (tools/pair_n_sweep.py)
   int a_halo;                // 2-CTA conv mode, 3x3 in-plane filter: one A box with bH+2 lines per (dt, dw, channel block) serves the 3 dh taps
   int conv_grp_b;            // conv mode, grouped weights: batch entries per group (0 = one shared W); group = b / conv_grp_b owns W rows
                              // [group * grp_b_rows, ...) and bias [group * N, ...): several heads' identical layers in one launch
@@ -785,7 +787,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t b_bytes = (uint32_t)p.block_n * 128u;
-  const uint32_t stage_bytes = kABytes + b_bytes;
+  const uint32_t kslabs = p.k128 ? 2u : 1u;
+  const uint32_t stage_bytes = kslabs * (kABytes + b_bytes);   // [A slab 0][A slab 1][B slab 0][B slab 1]
   const int num_tiles = p.tiles_m * p.tiles_n * p.split_k;  // work units: (tile, K slice); split_k == 1 outside split-K mode
 
   if (threadIdx.x == 0) {
@@ -838,6 +841,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           dh = (tapi / p.kW) % p.kH - p.kH / 2;
           dt = tapi / (p.kW * p.kH) - p.kT / 2;
         }
+        if (p.k128) {   // matrix mode, two k-blocks per stage (split_k == 1)
+          for (int kb = 0; kb < p.num_kb; kb += 2) {
+            mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
+            const uint32_t full = smem_u32(&bar_full[stage]);
+            mbar_expect_tx(full, stage_bytes);
+            tma_load_3d(smem_base + stage * stage_bytes, &tmA, full, 0, tc.m_blk * p.m_stride, kb);
+            GEMM_STAMP(0, pg); ++pg;
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+          }
+        } else
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
           const uint32_t full = smem_u32(&bar_full[stage]);
@@ -876,6 +889,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int split = tile % p.split_k;
         const int kb0 = (int)((long long)split * p.num_kb / p.split_k), kb1 = (int)((long long)(split + 1) * p.num_kb / p.split_k);
         const int n0 = tc.n_blk * p.block_n + tile_group(p, tc) * p.grp_b_rows;
+        if (p.k128) {
+          for (int kb = 0; kb < p.num_kb; kb += 2) {
+            mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
+            tma_load_3d(smem_base + stage * stage_bytes + 2 * kABytes, &tmB, smem_u32(&bar_full[stage]), 0, n0, kb);
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+          }
+        } else
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
           tma_load_2d(smem_base + stage * stage_bytes + kABytes, &tmB, smem_u32(&bar_full[stage]), kb * kBlockK, n0);
@@ -891,7 +911,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const bool leader = elect_one();
     const uint32_t idesc = umma_idesc_f16(BF16, kBlockM, (uint32_t)p.block_n);
     constexpr uint32_t hi128 = umma_desc_hi(128, 2);
-    const uint32_t a_lo0 = umma_desc_lo(smem_base), b_lo0 = umma_desc_lo(smem_base + kABytes);
+    const uint32_t a_lo0 = umma_desc_lo(smem_base), b_lo0 = umma_desc_lo(smem_base + kslabs * kABytes);
     const uint32_t stage_step = stage_bytes >> 4;
     int stage = 0, mg = 0;
     uint32_t phase = 0;
@@ -903,6 +923,31 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const uint32_t d_tmem = tmem_base + (uint32_t)acc * kAccCols;
       const int split = tile % p.split_k;
       const int kb0 = (int)((long long)split * p.num_kb / p.split_k), kb1 = (int)((long long)(split + 1) * p.num_kb / p.split_k);
+      if (p.k128) {
+        // two k-blocks per stage: slab 1 sits one A tile / one B tile behind slab 0; an odd tail stage holds one valid slab
+        for (int kb = 0; kb < p.num_kb; kb += 2) {
+          mbar_wait(smem_u32(&bar_full[stage]), phase);
+          tc_fence_after();
+          if (leader) {
+            GEMM_STAMP(1, mg);
+            const uint32_t a_lo = a_lo0 + (uint32_t)stage * stage_step, b_lo = b_lo0 + (uint32_t)stage * stage_step;
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k)
+              umma_ss(d_tmem, umma_desc_make(a_lo + 2 * k, hi128), umma_desc_make(b_lo + 2 * k, hi128), idesc, (kb | k) != 0 ? 1u : 0u);
+            if (kb + 1 < p.num_kb) {
+              const uint32_t a_l1 = a_lo + (kABytes >> 4), b_l1 = b_lo + (b_bytes >> 4);
+#pragma unroll
+              for (int k = 0; k < kBlockK / 16; ++k)
+                umma_ss(d_tmem, umma_desc_make(a_l1 + 2 * k, hi128), umma_desc_make(b_l1 + 2 * k, hi128), idesc, 1u);
+            }
+            umma_commit(smem_u32(&bar_empty[stage]));
+            if (kb + 2 >= p.num_kb) umma_commit(smem_u32(&bar_tfull[acc]));
+          }
+          __syncwarp();
+          ++mg;
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        }
+      } else
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(smem_u32(&bar_full[stage]), phase);
         tc_fence_after();
@@ -998,7 +1043,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t half_n = (uint32_t)p.block_n / 2;
   const uint32_t b_bytes = half_n * 128u;
-  const uint32_t stage_bytes = p.a_halo ? (uint32_t)((p.bH + 2) * p.bW) * 128u + 3u * b_bytes : kABytes + b_bytes;
+  const uint32_t kslabs = p.k128 ? 2u : 1u;
+  const uint32_t stage_bytes = p.a_halo ? (uint32_t)((p.bH + 2) * p.bW) * 128u + 3u * b_bytes : kslabs * (kABytes + b_bytes);
   const int tiles_m2 = (p.tiles_m + 1) / 2;
   const int num_tiles = tiles_m2 * p.tiles_n;
   const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
@@ -1061,6 +1107,16 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               }
           continue;
         }
+        if (p.k128) {   // matrix mode, two k-blocks per stage
+          for (int kb = 0; kb < p.num_kb; kb += 2) {
+            mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
+            if (is_leader) mbar_expect_tx(smem_u32(&bar_full[stage]), 2 * stage_bytes);
+            tma2_load_3d(smem_base + stage * stage_bytes, &tmA, mapa_shared(smem_u32(&bar_full[stage]), 0), 0, tc.m_blk * kBlockM, kb);
+            GEMM_STAMP(0, pg); ++pg;
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+          }
+          continue;
+        }
         int cb = 0, dw = -(p.kW / 2), dh = -(p.kH / 2), dt = -(p.kT / 2);
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
@@ -1111,6 +1167,14 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               }
           continue;
         }
+        if (p.k128) {
+          for (int kb = 0; kb < p.num_kb; kb += 2) {
+            mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
+            tma2_load_3d(smem_base + stage * stage_bytes + 2 * kABytes, &tmB, mapa_shared(smem_u32(&bar_full[stage]), 0), 0, n0, kb);
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+          }
+          continue;
+        }
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
           tma2_load_2d(smem_base + stage * stage_bytes + a_bytes, &tmB, mapa_shared(smem_u32(&bar_full[stage]), 0), kb * kBlockK, n0);
@@ -1126,7 +1190,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const bool leader_lane = elect_one();
       const uint32_t idesc = umma_idesc_f16(BF16, 2 * kBlockM, (uint32_t)p.block_n);
       constexpr uint32_t hi128 = umma_desc_hi(128, 2);
-      const uint32_t a_lo0 = umma_desc_lo(smem_base), b_lo0 = umma_desc_lo(smem_base + kABytes);
+      const uint32_t a_lo0 = umma_desc_lo(smem_base), b_lo0 = umma_desc_lo(smem_base + kslabs * kABytes);
       const uint32_t stage_step = stage_bytes >> 4;
       int stage = 0, mg = 0;
       uint32_t phase = 0;
@@ -1157,6 +1221,32 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               }
               umma2_commit_mc(smem_u32(&bar_empty[stage]), 3);
               if (st == nst - 1) umma2_commit_mc(smem_u32(&bar_tfull[acc]), 3);
+            }
+            __syncwarp();
+            ++mg;
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+          }
+          if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+          continue;
+        }
+        if (p.k128) {
+          for (int kb = 0; kb < p.num_kb; kb += 2) {
+            mbar_wait(smem_u32(&bar_full[stage]), phase);
+            tc_fence_after();
+            if (leader_lane) {
+              GEMM_STAMP(1, mg);
+              const uint32_t a_lo = a_lo0 + (uint32_t)stage * stage_step, b_lo = b_lo0 + (uint32_t)stage * stage_step;
+#pragma unroll
+              for (int k = 0; k < kBlockK / 16; ++k)
+                umma2_ss(d_tmem, umma_desc_make(a_lo + 2 * k, hi128), umma_desc_make(b_lo + 2 * k, hi128), idesc, (kb | k) != 0 ? 1u : 0u);
+              if (kb + 1 < p.num_kb) {
+                const uint32_t a_l1 = a_lo + (kABytes >> 4), b_l1 = b_lo + (b_bytes >> 4);
+#pragma unroll
+                for (int k = 0; k < kBlockK / 16; ++k)
+                  umma2_ss(d_tmem, umma_desc_make(a_l1 + 2 * k, hi128), umma_desc_make(b_l1 + 2 * k, hi128), idesc, 1u);
+              }
+              umma2_commit_mc(smem_u32(&bar_empty[stage]), 3);
+              if (kb + 2 >= p.num_kb) umma2_commit_mc(smem_u32(&bar_tfull[acc]), 3);
             }
             __syncwarp();
             ++mg;

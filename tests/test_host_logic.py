@@ -133,9 +133,11 @@ def test_gemm_plan_tile_selection():
     from l4p_b200 import lib
     # encoder at one clip (M = 2048)
     fc1 = _plan(M=2048, N=6144, K=1408)
-    assert fc1["block_n"] == 256 and fc1["pair"] == 1 and fc1["grid"] == 148 and fc1["threads"] == 384
+    assert fc1["block_n"] == 240 and fc1["pair"] == 1 and fc1["grid"] == 148 and fc1["threads"] == 384   # 3 rounds like 24 x 256, narrower
     proj = _plan(M=2048, N=1408, K=1408, out_f32=0x10000, res_f32=0x10000)
-    assert proj["block_n"] == 176 and proj["pair"] == 1 and proj["grid"] == 128     # 64 pair tiles >= 80 % of 74 pairs
+    assert proj["block_n"] == 160 and proj["pair"] == 1 and proj["grid"] == 144     # 72 pair tiles on 74 pairs, one round
+    assert proj["stages"] == 3                                                       # 128-wide K stages: 2 x (16 + 10) KiB each
+    assert _plan(M=16384, N=6144, K=1408)["block_n"] == 256                          # many rounds: the widest tile
     qkv = _plan(M=2048, N=4224, K=1408, store_mode=lib.STORE_QKV, q=0x10000, k=0x10000, vt=0x10000, heads=16, head_dim=88,
                 head_dim_pad=96, tokens=2048)
     assert qkv["block_n"] in (240, 256) and qkv["pair"] == 1                        # ragged wide tiles (2 rounds), not 22 x 192 (3 rounds)
