@@ -164,6 +164,21 @@ __shared__ int g_fine_n[2];
 #define FINE_FLUSH() do { } while (0)
 #endif
 
+// -DL4P_GEMM_GRID_PROF=1 (tools/gemm_grid_prof.py, experiment builds only): every CTA writes the global timer at kernel entry, after the
+// PDL wait and at its end to prof[1536 + 3 * blockIdx.x ...] (a 2048-entry prof buffer): launch skew, slowest CTA, boundary gaps.
+#ifdef L4P_GEMM_GRID_PROF
+#define GRID_STAMP(i)                                                                          \
+  do {                                                                                         \
+    if (p.prof != nullptr && threadIdx.x == 0) {                                               \
+      unsigned long long gt_;                                                                  \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_));                                  \
+      p.prof[1536 + 3 * blockIdx.x + (i)] = (long long)gt_;                                    \
+    }                                                                                          \
+  } while (0)
+#else
+#define GRID_STAMP(i) do { } while (0)
+#endif
+
 struct TileCoord {
   int m_blk, n_blk;
   int b, t0, h0, w0;  // conv mode
@@ -819,8 +834,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
+  GRID_STAMP(0);
   pdl_launch_dependents();  // single-wave persistent grid: the next kernel's CTAs may queue up behind ours right away
   pdl_wait();               // everything above overlapped the previous kernel's tail; from here on we touch its outputs
+  GRID_STAMP(1);
 
   if (warp == kWarpProducer) {
     // ------------------------------------------------------------------ TMA producer
@@ -1005,6 +1022,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   tc_fence_before();
   __syncthreads();
   FINE_FLUSH();
+  GRID_STAMP(2);
   if (warp == kWarpAlloc) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
@@ -1077,8 +1095,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   cluster_sync_all();  // barriers of both CTAs are initialised before any remote arrive / multicast / peer TMA signal
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
+  GRID_STAMP(0);
   pdl_launch_dependents();
   pdl_wait();
+  GRID_STAMP(1);
 
   if (warp == kWarpProducer) {
     // ------------------------------------------------------------------ TMA producer (both CTAs)
@@ -1311,6 +1331,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   tc_fence_before();
   cluster_sync_all();  // nobody exits (or frees TMEM) while the peer may still signal / read this CTA
   FINE_FLUSH();
+  GRID_STAMP(2);
   if (warp == kWarpAlloc) {
     tc_fence_after();
     tmem_dealloc2(tmem_base, 512);
