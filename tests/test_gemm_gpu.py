@@ -41,6 +41,31 @@ def test_linear_plain(dtype, M, N, K):
 
 
 @pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("M,N,K,pair,bn", [(4096, 384, 704, 1, 0),      # 2-CTA kernel, 11 k-blocks: odd tail stage (one valid slab)
+                                           (4096, 384, 448, 1, 128),    # 7 k-blocks, forced 128-wide tiles
+                                           (512, 64, 320, -1, 64),      # 1-CTA kernel, 5 k-blocks, three 128-wide stages
+                                           (640, 96, 1408, -1, 96),     # 1-CTA kernel, 22 k-blocks (even)
+                                           (2048, 1408, 6144, 0, 0),    # fc2 as shipped (9 x 160, one round of 72 pair tiles)
+                                           (300, 208, 256, 1, 0),       # ragged M, 4 k-blocks = two full stages
+                                           (2048, 1408, 264, 0, 0)])    # K % 64 != 0: 64-wide stages (plain 2-D boxes, zero-filled tail)
+def test_linear_k128_stages(dtype, M, N, K, pair, bn):
+    """Matrix mode with K % 64 == 0 runs ring stages of two k-blocks per operand (3-D TMA boxes, slab-major in shared memory);
+    odd k-block counts end on a half-filled stage whose second slab is skipped. Columns are scaled per k-block so that a wrong
+    slab pairing (A slab i against B slab j) cannot cancel out."""
+    ops = _ops()
+    a = _rand((M, K), dtype, 31)
+    w = _rand((N, K), dtype, 32, K ** -0.5)
+    scale = (1.0 + 0.25 * (torch.arange(K, device="cuda") // 64)).to(dtype)
+    a = a * scale
+    b = _rand((N,), torch.float32, 33)
+    out = torch.empty(M, N, device="cuda", dtype=torch.float32)
+    ops.linear(a, w, bias=b, out_f32=out, cta_pair=pair, block_n=bn)
+    torch.cuda.synchronize()
+    ref = a.float() @ w.float().t() + b
+    _close(out, ref, 2e-5)
+
+
+@pytest.mark.parametrize("dtype", DT)
 def test_linear_bias_gelu_16(dtype):
     ops = _ops()
     from l4p_b200 import lib
