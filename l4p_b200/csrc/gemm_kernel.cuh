@@ -576,12 +576,14 @@ L4P_DEVICE void epilogue_tile(const GemmKParams& p, const TileCoord& tc, const i
 
     mbar_wait(tfull_bar, tfull_phase);
     tc_fence_after();
+    EPI_STAMP();   // tuning builds: [acc ready | per chunk: tmem loaded, staged, staging read, stored]
 
     for (; c0 < p.block_n; c0 += kEpiChunk * kEpiGroups) {
       uint32_t raw[32];
       __syncwarp();  // tcgen05.ld is warp-collective; also orders the previous chunk's staging reads before new writes
       tmem_ld32(t_addr + (uint32_t)c0, raw);
       tmem_ld_wait();
+      EPI_STAMP();
       if (c0 >= ncols) continue;  // uniform across the CTA
       const int col0 = n0 + c0;
 
@@ -628,6 +630,7 @@ L4P_DEVICE void epilogue_tile(const GemmKParams& p, const TileCoord& tc, const i
         for (int u = 0; u < 8; ++u) sts128(wbase + ((((uint32_t)u) ^ sw) << 4), raw[4 * u], raw[4 * u + 1], raw[4 * u + 2], raw[4 * u + 3]);
       }
       __syncwarp();
+      EPI_STAMP();
 
       // the next chunk's residual is fetched row by row as soon as the current value has been consumed
       const int cn = c0 + kEpiChunk * kEpiGroups;
@@ -681,6 +684,7 @@ L4P_DEVICE void epilogue_tile(const GemmKParams& p, const TileCoord& tc, const i
         const uint32_t rl = (uint32_t)(it * 4 + rgrp);
         xs[it] = lds128(rbase + (uint32_t)it * 512u + ((((uint32_t)sub) ^ (rl & 7u)) << 4));
       }
+      EPI_STAMP();
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
         float4 x = xs[it];
@@ -706,6 +710,7 @@ L4P_DEVICE void epilogue_tile(const GemmKParams& p, const TileCoord& tc, const i
           }
         }
       }
+      EPI_STAMP();
     }
     // accumulator stage drained -> hand TMEM back to the MMA warp
     tc_fence_before();
