@@ -218,6 +218,28 @@ L4P_DEVICE uint2 ldg_res16x4(const uint16_t* p) {
   asm("ld.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
   return v;
 }
+// Predicated global accesses of the store-mode epilogue. As plain C++ inside `if (row / column valid)` every access became a branch
+// with its own reconvergence barrier and re-derived its address from the kernel parameters (~35 SASS instructions per 4-row
+// store, tools/epi_fine_prof.py); as predicated PTX there is no branch and the address is one IMAD.WIDE + LEA pair.
+L4P_DEVICE void stg_f32x4_if(float* p, const float4& v, const bool ok) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t@q st.global.v4.f32 [%0], {%1, %2, %3, %4};\n\t}"
+               ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"((int)ok));
+}
+L4P_DEVICE void stg_b32x2_if(uint16_t* p, const uint32_t lo, const uint32_t hi, const bool ok) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %3, 0;\n\t@q st.global.v2.b32 [%0], {%1, %2};\n\t}"
+               ::"l"(p), "r"(lo), "r"(hi), "r"((int)ok));
+}
+L4P_DEVICE float4 ldg_f32x4_if(const float* p, const bool ok) {   // zeros when !ok; not volatile (consumed one chunk later)
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t@q ld.global.v4.f32 {%0, %1, %2, %3}, [%4];\n\t}"
+      : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w) : "l"(p), "r"((int)ok));
+  return v;
+}
+L4P_DEVICE uint2 ldg_res16x4_if(const uint16_t* p, const bool ok) {   // +0.0 pairs when !ok
+  uint2 v = make_uint2(0u, 0u);
+  asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %3, 0;\n\t@q ld.global.v2.u32 {%0, %1}, [%2];\n\t}" : "+r"(v.x), "+r"(v.y) : "l"(p), "r"((int)ok));
+  return v;
+}
 template <bool BF16>
 L4P_DEVICE void add_res16(float4& a, const uint16_t* p) {
   const uint2 u = *reinterpret_cast<const uint2*>(p);
@@ -541,18 +563,20 @@ L4P_DEVICE void epilogue_tile(const GemmKParams& p, const TileCoord& tc, const i
     // instruction right behind every load and serialises the whole prefetch (measured: res_16 -> out_16 at M = 262144,
     // N = 1408, K = 704 took 2054 us against 794 us with an fp32 residual of twice the bytes).
     struct ResRaw { float4 f; uint2 h, h2; };
-    auto fetch_res = [&](const int c0, const int it) -> ResRaw {
+    auto fetch_res = [&](const int c0, const int it, const bool want = true) -> ResRaw {
       const int colg = c0 + sub * 4;
       ResRaw a;
       a.f = make_float4(0.f, 0.f, 0.f, 0.f);
       a.h = make_uint2(0u, 0u);   // +0.0 in both 16-bit formats
       a.h2 = make_uint2(0u, 0u);
-      if (colg < ncols && ((okm >> it) & 1u)) {
-        if (res32) a.f = *reinterpret_cast<const float4*>(res_f32 + ((long long)rrow[it] * ld_res + (n0 + colg)));
+      const bool ok = want && colg < ncols && ((okm >> it) & 1u);
+      if constexpr (STORE == L4P_STORE_ROWMAJOR) {
+        const long long cb = n0 + colg;   // one IMAD.WIDE per address: row * ld + column
+        if (res32) a.f = ldg_f32x4_if(res_f32 + ((long long)rrow[it] * ld_res + cb), ok);
         if (res16) {
-          const long long o = (long long)orow[it] * ld_res + (n0 + colg);
-          if (res_16 != nullptr) a.h = ldg_res16x4(res_16 + o);
-          if (res2_16 != nullptr) a.h2 = ldg_res16x4(res2_16 + o);
+          const long long o = (long long)orow[it] * ld_res + cb;
+          if (res_16 != nullptr) a.h = ldg_res16x4_if(res_16 + o, ok);
+          if (res2_16 != nullptr) a.h2 = ldg_res16x4_if(res2_16 + o, ok);
         }
       }
       return a;
@@ -696,18 +720,17 @@ L4P_DEVICE void epilogue_tile(const GemmKParams& p, const TileCoord& tc, const i
         }
         if (has_res) {
           add_res(x, rcur[it]);
-          if (more) rcur[it] = fetch_res(cn, it);
+          rcur[it] = fetch_res(cn, it, more);   // predicate, not a branch: no reconvergence region per row
         }
-        if (cok && ((okm >> it) & 1u)) {
-          if constexpr (STORE == L4P_STORE_ROWMAJOR) {
-            const long long o = (long long)orow[it] * ld_out + col;
-            if (out32) *reinterpret_cast<float4*>(out_f32 + o) = x;
-            if (out16) store4_16<BF16>(out_16 + o, x);
-            if (out16r)
-              store4_16<BF16>(out_16_relu + o, make_float4(fmaxf(x.x, 0.f), fmaxf(x.y, 0.f), fmaxf(x.z, 0.f), fmaxf(x.w, 0.f)));
-          } else {  // QKV head-major scatter / CONVT pixel shuffle
-            store4_16<BF16>(sbase + (long long)orow[it] * srow_ld, x);
-          }
+        if constexpr (STORE == L4P_STORE_ROWMAJOR) {
+          const bool ok = cok && ((okm >> it) & 1u);
+          const long long o = (long long)orow[it] * ld_out + col;
+          if (out32) stg_f32x4_if(out_f32 + o, x, ok);
+          if (out16) stg_b32x2_if(out_16 + o, pack2<BF16>(x.x, x.y), pack2<BF16>(x.z, x.w), ok);
+          if (out16r)
+            stg_b32x2_if(out_16_relu + o, pack2<BF16>(fmaxf(x.x, 0.f), fmaxf(x.y, 0.f)), pack2<BF16>(fmaxf(x.z, 0.f), fmaxf(x.w, 0.f)), ok);
+        } else {  // QKV head-major scatter / CONVT pixel shuffle
+          stg_b32x2_if(sbase + (long long)orow[it] * srow_ld, pack2<BF16>(x.x, x.y), pack2<BF16>(x.z, x.w), cok && ((okm >> it) & 1u));
         }
       }
       EPI_STAMP();
