@@ -70,7 +70,7 @@ static int make_tmap_k128(CUtensorMap* m, const void* base, uint64_t K, uint64_t
 // N-tile width from a measured cost model (tools/pair_n_sweep.py, tools/blockn_sweep2.py). With the operands issued by two warps and
 // 128-wide K stages the 2-CTA kernel is tensor-bound down to 96-column tiles: one k-block of a 256 x bn pair tile costs ~2 bn cycles,
 // a tile a fixed ~2300 cycles more (pipeline drain, epilogue hand-over), and the kernel needs ceil(tiles / CTA pairs) rounds of tiles.
-// The 1-CTA kernel (128-row tiles) is L2 -> SM bound: ~480 + 0.4 bn cycles per k-block whatever the width, so it wants the fewest,
+// The 1-CTA kernel (128-row tiles) still measures ~480 + 0.4 bn cycles per k-block whatever the width, so it wants the fewest,
 // widest tiles. A ragged last N tile (TMA zero fill + column masking) is fine. Examples at M = 2048: N = 1408 -> 9 x 160 (72 pair
 // tiles on 74 pairs, one round; 8 x 176 costs 10 % more per k-block), N = 6144 -> 26 x 240 (3 rounds like 24 x 256, 6 % cheaper),
 // N = 4224 -> 17 x 256 (2 rounds; 22 x 192 needs 3).
@@ -395,8 +395,9 @@ extern "C" int l4p_gemm(const l4p_gemm_desc* d, void* stream_) {
     rc = t_plan ? L4P_OK : host_make_tmap_16b(&tmB, d->w, 2, dims, strides, box, 128);
     if (rc != L4P_OK) return rc;
     // Line-halo stages (gemm_kernel.cuh, gemm2_kernel producer): the three in-plane row taps share one A box with bH + 2
-    // lines. A 256 x 128 pair tile otherwise needs 16 + 8 KiB per CTA and k-block = 96 B/clk through the 64 B/clk L2 -> SM
-    // port (measured 927 -> 1519 TFLOP/s on the 224^2 head convolution); 256 x 256 tiles sit exactly at 64 B/clk.
+    // lines: one ring iteration (1 + 3 TMA loads, one wait / expect_tx / commit) per THREE k-blocks and a third of the activation
+    // traffic. Measured 927 -> 1519 TFLOP/s on the 224^2 head convolution; the plain stages were capped by the producer thread's
+    // ~490 cycles per k-block (then read as a 64 B/clk L2 -> SM port limit).
     // L4P_CONV_HALO=0 restores one box per tap (tuning / A-B).
     static int halo_env = -1;
     if (halo_env < 0) {

@@ -1059,8 +1059,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
 // ------------------------------------------------------------------------------------------------------------------
 // 2-CTA variant: a CTA pair (cluster of 2, same TPC) owns a 256-row x block_n tile. Each CTA stages its own 128 rows
-// of A and HALF of the B tile per k-block (32 KiB instead of 48 KiB per 128 output rows: 128-row tiles are
-// L2->SM-bandwidth-bound), the leader issues tcgen05.mma.cta_group::2 (M=256) which reads both CTAs' shared memory and
+// of A and HALF of the B tile per k-block (32 KiB instead of 48 KiB per 128 output rows: half the L2 -> SM traffic of the
+// B operand), the leader issues tcgen05.mma.cta_group::2 (M=256) which reads both CTAs' shared memory and
 // writes each CTA's half of the accumulator into that CTA's own TMEM; both epilogues run independently.
 //   full[s]    lives in the leader: 1 arrival (leader's expect_tx of BOTH CTAs' bytes) + the bytes of all four TMA loads
 //   empty[s]   one per CTA, released by a multicast tcgen05.commit
@@ -1140,8 +1140,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (p.a_halo) {
           // Line-halo stages: A = the tile's voxel box grown by one line above and below (bH + 2 lines, shifted by dw in W and dt
           // in T), B = the weights of the three taps (dt, -1..1, dw) of one 64-channel block. The three dh taps read the SAME
-          // A box at line offsets 0 / 1 / 2, so every activation byte crosses the 64 B/clk L2 -> SM port once per dw shift
-          // instead of once per tap (9 instead of 27 times): 24 + 3 x 8 KiB per 768 cycles of UMMA instead of 3 x (16 + 8).
+          // A box at line offsets 0 / 1 / 2, so every activation byte crosses the L2 -> SM port once per dw shift instead of
+          // once per tap (9 instead of 27 times: 24 + 3 x 8 KiB per 768 cycles of UMMA instead of 3 x (16 + 8)), and this
+          // thread runs one ring iteration per three k-blocks (the B warp issues the three weight tiles).
           for (int dti = 0; dti < p.kT; ++dti)
             for (int dwi = 0; dwi < 3; ++dwi)
               for (int cb = 0; cb < p.cblocks; ++cb) {
