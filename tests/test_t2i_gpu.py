@@ -29,7 +29,8 @@ def _close(got, ref, tol):
 
 
 @pytest.mark.parametrize("dtype", DT)
-@pytest.mark.parametrize("G,J,n,K", [(3, 48, 2048, 1408), (5, 48, 256, 704), (2, 16, 128, 192), (130, 48, 64, 64)])
+@pytest.mark.parametrize("G,J,n,K", [(3, 48, 2048, 1408), (5, 48, 256, 704), (2, 16, 128, 192), (130, 48, 64, 64),
+                                     (6, 48, 64, 704), (4, 128, 96, 1408)])   # narrow tiles: 128-wide K stages with grouped weights
 def test_grouped_linear(dtype, G, J, n, K):
     """l4p_gemm with grouped weights: rows [g*J, (g+1)*J) of A against W rows [g*n, (g+1)*n); in-place fp32 residual; tiles
     J rows apart (J < 128: the rows a tile reads beyond its group are never stored)."""
