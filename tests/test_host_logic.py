@@ -161,6 +161,30 @@ def test_gemm_plan_tile_selection():
     assert lib.load().l4p_gemm_plan(C.byref(d), (C.c_int * 6)()) != 0
 
 
+def test_gemm_plan_k128_stages():
+    """128-wide K stages (two k-blocks per operand and ring stage) are planned for matrix-mode problems with K % 64 == 0 when three
+    such stages fit; K % 64 != 0, short K, convolutions and L4P_GEMM_K128=0 keep 64-wide stages (more, smaller stages)."""
+    import subprocess
+    import sys
+    fc2 = _plan(M=2048, N=1408, K=6144, out_f32=0x10000, res_f32=0x10000)
+    assert fc2["block_n"] == 160 and fc2["pair"] == 1 and fc2["stages"] == 3           # 2 x (16 + 10) KiB per stage
+    fc1 = _plan(M=16384, N=6144, K=1408)
+    assert fc1["block_n"] == 256 and fc1["stages"] == 5                                 # 256-wide pair tiles: 64-wide stages of 32 KiB
+    ragged_k = _plan(M=2048, N=1408, K=264, out_f32=0x10000, res_f32=0x10000)
+    assert ragged_k["stages"] >= 5                                                       # K % 64 != 0: plain 2-D boxes
+    narrow = _plan(M=768, N=1408, K=1408)                                                # narrow-tile rule: one wave of 64-wide tiles
+    assert narrow["block_n"] <= 96 and narrow["split_k"] == 1 and 3 <= narrow["stages"] <= 8
+    code = ("import ctypes as C; from l4p_b200 import lib; d = lib.GemmDesc(); d.a = d.w = d.out_f32 = d.res_f32 = 0x10000;"
+            "d.M, d.N, d.K, d.lda, d.ldw, d.ld_out, d.ld_res = 2048, 1408, 6144, 6144, 6144, 1408, 1408;"
+            "d.a_mode, d.store_mode = lib.A_MATRIX, lib.STORE_ROWMAJOR; o = (C.c_int * 6)();"
+            "assert lib.load().l4p_gemm_plan(C.byref(d), o) == 0; print(o[3])")
+    import os
+    env = dict(os.environ, L4P_GEMM_K128="0")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, cwd=os.path.dirname(os.path.dirname(__file__)))
+    assert out.returncode == 0, out.stderr
+    assert int(out.stdout.strip()) >= 6                                                  # 64-wide stages of 26 KiB
+
+
 def test_prepare_model_mirrors_reference_loader(tmp_path):
     """l4p/models/utils.py:15-60: yaml -> max_queries override -> strict state_dict load -> eval; precision selects the
     16-bit operand type; CPU / fp32 requests raise instead of falling back."""
